@@ -133,7 +133,7 @@ def qpsk_map(bits2):
     (0,0)->(1+1j), (1,0)->(1-1j), (1,1)->(-1-1j), (0,1)->(-1+1j), all /sqrt(2).
     bits2[..., 2] -> complex128[...]
     """
-    b = np.asarray(bits2)
+    b = np.asarray(bits2).astype(np.int64)          # uint8 input would wrap in 1-2*b
     # the reference stores the table entries as (x+yj)/np.sqrt(2): reproduce that division
     return ((1 - 2 * b[..., 1]) + 1j * (1 - 2 * b[..., 0])) / np.sqrt(2)
 
