@@ -1,0 +1,394 @@
+"""Drop-in replacement for the reference's OFDM.py (adamg-97/GF3-audio-modem).
+
+Same classes, methods, argument meaning, prints and error behaviour as the reference module, so
+`from OFDM import *` in the notebooks keeps working (Final System Test.ipynb:9) -- but the
+physical-layer arithmetic (transmit chain, chirp synchronisation, receive chain) runs in
+hand-written sm_100a CUDA kernels (libgf3b200.so) through gf3b200.Phy.  numpy arrays in, bits or
+waveforms out.  No CPU fallback: without a CUDA device the compute methods raise gf3b200.Gf3Error.
+
+Host-side pieces kept in numpy are index / RNG bookkeeping only: bit padding and XOR coding
+(np.random draw order must match the reference, OFDM.py:172,203), reshapes, slicing, file framing.
+"""
+import os
+import sys
+
+import numpy as np
+import scipy  # noqa: F401  (re-exported like the reference, OFDM.py:3)
+from scipy.io import wavfile  # noqa: F401
+from scipy.signal import chirp, convolve, lfilter  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+if _HERE not in sys.path:
+    sys.path.insert(0, _HERE)
+import gf3b200  # noqa: E402
+from gf3b200 import Phy  # noqa: E402
+
+
+class _Missing:
+    """Stand-in for an optional module of the reference (matplotlib, sounddevice, IPython, pyldpc)
+    that is not installed: attribute access raises with a clear message."""
+
+    def __init__(self, name):
+        object.__setattr__(self, "_name", name)
+
+    def __getattr__(self, item):
+        raise ImportError("optional dependency '%s' is not installed (needed for %s.%s)" % (self._name, self._name, item))
+
+    def __setattr__(self, k, v):
+        pass
+
+
+def _optional(name, attr=None):
+    try:
+        mod = __import__(name, fromlist=["_"])
+        return getattr(mod, attr) if attr else mod
+    except Exception:
+        return _Missing(name)
+
+
+plt = _optional("matplotlib.pyplot")          # OFDM.py:4
+sd = _optional("sounddevice")                 # OFDM.py:7
+try:
+    sd.default.channels = 1                   # OFDM.py:8
+except Exception:
+    pass
+Audio = _optional("IPython.display", "Audio")  # OFDM.py:9
+pyldpc = _optional("pyldpc")                  # OFDM.py:10
+
+
+def _find_ci(path):
+    """Resolve a relative path case-insensitively (the reference opens handouts/, input_files/
+    but the repository has Handouts/, input_Files/: OFDM.py:99,757)."""
+    if os.path.exists(path):
+        return path
+    cur = "." if not os.path.isabs(path) else os.sep
+    for part in [p for p in path.split(os.sep) if p]:
+        try:
+            entries = os.listdir(cur)
+        except OSError:
+            return path
+        match = [e for e in entries if e.lower() == part.lower()]
+        if not match:
+            return path
+        cur = os.path.join(cur, match[0])
+    return cur
+
+
+#########################################
+#                 CamG                  #
+#########################################
+
+class CamG:
+    """Parameter object (OFDM.py:17-115).  Extra keyword arguments (not in the reference) reach
+    the parameter space its notebooks used through older revisions: any power-of-two symbol size,
+    any CP, any data-bin range."""
+
+    def __init__(self, mode, encoding="None", no_pilots=20, packet_length=180, *,
+                 ofdm_symbol_size=None, cp_length=None, lowest_bin=None, highest_bin=None):
+        self.encoding = encoding
+        self.fs = 48000
+        self.ofdm_symbol_size = 4096 if ofdm_symbol_size is None else int(ofdm_symbol_size)
+        self.K = self.ofdm_symbol_size // 2 - 1
+        K = 2047
+        modes = {
+            "A1": (224, (1, K)), "A2": (224, (100, 1500)), "A3": (224, (100, 1000)),
+            "B1": (704, (1, K)), "B2": (704, (100, 1500)), "B3": (704, (100, 1000)),
+            "C1": (1184, (1, K)), "C2": (1184, (100, 1500)), "C3": (1184, (100, 1000)),
+        }
+        self.cp_length = modes[mode][0] if cp_length is None else int(cp_length)
+        self.lowest_bin = modes[mode][1][0] if lowest_bin is None else int(lowest_bin)
+        self.highest_bin = modes[mode][1][1] if highest_bin is None else int(highest_bin)
+        self.packet_length = packet_length
+        self.no_pilots = no_pilots
+        self.sync_method = "chirp"
+        self.L = self.K + 1
+        self.f0 = 0
+        self.f1 = 8000
+        self.modulation = "QPSK"
+        if self.modulation == "QPSK":
+            self.mapping_table = {
+                (0, 0): (1 + 1j) / np.sqrt(2), (1, 0): (1 - 1j) / np.sqrt(2),
+                (1, 1): (-1 - 1j) / np.sqrt(2), (0, 1): (-1 + 1j) / np.sqrt(2),
+            }
+            self.mu = 2
+        else:
+            raise ValueError("Invalid Modulation Type")
+        self._derive()
+        # known sequence: handouts/random_bits.txt if the caller's tree has it, else the packaged copy
+        path = _find_ci(os.path.join("handouts", "random_bits.txt"))
+        if os.path.exists(path):
+            with open(path, "rb") as f:
+                raw = np.frombuffer(f.read(4096), dtype=np.uint8)
+            self.known_sequence = (raw - ord("0")).astype(np.int64)
+        else:
+            self.known_sequence = gf3b200.default_known_sequence()
+        self._phy = None
+        self._phy_key = None
+
+    def _derive(self):
+        """Derived attributes of OFDM.py:46-49,64,94-95 (recomputed when the base ones change)."""
+        self.carriers = np.arange(1, self.K + 1)
+        self.data_carriers = np.arange(self.lowest_bin, self.highest_bin)
+        self.data_carriers_per_symbol = len(self.data_carriers)
+        self.unused_carriers = np.delete(self.carriers, (self.data_carriers - 1))
+        self.chirp_length = 5 * (self.ofdm_symbol_size + self.cp_length)
+        self.data_bits_per_symbol = self.data_carriers_per_symbol * self.mu
+        self.bits_per_symbol = self.K * self.mu
+
+    @property
+    def phy(self):
+        """The device plan for the CURRENT attribute values (rebuilt if they were patched)."""
+        key = (self.ofdm_symbol_size, self.cp_length, self.lowest_bin, self.highest_bin, self.no_pilots,
+               self.packet_length, self.chirp_length, self.f0, self.f1, self.fs)
+        if self._phy is None or key != self._phy_key:
+            self._phy = Phy(N=self.ofdm_symbol_size, cp=self.cp_length, lo=self.lowest_bin, hi=self.highest_bin,
+                            n_pilots=self.no_pilots, packet_len=self.packet_length,
+                            known_sequence=self.known_sequence, chirp_len=self.chirp_length,
+                            fs=float(self.fs), f0=float(self.f0), f1=float(self.f1))
+            self._phy_key = key
+        return self._phy
+
+    def sync_chirp(self):
+        """OFDM.py:106-109 (device kernel, float64 out)."""
+        return self.phy.sync_chirp().cpu().numpy().astype(np.float64)
+
+    def __repr__(self):
+        return ("Number of actual Sub Carriers:      {:.0f} \nCyclic prefix length:               {:.0f} \n"
+                "Modulation method:                  {} \nSync Method:                        {} \n"
+                "Packet Length:                      {}").format(self.K, self.cp_length, self.modulation,
+                                                                 self.sync_method, self.packet_length)
+
+
+#########################################
+#              Transmitter              #
+#########################################
+
+class transmitter(CamG):
+
+    def encode(self, bits):
+        """OFDM.py:128-187.  Host side: the RNG draw (np.random.binomial) must stay in the
+        reference's order so seeded runs see identical padding."""
+        if self.encoding == "LDPC":
+            raise NotImplementedError('encoding "LDPC" is marked broken in the reference (OFDM.py:21) and is out of scope')
+        bits = np.asarray(bits)
+        if self.encoding == "XOR":
+            dbs = self.data_bits_per_symbol
+            known_bits = np.tile(self.known_sequence[:dbs], int(np.ceil(len(bits) / dbs)))[:len(bits)]
+            bits = np.bitwise_xor(bits, known_bits)
+        bits_per_packet = self.data_bits_per_symbol * self.packet_length
+        padding_length = (bits_per_packet - len(bits) % bits_per_packet) % bits_per_packet
+        padding = np.random.binomial(n=1, p=0.5, size=(padding_length,))
+        return np.hstack([bits, padding])
+
+    def SP(self, bits):
+        return bits.reshape(-1, self.data_carriers_per_symbol, self.mu)
+
+    def map(self, bits):
+        """OFDM.py:196-197 as a table lookup (formatting only; transmit() maps on the device)."""
+        return gf3b200.qpsk_points(bits)
+
+    def random_qpsk(self):
+        qpsk = np.array([1 + 1j, 1 - 1j, -1 + 1j, -1 - 1j]) / np.sqrt(2)
+        return np.random.choice(qpsk, size=(self.K - self.data_carriers_per_symbol), replace=True)
+
+    def build_OFDM_symbol(self, payload):
+        symbols = np.zeros([payload.shape[0], self.ofdm_symbol_size], dtype=complex)
+        rand_qpsk = self.random_qpsk()
+        symbols[:, self.data_carriers] = payload
+        symbols[:, self.unused_carriers] = rand_qpsk
+        symbols[:, -self.data_carriers] = np.conj(payload)
+        symbols[:, -self.unused_carriers] = np.conj(rand_qpsk)
+        return symbols
+
+    def add_cp(self, time_data):
+        if self.cp_length == 0:
+            return time_data
+        return np.hstack([time_data[:, -self.cp_length:], time_data])
+
+    def _modulate(self, bits_encoded, filler):
+        """Fused device transmit chain: encoded bits -> framed waveform (float64 numpy)."""
+        import torch
+        phy = self.phy
+        bpp = phy.bits_per_packet
+        if len(bits_encoded) % bpp:
+            raise ValueError("cannot reshape array of size %d into packets of %d bits" % (len(bits_encoded), bpp))
+        n_packets = len(bits_encoded) // bpp
+        self.no_packets = n_packets
+        packed = np.zeros((n_packets, phy.bits_stride), dtype=np.uint8)
+        pk = np.packbits(np.asarray(bits_encoded, dtype=np.uint8).reshape(n_packets, bpp), axis=1)
+        packed[:, : pk.shape[1]] = pk
+        d_bits = torch.from_numpy(packed).to(phy.device).reshape(1, n_packets, phy.bits_stride)
+        d_fill = torch.from_numpy(np.asarray(filler).astype(np.complex64)).to(phy.device).reshape(1, -1) if phy.K > phy.Nd else None
+        out = phy.tx_modulate(d_bits, d_fill, 1, n_packets)
+        return out[0].cpu().numpy().astype(np.float64)
+
+    def transmit(self, bits, graph_output=False):
+        """OFDM.py:296-343."""
+        print("-" * 42 + "\nTRANSMIT\n" + "-" * 42)
+        print("OFDM Paramters:")
+        print(self)
+        bits_encoded = self.encode(bits)
+        filler = self.random_qpsk()                     # same draw order as build_OFDM_symbol (OFDM.py:210)
+        n_symbols = len(bits_encoded) // self.data_bits_per_symbol
+        print("Number of bits to transmit:         " + str(len(bits)))
+        print("Number of OFDM symbols to transmit: " + str(n_symbols))
+        signal = self._modulate(bits_encoded, filler)
+        print("Number of packets to transmit:      " + str(self.no_packets))
+        if graph_output:
+            time = np.linspace(0, len(signal) / self.fs, len(signal))
+            plt.plot(time, 5 * signal, label="Signal")
+            plt.title("OFDM Frame")
+            plt.xlabel("time")
+            plt.legend()
+            plt.savefig("OFDM Frame")
+            plt.show()
+        return signal
+
+
+#########################################
+#               Receiver                #
+#########################################
+
+class receiver(transmitter):
+
+    def _sync(self, r):
+        """Device matched filter + peak picking; returns (peak indices into `zeros`, len(zeros))."""
+        import torch
+        phy = self.phy
+        r = np.ascontiguousarray(np.asarray(r, dtype=np.float32)).reshape(1, -1)
+        T = r.shape[1]
+        d_r = torch.from_numpy(r).to(phy.device)
+        P, pmax = phy.xcorr(d_r)
+        max_peaks = max(4, T // max(1, phy.chirp_len) + 2)
+        peaks, count = phy.peak_pick(P, pmax, T, max_peaks)
+        n = int(count[0].item())
+        return peaks[0, :n].cpu().numpy(), T + phy.chirp_len - 3, d_r
+
+    def chirp_method(self, r):
+        """OFDM.py:356-372: boolean `zeros` array with the surviving detections."""
+        peaks, nz, _ = self._sync(r)
+        zeros = np.zeros(nz, dtype=bool)
+        zeros[peaks] = True
+        return zeros
+
+    def get_symbols(self, r, zeros):
+        """OFDM.py:391-403 (index bookkeeping on the host)."""
+        zero_indicies = np.where(zeros == True)[0] + 2   # noqa: E712
+        zero_indicies = zero_indicies[:-1]
+        self.no_packets = len(zero_indicies)
+        n = (2 * self.no_pilots + self.packet_length) * (self.cp_length + self.ofdm_symbol_size)
+        rx = np.vstack([[r[i:i + n]] for i in zero_indicies])
+        return rx.reshape(-1, 2 * self.no_pilots + self.packet_length, self.cp_length + self.ofdm_symbol_size)
+
+    def remove_cp(self, rx):
+        return rx[:, :, self.cp_length:]
+
+    def get_data(self, OFDM_symbols):
+        start_pilots = OFDM_symbols[:, :self.no_pilots, self.carriers]
+        end_pilots = OFDM_symbols[:, -self.no_pilots:, self.carriers]
+        data_symbols = OFDM_symbols[:, self.no_pilots:-self.no_pilots, self.carriers]
+        return data_symbols, start_pilots, end_pilots
+
+    def PS(self, bits):
+        return bits.reshape((-1,))
+
+    def decode(self, bits_encoded):
+        """OFDM.py:509-549 (receive() applies the XOR inside the demod kernel instead)."""
+        if self.encoding == "LDPC":
+            raise NotImplementedError('encoding "LDPC" is marked broken in the reference (OFDM.py:21) and is out of scope')
+        if self.encoding == "XOR":
+            dbs = self.data_bits_per_symbol
+            known_bits = np.tile(self.known_sequence[:dbs], int(np.ceil(len(bits_encoded) / dbs)))[:len(bits_encoded)]
+            return np.bitwise_xor(bits_encoded, known_bits)
+        return bits_encoded
+
+    def receive_packets(self, rx_cp, want_eq=False):
+        """Device receive chain on already-sliced packets rx_cp[pk, 2P+L, N+cp] (what get_symbols
+        returns): returns dict(bits, Hs, He, slope[, eq]).  Rows 8-12 of SURVEY 8a in two launches."""
+        import torch
+        phy = self.phy
+        rx_cp = np.ascontiguousarray(np.asarray(rx_cp, dtype=np.float32))
+        n_packets = rx_cp.shape[0]
+        self.no_packets = n_packets
+        d = torch.from_numpy(rx_cp.reshape(-1)).to(phy.device)
+        return self._demod_device(d, n_packets, None, want_eq)
+
+    def _demod_device(self, d_samples, n_packets, d_off, want_eq):
+        phy = self.phy
+        Hs, He, slope = phy.rx_estimate(d_samples, n_packets, d_off)
+        res = phy.rx_demod(d_samples, n_packets, Hs, He, slope, d_off, xor=(self.encoding == "XOR"), want_eq=want_eq)
+        bits_packed, eq = res if want_eq else (res, None)
+        out = dict(bits=phy.unpack_bits(bits_packed), Hs=Hs.cpu().numpy().astype(np.complex128),
+                   He=He.cpu().numpy().astype(np.complex128), slope=slope.cpu().numpy())
+        if want_eq:
+            out["eq"] = eq.cpu().numpy().reshape(-1, phy.K)
+        return out
+
+    def receive(self, signal, graph_output=False, _details=None):
+        """OFDM.py:581-657: sync -> slice -> FFT -> equalise -> demap -> decode, on the device."""
+        import torch
+        print("-" * 42 + "\nReceive \n" + "-" * 42)
+        print("OFDM Paramters:")
+        print(self)
+        if self.encoding == "LDPC":
+            raise NotImplementedError('encoding "LDPC" is out of scope (broken in the reference, OFDM.py:21)')
+        phy = self.phy
+        peaks, nz, d_r = self._sync(signal)
+        starts = (peaks + 2)[:-1]                                  # OFDM.py:393-395
+        self.no_packets = len(starts)
+        if self.no_packets == 0:
+            raise ValueError("need at least one array to concatenate")            # np.vstack([]) in OFDM.py:400
+        T = d_r.shape[1]
+        if starts[-1] + phy.pkt_samples > T:                       # ragged slices -> vstack/reshape error in the reference
+            raise ValueError("all the input array dimensions except for the concatenation axis must match exactly "
+                             "(signal ends inside the last packet)")
+        d_off = torch.from_numpy(starts.astype(np.int64)).to(phy.device)
+        print("Number of received OFDM symbols:    " + str(self.no_packets * self.packet_length))
+        out = self._demod_device(d_r.reshape(-1), self.no_packets, d_off, want_eq=_details is not None)
+        bits = out["bits"]
+        print("Number of received bits:            " + str(len(bits)))
+        if _details is not None:
+            _details.update(out, peaks=peaks, starts=starts)
+        return bits, out["Hs"][0], out["He"][0]
+
+
+def play_record(signal, fs, padding_before=1, padding_after=1):
+    """OFDM.py:681-689 (needs the optional sounddevice module)."""
+    data_padded = np.pad(signal, (int(padding_before * fs), int(padding_after * fs)), 'constant', constant_values=0)
+    print("Recording...")
+    signal = sd.playrec(data_padded, fs)
+    sd.wait()
+    print("Finished recording")
+    return signal[:, 0]
+
+
+class channel(receiver):
+    """OFDM.py:694-752 is dead code in the reference (calls a nonexistent self.pad); kept as a name."""
+
+    def measure_channel(self, bits):
+        raise NotImplementedError("channel.measure_channel is dead code in the reference (OFDM.py:707 calls self.pad)")
+
+
+def load_file(file_name):
+    """OFDM.py:756-761."""
+    data_bytes = np.fromfile(_find_ci(os.path.join("input_files", file_name)), dtype=np.uint8)
+    file_info = file_name + "\x00" + str(len(data_bytes)) + "\x00"
+    b = bytearray()
+    b.extend(map(ord, file_info))
+    return np.unpackbits(np.hstack([b, data_bytes]))
+
+
+def save_file(rx_bits):
+    """OFDM.py:766-794."""
+    data = np.packbits(rx_bits)
+    z1 = int(np.flatnonzero(data == 0)[0])
+    file_name = "".join(chr(c) for c in data[:z1])
+    data = data[z1 + 1:]
+    z2 = int(np.flatnonzero(data == 0)[0])
+    file_size = "".join(chr(c) for c in data[:z2])
+    data = data[z2 + 1:]
+    print("File Name: " + file_name + "\nFile Size: " + file_size + " bytes")
+    data = data[:int(file_size)]
+    out_dir = _find_ci("output_files")
+    data.tofile(os.path.join(out_dir, file_name[:-4] + "_received" + file_name[-4:]))
+    return file_name, data

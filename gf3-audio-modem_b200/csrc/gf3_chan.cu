@@ -1,0 +1,134 @@
+// gf3_chan.cu -- synthetic-channel and bit-error kernels for the batched sweeps.
+//
+//   channel_sim_kernel : y = lfilter(taps, 1, x) + sigma * N(0,1)   (per-stream FIR, Philox noise)
+//   ber_count_kernel   : popcount(a ^ b) -> u64 counters (all-reduced over NCCL by the host)
+#include "gf3_common.cuh"
+
+namespace gf3 {
+
+// Philox-4x32-10 (Salmon et al. 2011), counter-based: reproducible for any grid shape.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+    const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;    // (0, 1]
+    const float u2 = (float)b * 2.3283064365386963e-10f;             // [0, 1)
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    return make_float2(rad * c, rad * s);
+}
+
+constexpr int kMaxTaps = 64;
+
+struct ChanArgs {
+    const float* x;
+    const float* taps;
+    const float* sigma;
+    float* y;
+    int64_t x_stride, y_stride, T;
+    uint64_t seed;
+    int n_taps;
+};
+
+// grid.y = stream; each thread produces 4 consecutive samples.
+__global__ void __launch_bounds__(256) channel_sim_kernel(const ChanArgs a) {
+    __shared__ float h[kMaxTaps];
+    const int64_t stream = blockIdx.y;
+    if (threadIdx.x < a.n_taps) h[threadIdx.x] = a.taps[stream * a.n_taps + threadIdx.x];
+    __syncthreads();
+    const float* x = a.x + stream * a.x_stride;
+    float* y = a.y + stream * a.y_stride;
+    const float sg = a.sigma ? a.sigma[stream] : 0.f;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < a.T; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n0 = q * 4;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        // window x[n0 - n_taps + 1 .. n0 + 3]
+        for (int k = 0; k < a.n_taps; ++k) {
+            const float hk = h[k];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = n0 + e - k;
+                if (i >= 0 && i < a.T) acc[e] = fmaf(hk, x[i], acc[e]);
+            }
+        }
+        if (sg != 0.f) {
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)),
+                                            make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+            const float2 g0 = box_muller(rnd.x, rnd.y), g1 = box_muller(rnd.z, rnd.w);
+            acc[0] = fmaf(sg, g0.x, acc[0]); acc[1] = fmaf(sg, g0.y, acc[1]);
+            acc[2] = fmaf(sg, g1.x, acc[2]); acc[3] = fmaf(sg, g1.y, acc[3]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (n0 + e < a.T) y[n0 + e] = acc[e];
+    }
+}
+
+__global__ void __launch_bounds__(256) ber_count_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                       int64_t nbits, unsigned long long* counter) {
+    const int64_t nbytes = nbits >> 3;
+    unsigned long long errs = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (int64_t)gridDim.x * blockDim.x)
+        errs += __popc((unsigned)(a[i] ^ b[i]));
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (nbits & 7)) {
+        const unsigned mask = (0xFF00u >> (nbits & 7)) & 0xFFu;       // leading (MSB-first) bits of the last byte
+        errs += __popc((unsigned)((a[nbytes] ^ b[nbytes]) & mask));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) errs += __shfl_xor_sync(0xffffffffu, errs, o);
+    __shared__ unsigned long long wsum[8];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = errs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        if (t) atomicAdd(counter, t);
+        if (blockIdx.x == 0) atomicAdd(counter + 1, (unsigned long long)nbits);
+    }
+}
+
+}  // namespace gf3
+
+using namespace gf3;
+
+extern "C" int gf3_channel_sim(const float* x, int64_t x_stride, int64_t n_streams, int64_t T,
+                               const float* taps, int32_t n_taps, const float* sigma, uint64_t seed,
+                               float* y, int64_t y_stride, void* stream) {
+    GF3_REQUIRE(x && taps && y, "channel_sim: null argument");
+    GF3_REQUIRE(n_taps >= 1 && n_taps <= kMaxTaps, "channel_sim: n_taps must be in 1..%d", kMaxTaps);
+    GF3_REQUIRE(n_streams >= 0 && n_streams <= 65535 && T >= 0, "channel_sim: bad sizes (n_streams <= 65535)");
+    GF3_REQUIRE(x != y, "channel_sim: in-place operation is not supported");
+    if (n_streams == 0 || T == 0) return GF3_OK;
+    ChanArgs a;
+    a.x = x; a.taps = taps; a.sigma = sigma; a.y = y; a.x_stride = x_stride; a.y_stride = y_stride; a.T = T;
+    a.seed = seed; a.n_taps = n_taps;
+    int64_t gx = (T / 4 + 255) / 256;
+    if (gx > 4096) gx = 4096;
+    if (gx < 1) gx = 1;
+    channel_sim_kernel<<<dim3((unsigned)gx, (unsigned)n_streams), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}
+
+extern "C" int gf3_ber_count(const uint8_t* a, const uint8_t* b, int64_t nbits, uint64_t* counter, void* stream) {
+    GF3_REQUIRE(a && b && counter, "ber_count: null argument");
+    GF3_REQUIRE(nbits >= 0, "ber_count: negative bit count");
+    if (nbits == 0) return GF3_OK;
+    int64_t blocks = ((nbits >> 3) + 256 * 16 - 1) / (256 * 16);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    ber_count_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, nbits, reinterpret_cast<unsigned long long*>(counter));
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}

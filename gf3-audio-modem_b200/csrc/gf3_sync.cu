@@ -1,0 +1,372 @@
+// gf3_sync.cu -- chirp synchronisation (OFDM.py:356-372, 393-395).
+//
+// The reference convolves the whole recording with the time-reversed chirp through one big FFT
+// (scipy.signal.convolve, OFDM.py:358), normalises by the global max and walks the result in a
+// Python loop.  Here the matched filter is a uniformly-partitioned overlap-save convolution on
+// 4096-point real FFT blocks (hop B = 2048) built from the same register-resident FFT engine
+// as the receiver:
+//   xcorr_fwd_kernel : spectrum of every 50 %-overlapped input block           (4 B read, 8 B written / sample)
+//   xcorr_acc_kernel : Y_b = sum_p X_{b-p} H_p, inverse real FFT, last B samples, signed row max
+//   peak_pick_kernel : candidate mask + ascending hold-off scan, one CTA per stream
+#include <vector>
+
+#include "gf3_common.cuh"
+#include "gf3_fft.cuh"
+
+namespace gf3 {
+
+using SP = FftPlan<12>;                   // 4096 real samples per block
+constexpr int kB = SP::M;                 // hop = partition length = 2048
+constexpr int kSyncThreads = 256;
+
+int upload_twiddles(int logN, float2** d_out);   // gf3_lib.cu
+int make_chirp(gf3_plan* plan);                  // gf3_tx.cu
+
+// Spectrum layout per block: M complex values; element 0 packs (X[0], X[M]) (both real).
+
+struct FwdArgs {
+    const float* r;          // [n_streams, r_stride]
+    float2* spec;            // [n_streams, nblk, M]
+    const float2* tw;
+    float* pmax;             // [n_streams] reset to -inf here (may be null)
+    int64_t r_stride, T, n_streams;
+    int nblk;                // blocks per stream
+    int reverse;             // 1: input is read time-reversed (building the filter spectrum)
+    int in_off;              // block b covers input samples [b*B - B + in_off, +2B)
+    int valid_len;           // only the first valid_len samples of a block are taken (rest zero)
+};
+
+// block b of a stream = samples [b*B - B, b*B + B), zero outside [0, T)
+__global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArgs a) {
+    using P = SP;
+    constexpr int NT = kSyncThreads, T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP, SF = NT / T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* zbuf = reinterpret_cast<float2*>(smem_raw);
+    float2* tw = zbuf + SF * MP;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
+    const int g = tid / T, t = tid % T;
+    const int64_t blk_global = (int64_t)blockIdx.x * SF + g;
+    const int64_t stream = blk_global / a.nblk;
+    const int b = (int)(blk_global % a.nblk);
+    const bool live = stream < a.n_streams;
+    if (live && b == 0 && t == 0 && a.pmax) a.pmax[stream] = __int_as_float(0xff800000);
+    float2 x[R];
+    {
+        const float* row = a.r + (live ? stream : 0) * a.r_stride;
+        const int64_t s0 = (int64_t)b * kB - kB + a.in_off;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int loc = 2 * (t + i * T);
+            const int64_t n = s0 + loc;
+            float v0 = 0.f, v1 = 0.f;
+            if (live) {
+                const bool ok0 = n >= 0 && n < a.T && loc < a.valid_len;
+                const bool ok1 = n + 1 >= 0 && n + 1 < a.T && loc + 1 < a.valid_len;
+                if (!a.reverse) {
+                    if (ok0) v0 = row[n];
+                    if (ok1) v1 = row[n + 1];
+                } else {
+                    if (ok0) v0 = row[a.T - 1 - n];
+                    if (ok1) v1 = row[a.T - 2 - n];
+                }
+            }
+            x[i] = make_float2(v0, v1);
+        }
+    }
+    __syncthreads();
+    fft_forward<P, NT>(x, zbuf + g * MP, tw, t, g);
+    __syncthreads();
+    // untangle: X[k] = (s + w2 d)/2, X[M-k] = conj(s - w2 d)/2
+    for (int item = tid; item < SF * (M / 2 + 1); item += NT) {
+        const int gg = item / (M / 2 + 1), k = item % (M / 2 + 1), km = M - k;
+        const int64_t bg = (int64_t)blockIdx.x * SF + gg;
+        if (bg / a.nblk >= a.n_streams) continue;
+        const float2* zs = zbuf + gg * MP;
+        float2* out = a.spec + bg * M;
+        const float2 z1 = zs[zpad<P>(k)], z2 = zs[zpad<P>(km == M ? 0 : km)];
+        float sn, cs;
+        sincospif(2.0f * (float)k / (float)N, &sn, &cs);
+        const float2 w2 = make_float2(-sn, -cs);
+        const float2 s = make_float2(z1.x + z2.x, z1.y - z2.y);
+        const float2 d = make_float2(z1.x - z2.x, z1.y + z2.y);
+        const float2 tt = cmul(w2, d);
+        const float2 x1 = make_float2(0.5f * (s.x + tt.x), 0.5f * (s.y + tt.y));
+        const float2 x2 = make_float2(0.5f * (s.x - tt.x), 0.5f * (tt.y - s.y));
+        if (k == 0) out[0] = make_float2(x1.x, x2.x);          // (X[0], X[M])
+        else {
+            out[k] = x1;
+            if (km != k) out[km] = x2;
+        }
+    }
+}
+
+struct AccArgs {
+    const float2* spec;      // [n_streams, nblk_in, M]
+    const float2* H;         // [parts, M]
+    const float2* tw;
+    float* P;                // [n_streams, p_stride]
+    float* pmax;             // [n_streams]
+    int64_t p_stride, out_len;   // out_len = T + Lc - 1
+    int nblk_in, nblk_out, parts;
+};
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// One CTA (128 threads = one symbol group) per output block.
+__global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
+    using P = SP;
+    constexpr int NT = 128, T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP;
+    static_assert(T == NT, "one symbol group per CTA");
+    constexpr int PAIRS = M / 2 + 1, PPT = (PAIRS + NT - 1) / NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* zbuf = reinterpret_cast<float2*>(smem_raw);
+    float2* tw = zbuf + MP;
+    __shared__ float wmax[NT / 32];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
+    const int64_t stream = blockIdx.x / a.nblk_out;
+    const int b = (int)(blockIdx.x % a.nblk_out);
+
+    float2 acc1[PPT], acc2[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) acc1[q] = acc2[q] = make_float2(0.f, 0.f);
+    for (int p = 0; p < a.parts; ++p) {
+        const int bi = b - p;
+        if (bi < 0 || bi >= a.nblk_in) continue;
+        const float2* X = a.spec + (stream * a.nblk_in + bi) * M;
+        const float2* H = a.H + (int64_t)p * M;
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            const int k = tid + q * NT;
+            if (k >= PAIRS) continue;
+            const int km = M - k;
+            if (k == 0) {          // packed (DC, Nyquist): component-wise real products
+                const float2 xv = X[0], hv = H[0];
+                acc1[q].x += xv.x * hv.x;
+                acc2[q].x += xv.y * hv.y;
+            } else {
+                const float2 x1 = X[k], h1 = H[k];
+                acc1[q].x = fmaf(x1.x, h1.x, fmaf(-x1.y, h1.y, acc1[q].x));
+                acc1[q].y = fmaf(x1.x, h1.y, fmaf(x1.y, h1.x, acc1[q].y));
+                if (km != k) {
+                    const float2 x2 = X[km], h2 = H[km];
+                    acc2[q].x = fmaf(x2.x, h2.x, fmaf(-x2.y, h2.y, acc2[q].x));
+                    acc2[q].y = fmaf(x2.x, h2.y, fmaf(x2.y, h2.x, acc2[q].y));
+                }
+            }
+        }
+    }
+    // inverse untangle: Z[k] = E + jO, E = Y[k] + conj Y[M-k], O = (Y[k] - conj Y[M-k]) e^{+j theta}
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        const int k = tid + q * NT;
+        if (k >= PAIRS) continue;
+        const int km = M - k;
+        float2 Y1 = acc1[q], Y2 = (km == k) ? acc1[q] : acc2[q];      // k == 0: Y1 = (Y[0],0), Y2 = (Y[M],0)
+        float sn, cs;
+        sincospif(2.0f * (float)k / (float)N, &sn, &cs);
+        const float2 E = make_float2(Y1.x + Y2.x, Y1.y - Y2.y);
+        const float2 D = make_float2(Y1.x - Y2.x, Y1.y + Y2.y);
+        const float2 O = cmul(D, make_float2(cs, sn));
+        const float2 Zk = make_float2(E.x - O.y, E.y + O.x);
+        const float2 Zm = make_float2(E.x + O.y, O.x - E.y);
+        zbuf[zpad<P>(k == M ? 0 : k)] = cconj(Zk);
+        if (k != 0 && km != k) zbuf[zpad<P>(km)] = cconj(Zm);
+    }
+    __syncthreads();
+    float2 x[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) x[i] = zbuf[zpad<P>(tid + i * T)];
+    __syncthreads();
+    fft_forward<P, NT>(x, zbuf, tw, tid, 0);
+    __syncthreads();
+    // last B samples of the block: z[m], m in [M/2, M);  x[2m] = Re Y/N, x[2m+1] = -Im Y/N
+    const float scale = 1.0f / (float)N;
+    float* Prow = a.P + stream * a.p_stride;
+    float lmax = __int_as_float(0xff800000);
+    for (int m = M / 2 + tid; m < M; m += NT) {
+        const float2 y = zbuf[zpad<P>(m)];
+        const int64_t n = (int64_t)b * kB + (2 * m - kB);
+        const float v0 = y.x * scale, v1 = -y.y * scale;
+        if (n < a.out_len) { Prow[n] = v0; lmax = fmaxf(lmax, v0); }
+        if (n + 1 < a.out_len) { Prow[n + 1] = v1; lmax = fmaxf(lmax, v1); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    if ((tid & 31) == 0) wmax[tid >> 5] = lmax;
+    __syncthreads();
+    if (tid == 0) {
+        float m = wmax[0];
+        for (int w = 1; w < NT / 32; ++w) m = fmaxf(m, wmax[w]);
+        if (m > __int_as_float(0xff800000)) atomic_max_float(a.pmax + stream, m);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// chirp_method's detection rule + get_symbols' bookkeeping, one CTA per stream.
+//   zeros[i] = (D[i]*D[i+1] <= 0) & (Pn[i+1] > thresh),  Pn = P/pmax, D = diff(Pn), i in [0, len-2)
+//   ascending scan: a surviving detection at i clears zeros[i+1 .. i+Lc]; if i + Lc >= len(zeros)
+//   the reference's except-branch wipes every detection (OFDM.py:366-370).
+// ------------------------------------------------------------------------------------------
+struct PeakArgs {
+    const float* P;
+    const float* pmax;
+    int64_t* peaks;
+    int32_t* count;
+    int64_t p_stride, plen;      // plen = T + Lc - 1
+    int32_t max_peaks, Lc;
+    float thresh;
+};
+
+__global__ void __launch_bounds__(256) peak_pick_kernel(const PeakArgs a) {
+    constexpr int NT = 256, PER = 8, TILE = NT * PER;
+    __shared__ long long s_first;
+    const int tid = threadIdx.x;
+    const int64_t stream = blockIdx.x;
+    const float* Prow = a.P + stream * a.p_stride;
+    const float inv = 1.0f / a.pmax[stream];
+    const int64_t nz = a.plen - 2;
+    int32_t found = 0;
+    bool wiped = false;
+    int64_t pos = 0;
+    while (pos < nz) {
+        if (tid == 0) s_first = 0x7fffffffffffffffLL;
+        __syncthreads();
+        const int64_t base = pos + (int64_t)tid * PER;
+        long long mine = 0x7fffffffffffffffLL;
+        if (base < nz) {
+            float prev = Prow[base] * inv, cur = Prow[base + 1] * inv;
+#pragma unroll
+            for (int e = 0; e < PER; ++e) {
+                const int64_t i = base + e;
+                if (i >= nz) break;
+                const float nxt = Prow[i + 2] * inv;
+                const float d0 = cur - prev, d1 = nxt - cur;
+                if (d0 * d1 <= 0.f && cur > a.thresh) { mine = i; break; }
+                prev = cur; cur = nxt;
+            }
+        }
+        if (mine != 0x7fffffffffffffffLL) atomicMin(&s_first, mine);
+        __syncthreads();
+        const long long first = s_first;
+        __syncthreads();
+        if (first == 0x7fffffffffffffffLL) { pos += TILE; continue; }
+        if (first + a.Lc >= nz) { wiped = true; break; }
+        if (tid == 0 && found < a.max_peaks) a.peaks[stream * a.max_peaks + found] = first;
+        ++found;
+        pos = first + a.Lc + 1;
+    }
+    if (tid == 0) a.count[stream] = wiped ? 0 : found;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static int run_fwd(const float* r, int64_t r_stride, int64_t n_streams, int64_t T, int nblk, int reverse,
+                   int in_off, int valid_len, float2* spec, const float2* tw, float* pmax, cudaStream_t st) {
+    constexpr int SF = kSyncThreads / SP::T;
+    FwdArgs f;
+    f.r = r; f.spec = spec; f.tw = tw; f.pmax = pmax; f.r_stride = r_stride; f.T = T; f.n_streams = n_streams;
+    f.nblk = nblk; f.reverse = reverse; f.in_off = in_off; f.valid_len = valid_len;
+    const size_t smem = (size_t)(SF * SP::MP + SP::TW_TOTAL) * sizeof(float2);
+    GF3_CHECK_CUDA(cudaFuncSetAttribute(xcorr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t gx = (n_streams * nblk + SF - 1) / SF;
+    GF3_REQUIRE(gx <= 0x7fffffff, "xcorr: too many blocks in one tile");
+    xcorr_fwd_kernel<<<(unsigned)gx, kSyncThreads, smem, st>>>(f);
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}
+
+int sync_plan_init(gf3_plan* plan) {
+    const gf3_params& p = plan->p;
+    int rc = make_chirp(plan);
+    if (rc) return rc;
+    plan->sync_logN = SP::LOGN;
+    plan->sync_parts = (p.chirp_len + kB - 1) / kB;
+    if (plan->logN == SP::LOGN) plan->d_sync_tw = plan->d_tw;
+    else { rc = upload_twiddles(SP::LOGN, &plan->d_sync_tw); if (rc) return rc; }
+    GF3_CHECK_CUDA(cudaMalloc(&plan->d_chirp_spec, (size_t)plan->sync_parts * SP::M * sizeof(float2)));
+    // H_p = rfft_{2B}([h[pB .. pB+B), 0 ... 0]),  h[m] = chirp[Lc-1-m]  (fsweep of OFDM.py:357)
+    rc = run_fwd(plan->d_chirp, 0, 1, p.chirp_len, plan->sync_parts, 1, kB, kB, plan->d_chirp_spec,
+                 plan->d_sync_tw, nullptr, 0);
+    if (rc) return rc;
+    GF3_CHECK_CUDA(cudaDeviceSynchronize());
+    return GF3_OK;
+}
+
+void sync_plan_free(gf3_plan* plan) {
+    if (plan->d_sync_tw && plan->d_sync_tw != plan->d_tw) cudaFree(plan->d_sync_tw);
+    if (plan->d_chirp_spec) cudaFree(plan->d_chirp_spec);
+    if (plan->d_chirp) cudaFree(plan->d_chirp);
+    if (plan->d_known_time) cudaFree(plan->d_known_time);
+    plan->d_sync_tw = nullptr; plan->d_chirp_spec = nullptr; plan->d_chirp = nullptr; plan->d_known_time = nullptr;
+}
+
+struct XcorrGeom { int nblk_out, nblk_in; int64_t out_len; size_t per_stream; int64_t tile; };
+static XcorrGeom xcorr_geom(const gf3_plan* plan, int64_t n_streams, int64_t T) {
+    XcorrGeom g;
+    g.out_len = T + plan->p.chirp_len - 1;
+    g.nblk_out = (int)((g.out_len + kB - 1) / kB);
+    int64_t nin = (T - 1) / kB + 2;                      // blocks that see at least one real sample
+    g.nblk_in = (int)(nin < g.nblk_out ? nin : g.nblk_out);
+    g.per_stream = (size_t)g.nblk_in * SP::M * sizeof(float2);
+    const size_t cap = (size_t)2 << 30;                   // bound the scratch to 2 GiB: streams are tiled
+    int64_t tile = (int64_t)(cap / g.per_stream);
+    if (tile < 1) tile = 1;
+    if (tile > n_streams) tile = n_streams;
+    g.tile = tile;
+    return g;
+}
+
+}  // namespace gf3
+
+using namespace gf3;
+
+extern "C" size_t gf3_xcorr_work_bytes(const gf3_plan* plan, int64_t n_streams, int64_t T) {
+    if (!plan || n_streams <= 0 || T <= 0) return 0;
+    const XcorrGeom g = xcorr_geom(plan, n_streams, T);
+    return g.per_stream * (size_t)g.tile;
+}
+
+extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride, int64_t n_streams,
+                         int64_t T, float* P, int64_t p_stride, float* pmax, void* work, void* stream) {
+    GF3_REQUIRE(plan && r && P && pmax && work, "xcorr: null argument");
+    GF3_REQUIRE(n_streams >= 0 && T >= 1, "xcorr: bad sizes");
+    if (n_streams == 0) return GF3_OK;
+    const XcorrGeom g = xcorr_geom(plan, n_streams, T);
+    GF3_REQUIRE(p_stride >= g.out_len, "xcorr: p_stride %lld < T + chirp_len - 1 = %lld", (long long)p_stride, (long long)g.out_len);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    float2* spec = reinterpret_cast<float2*>(work);
+    const size_t smem = (size_t)(SP::MP + SP::TW_TOTAL) * sizeof(float2);
+    GF3_CHECK_CUDA(cudaFuncSetAttribute(xcorr_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t s0 = 0; s0 < n_streams; s0 += g.tile) {
+        const int64_t ns = (n_streams - s0 < g.tile) ? n_streams - s0 : g.tile;
+        int rc = run_fwd(r + s0 * r_stride, r_stride, ns, T, g.nblk_in, 0, 0, 2 * kB, spec, plan->d_sync_tw, pmax + s0, st);
+        if (rc) return rc;
+        AccArgs a;
+        a.spec = spec; a.H = plan->d_chirp_spec; a.tw = plan->d_sync_tw; a.P = P + s0 * p_stride; a.pmax = pmax + s0;
+        a.p_stride = p_stride; a.out_len = g.out_len; a.nblk_in = g.nblk_in; a.nblk_out = g.nblk_out; a.parts = plan->sync_parts;
+        const int64_t grid = ns * g.nblk_out;
+        GF3_REQUIRE(grid <= 0x7fffffff, "xcorr: grid too large");
+        xcorr_acc_kernel<<<(unsigned)grid, 128, smem, st>>>(a);
+        GF3_LAUNCH_CHECK();
+    }
+    return GF3_OK;
+}
+
+extern "C" int gf3_peak_pick(const gf3_plan* plan, const float* P, int64_t p_stride, int64_t n_streams,
+                             int64_t T, const float* pmax, int64_t* peaks, int32_t max_peaks, int32_t* count,
+                             void* stream) {
+    GF3_REQUIRE(plan && P && pmax && peaks && count, "peak_pick: null argument");
+    GF3_REQUIRE(max_peaks >= 1 && n_streams >= 0 && n_streams <= 0x7fffffff, "peak_pick: bad sizes");
+    if (n_streams == 0) return GF3_OK;
+    PeakArgs a;
+    a.P = P; a.pmax = pmax; a.peaks = peaks; a.count = count; a.p_stride = p_stride;
+    a.plen = T + plan->p.chirp_len - 1; a.max_peaks = max_peaks; a.Lc = plan->p.chirp_len; a.thresh = plan->p.thresh;
+    GF3_REQUIRE(a.plen >= 3, "peak_pick: signal too short");
+    peak_pick_kernel<<<(unsigned)n_streams, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}

@@ -1,0 +1,229 @@
+"""Device-level GF3 physical layer: torch tensors in HBM in, torch tensors out.
+
+`Phy` wraps one gf3_plan (include/gf3_b200.h) and exposes the fused kernels batch-wise; the
+numpy drop-in surface of the reference (OFDM.py: CamG / transmitter / receiver) sits on top of it
+in ../OFDM.py.  PyTorch is used only for device memory, streams and (in bench.py / sweep.py)
+torch.distributed -- every arithmetic step of the path runs in libgf3b200.so.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Gf3Params, check
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+KNOWN_SEQUENCE_FILE = os.path.join(_HERE, "known_sequence_4096.txt")
+
+# OFDM.py:30-40
+MODES = {
+    "A1": (224, (1, 2047)), "A2": (224, (100, 1500)), "A3": (224, (100, 1000)),
+    "B1": (704, (1, 2047)), "B2": (704, (100, 1500)), "B3": (704, (100, 1000)),
+    "C1": (1184, (1, 2047)), "C2": (1184, (100, 1500)), "C3": (1184, (100, 1000)),
+}
+
+
+def default_known_sequence():
+    """The CamG-standard known bit sequence: first 4096 characters of Handouts/random_bits.txt
+    (OFDM.py:99-101), shipped with the package so the GPU box does not need the reference tree."""
+    raw = np.fromfile(KNOWN_SEQUENCE_FILE, dtype=np.uint8)
+    return (raw - ord("0")).astype(np.int64)
+
+
+def qpsk_points(bits2):
+    """Gray QPSK table of OFDM.py:72-77 as an array expression (host-side formatting only)."""
+    b = np.asarray(bits2).astype(np.int64)
+    return ((1 - 2 * b[..., 1]) + 1j * (1 - 2 * b[..., 0])) / np.sqrt(2)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Phy:
+    """One parameter set of the modem on one CUDA device."""
+
+    def __init__(self, N=4096, cp=224, lo=100, hi=1500, n_pilots=20, packet_len=180,
+                 known_sequence=None, device=None, fit_lo=None, fit_hi=None, chirp_len=None,
+                 thresh=None, fs=None, f0=None, f1=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available() or self.lib.gf3_device_count() == 0:
+            raise _lib.Gf3Error(_lib.GF3_ERR_NODEVICE,
+                                "no CUDA device: the GF3 B200 physical layer has no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        p = Gf3Params()
+        check(self.lib.gf3_params_default(ctypes.byref(p), N, cp, lo, hi, n_pilots, packet_len))
+        for name, val in (("fit_lo", fit_lo), ("fit_hi", fit_hi), ("chirp_len", chirp_len),
+                          ("thresh", thresh), ("fs", fs), ("f0", f0), ("f1", f1)):
+            if val is not None:
+                setattr(p, name, val)
+        self.params = p
+        self.N, self.cp, self.lo, self.hi = N, cp, lo, hi
+        self.P, self.L = n_pilots, packet_len
+        self.K = N // 2 - 1
+        self.Nd = hi - lo
+        self.symlen = N + cp
+        self.chirp_len = int(p.chirp_len)
+        self.pkt_samples = (2 * n_pilots + packet_len) * self.symlen
+        self.bits_per_packet = 2 * self.Nd * packet_len
+        # row stride of packed-bit buffers: whole 32-bit words, 16-byte multiple for vector access
+        self.bits_stride = ((self.bits_per_packet + 31) // 32 * 4 + 15) // 16 * 16
+        self._plan = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.gf3_plan_create(ctypes.byref(p), ctypes.byref(self._plan)))
+        ks = default_known_sequence() if known_sequence is None else np.asarray(known_sequence).astype(np.int64)
+        if len(ks) < 2 * self.K:
+            raise ValueError("known_sequence needs at least 2K = %d bits" % (2 * self.K))
+        self.known_sequence = ks
+        known = qpsk_points(ks[: 2 * self.K].reshape(self.K, 2)).astype(np.complex64)     # OFDM.py:429
+        self.known = torch.from_numpy(known).to(self.device)
+        kb = ks[: 2 * self.Nd].reshape(self.Nd, 2)
+        self.xor2 = torch.from_numpy(((kb[:, 0] << 1) | kb[:, 1]).astype(np.uint8)).to(self.device)   # OFDM.py:542
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None):
+                self.lib.gf3_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _f32(self, t):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "need contiguous float32 CUDA tensor"
+        return t
+
+    def _offsets(self, pkt_offset, n):
+        if pkt_offset is None:
+            return None
+        assert pkt_offset.is_cuda and pkt_offset.dtype == torch.int64 and pkt_offset.numel() == n
+        return pkt_offset.contiguous()
+
+    # ------------------------------------------------------------------ receive chain
+    def rx_estimate(self, samples, n_packets, pkt_offset=None):
+        """-> Hs, He complex64 [n_packets, K], slope float64 [n_packets]  (OFDM.py:429-462)."""
+        self._f32(samples)
+        off = self._offsets(pkt_offset, n_packets)
+        Hs = torch.empty((n_packets, self.K), dtype=torch.complex64, device=self.device)
+        He = torch.empty_like(Hs)
+        slope = torch.empty((n_packets,), dtype=torch.float64, device=self.device)
+        check(self.lib.gf3_rx_estimate(self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(self.known),
+                                       _ptr(Hs), _ptr(He), _ptr(slope), _stream()))
+        return Hs, He, slope
+
+    def rx_demod(self, samples, n_packets, Hs, He, slope, pkt_offset=None, xor=True, want_eq=False,
+                 out=None):
+        """-> packed bits uint8 [n_packets, bits_stride] (and eq complex64 [n_packets, L, K]).
+        Fused CP strip + FFT + equalise + demap + XOR decode (OFDM.py:407-418,593,466-505,541-544)."""
+        self._f32(samples)
+        off = self._offsets(pkt_offset, n_packets)
+        bits = out if out is not None else torch.empty((n_packets, self.bits_stride), dtype=torch.uint8, device=self.device)
+        eq = torch.empty((n_packets, self.L, self.K), dtype=torch.complex64, device=self.device) if want_eq else None
+        check(self.lib.gf3_rx_demod(self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(Hs), _ptr(He), _ptr(slope),
+                                    _ptr(self.xor2) if xor else None, _ptr(bits), self.bits_stride, _ptr(eq), _stream()))
+        return (bits, eq) if want_eq else bits
+
+    def rx_known_channel(self, samples, n_packets, Hinv, pkt_offset=None, xor=False, want_eq=False):
+        """Known-channel receiver (Weekend Challenge.ipynb:162-226): Y * Hinv on bins 1..K, demap."""
+        self._f32(samples)
+        off = self._offsets(pkt_offset, n_packets)
+        assert Hinv.is_cuda and Hinv.dtype == torch.complex64 and Hinv.numel() == self.K
+        bits = torch.empty((n_packets, self.bits_stride), dtype=torch.uint8, device=self.device)
+        eq = torch.empty((n_packets, self.L, self.K), dtype=torch.complex64, device=self.device) if want_eq else None
+        check(self.lib.gf3_rx_known_channel(self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(Hinv.contiguous()),
+                                            _ptr(self.xor2) if xor else None, _ptr(bits), self.bits_stride, _ptr(eq), _stream()))
+        return (bits, eq) if want_eq else bits
+
+    def spectrum(self, samples, n_symbols, sym_offset=None):
+        """FFT bins 1..K of n_symbols symbols (CP stripped): complex64 [n_symbols, K] (OFDM.py:407-416,593)."""
+        self._f32(samples)
+        off = self._offsets(sym_offset, n_symbols)
+        out = torch.empty((n_symbols, self.K), dtype=torch.complex64, device=self.device)
+        check(self.lib.gf3_rx_spectrum(self._plan, _ptr(samples), _ptr(off), n_symbols, _ptr(out), _stream()))
+        return out
+
+    def unpack_bits(self, packed, n_packets=None):
+        """Host-side: packed [n_packets, bits_stride] -> int64 bit vector (np.unpackbits order)."""
+        a = packed.cpu().numpy() if isinstance(packed, torch.Tensor) else np.asarray(packed)
+        bits = np.unpackbits(a, axis=1)[:, : self.bits_per_packet]
+        return bits.reshape(-1).astype(np.int64)
+
+    # ------------------------------------------------------------------ synchronisation
+    def sync_chirp(self):
+        out = torch.empty((self.chirp_len,), dtype=torch.float32, device=self.device)
+        check(self.lib.gf3_sync_chirp(self._plan, _ptr(out), _stream()))
+        return out
+
+    def xcorr(self, r):
+        """Matched filter of chirp_method (OFDM.py:357-358): r [B, T] -> P [B, T+Lc-1], pmax [B]."""
+        self._f32(r)
+        assert r.dim() == 2
+        B, T = r.shape
+        plen = T + self.chirp_len - 1
+        pstride = (plen + 3) // 4 * 4
+        P = torch.empty((B, pstride), dtype=torch.float32, device=self.device)
+        pmax = torch.empty((B,), dtype=torch.float32, device=self.device)
+        wb = int(self.lib.gf3_xcorr_work_bytes(self._plan, B, T))
+        work = torch.empty((wb,), dtype=torch.uint8, device=self.device)
+        check(self.lib.gf3_xcorr(self._plan, _ptr(r), T, B, T, _ptr(P), pstride, _ptr(pmax), _ptr(work), _stream()))
+        return P[:, :plen], pmax
+
+    def peak_pick(self, P, pmax, T, max_peaks=64):
+        """Detection rule of chirp_method (OFDM.py:359-372): -> peaks int64 [B, max_peaks], count int32 [B]."""
+        assert P.is_cuda and P.dtype == torch.float32 and P.stride(1) == 1
+        B = P.shape[0]
+        peaks = torch.full((B, max_peaks), -1, dtype=torch.int64, device=self.device)
+        count = torch.empty((B,), dtype=torch.int32, device=self.device)
+        check(self.lib.gf3_peak_pick(self._plan, _ptr(P), P.stride(0), B, T, _ptr(pmax), _ptr(peaks), max_peaks,
+                                     _ptr(count), _stream()))
+        return peaks, count
+
+    # ------------------------------------------------------------------ transmit chain
+    def tx_len(self, pk_per_stream):
+        return pk_per_stream * (self.chirp_len + self.pkt_samples) + self.chirp_len
+
+    def tx_modulate(self, bits_packed, filler, n_streams, pk_per_stream, out=None):
+        """bits_packed uint8 [n_streams, pk_per_stream, bits_stride] (encoded bits, MSB first),
+        filler complex64 [n_streams, K-Nd] -> waveform float32 [n_streams, tx_len]
+        (OFDM.py:191-226, 244-259, 322-323)."""
+        assert bits_packed.is_cuda and bits_packed.dtype == torch.uint8 and bits_packed.is_contiguous()
+        stride = bits_packed.shape[-1]
+        if filler is not None:
+            assert filler.is_cuda and filler.dtype == torch.complex64 and filler.is_contiguous()
+        T = self.tx_len(pk_per_stream)
+        tstride = (T + 3) // 4 * 4
+        if out is None:
+            out = torch.empty((n_streams, tstride), dtype=torch.float32, device=self.device)
+        check(self.lib.gf3_tx_modulate(self._plan, _ptr(bits_packed), stride, _ptr(filler), _ptr(self.known),
+                                       n_streams, pk_per_stream, _ptr(out), out.stride(0), _stream()))
+        return out[:, :T]
+
+    # ------------------------------------------------------------------ channel + counters
+    def channel_sim(self, x, taps, sigma, seed):
+        """y = lfilter(taps, 1, x) + sigma*N(0,1): x [B, T] (row stride may exceed T)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
+        B, T = x.shape
+        taps = taps.to(torch.float32).contiguous()
+        y = torch.empty((B, (T + 3) // 4 * 4), dtype=torch.float32, device=self.device)
+        sg = sigma.to(torch.float32).contiguous() if sigma is not None else None
+        check(self.lib.gf3_channel_sim(_ptr(x), x.stride(0), B, T, _ptr(taps), taps.shape[1], _ptr(sg),
+                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(y), y.stride(0), _stream()))
+        return y[:, :T]
+
+    def ber_count(self, a, b, nbits, counter):
+        """counter (int64/uint64 [2]) += (bit errors, bits) between two packed rows."""
+        check(self.lib.gf3_ber_count(_ptr(a), _ptr(b), nbits, _ptr(counter), _stream()))
+        return counter
+
+    # ------------------------------------------------------------------ whole receive chain
+    def receive_packets(self, samples, n_packets, pkt_offset=None, xor=True, want_eq=False):
+        """estimate + demod for n_packets packets whose starts are known."""
+        Hs, He, slope = self.rx_estimate(samples, n_packets, pkt_offset)
+        out = self.rx_demod(samples, n_packets, Hs, He, slope, pkt_offset, xor=xor, want_eq=want_eq)
+        return out, Hs, He, slope

@@ -1,0 +1,174 @@
+/* gf3_b200.h -- C ABI of the B200-native GF3 OFDM physical layer (libgf3b200.so).
+ *
+ * The reference (adamg-97/GF3-audio-modem) is one Python module, OFDM.py, with no FFI of its
+ * own; its boundary is the numpy-in / numpy-out method surface of the classes CamG /
+ * transmitter / receiver.  This header is the C-ABI a binding for that surface loads (the
+ * ctypes stub is gf3-audio-modem_b200/gf3b200/_lib.py; INTEGRATION.md shows the reference-side
+ * patch).  Each entry point names the reference lines (file:line in the reference repo) it
+ * replaces.
+ *
+ * Conventions
+ *  - every array pointer is a DEVICE pointer owned by the caller (e.g. torch tensor storage);
+ *    the library allocates nothing except inside an explicit gf3_plan handle (small constant
+ *    tables: FFT twiddles, chirp spectrum);
+ *  - every call is asynchronous on the cudaStream_t passed as `stream` (NULL = default stream);
+ *  - return value 0 = OK, < 0 = error; gf3_last_error() returns a thread-local message;
+ *  - complex arrays are interleaved float (re, im) = numpy complex64;
+ *  - "packed bits" are MSB-first bytes exactly as np.packbits produces (OFDM.py:761,769);
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef GF3_B200_H
+#define GF3_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GF3_ABI_VERSION 1
+
+/* exported from libgf3b200.so (everything else in the library has hidden visibility) */
+#if defined(__GNUC__)
+#define GF3_API __attribute__((visibility("default")))
+#else
+#define GF3_API
+#endif
+
+enum {
+    GF3_OK = 0,
+    GF3_ERR_INVALID = -1,   /* bad argument / unsupported parameter combination */
+    GF3_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+    GF3_ERR_NODEVICE = -3   /* no CUDA device: the product has no CPU path */
+};
+
+/* Parameter contract of CamG.__init__ (OFDM.py:18-101), generalised to any power-of-two N. */
+typedef struct gf3_params {
+    int32_t N;            /* OFDM.py:27   ofdm_symbol_size (power of two, 64..8192)        */
+    int32_t cp;           /* OFDM.py:42   cyclic prefix length (even)                      */
+    int32_t lo;           /* OFDM.py:43   lowest data bin, inclusive (>= 1)                */
+    int32_t hi;           /* OFDM.py:44,47 highest data bin, EXCLUSIVE (<= N/2)            */
+    int32_t n_pilots;     /* OFDM.py:51   known OFDM symbols before and after the data     */
+    int32_t packet_len;   /* OFDM.py:50   data symbols per packet                          */
+    int32_t fit_lo;       /* OFDM.py:462  phase-slope fit window start (reference: 500)    */
+    int32_t fit_hi;       /* OFDM.py:462  phase-slope fit window end, exclusive (1000)     */
+    int32_t chirp_len;    /* OFDM.py:64   5*(N+cp) in the reference                        */
+    float fs;             /* OFDM.py:24   48000                                            */
+    float f0;             /* OFDM.py:62   chirp start frequency                            */
+    float f1;             /* OFDM.py:63   chirp end frequency                              */
+    float thresh;         /* OFDM.py:361  0.4 (fraction of the global matched-filter max)  */
+    float tx_gain;        /* OFDM.py:256  2.0                                              */
+    float chirp_gain;     /* OFDM.py:109  0.2 (= 1/5)                                      */
+} gf3_params;
+
+typedef struct gf3_plan gf3_plan;   /* opaque: device-resident constant tables for one params set */
+
+/* ---- library / plan ------------------------------------------------------------------ */
+GF3_API int gf3_abi_version(void);
+GF3_API const char* gf3_last_error(void);
+/* Number of CUDA devices visible; 0 means every compute call will return GF3_ERR_NODEVICE. */
+GF3_API int gf3_device_count(void);
+/* Fill derived defaults (fit window 500..1000, chirp_len 5*(N+cp), fs 48000, f0 0, f1 8000,
+ * thresh 0.4, tx_gain 2, chirp_gain 0.2) -- the constants hard-coded in OFDM.py:24,62-64,109,
+ * 256,361,462.  Only N, cp, lo, hi, n_pilots, packet_len are read from the arguments. */
+GF3_API int gf3_params_default(gf3_params* p, int N, int cp, int lo, int hi, int n_pilots, int packet_len);
+/* Builds the twiddle tables on the current device.  Replaces CamG.__init__ (OFDM.py:18-101). */
+GF3_API int gf3_plan_create(const gf3_params* p, gf3_plan** out);
+GF3_API int gf3_plan_destroy(gf3_plan* plan);
+GF3_API int gf3_plan_params(const gf3_plan* plan, gf3_params* out);
+/* Kernels launched by this library since load (all entry points; for bench.py's gpu_launches). */
+GF3_API int64_t gf3_launch_count(void);
+
+/* ---- receive chain ----------------------------------------- */
+/* Packet p's samples start at samples[pkt_offset[p]] (pkt_offset == NULL: packets are
+ * contiguous, offset p*(2P+L)*(N+cp)).  This one addressing mode covers both the reference's
+ * get_symbols slicing (OFDM.py:391-403: offset = sync index) and pre-sliced symbol arrays.
+ * Any sample alignment is accepted; 8-byte aligned packets take the vectorised load path.   */
+
+/* Channel estimate from the known symbols: remove_cp + fft + get_data (pilot part) + the first
+ * half of equalise (OFDM.py:407-418, 593, 429-462).
+ *   known[K]   complex64, the known QPSK symbols on bins 1..K (OFDM.py:429)
+ *   Hs, He     complex64 [n_packets, K]   = mean_P(FFT(pilots))/known        (OFDM.py:443-451)
+ *   slope      float64   [n_packets]      = LS slope of unwrap(angle(He))-unwrap(angle(Hs))
+ *                                           over bins [fit_lo, min(fit_hi,K))  (OFDM.py:454-462) */
+GF3_API int gf3_rx_estimate(const gf3_plan* plan, const float* samples, const int64_t* pkt_offset,
+                    int64_t n_packets, const float* known, float* Hs, float* He, double* slope,
+                    void* stream);
+
+/* Data symbols: remove_cp + fft + get_data + equalise second half + carrier select + demap + PS
+ * + decode("XOR") fused; every data sample is read from HBM once (OFDM.py:407-418, 593,
+ * 466-478, 603, 484-505, 541-544).
+ *   xor2[Nd]     uint8 or NULL: per data carrier (b0<<1)|b1 of known_sequence[:2Nd] (OFDM.py:542)
+ *   bits_packed  uint8 [n_packets, bits_stride]: packet p's L*Nd*2 bits, MSB first, symbol-major,
+ *                carrier, b0 then b1 (OFDM.py:500,505); bits_stride % 4 == 0 and
+ *                bits_stride*8 >= L*Nd*2 rounded up to 32; pad bits are written as 0
+ *   eq           complex64 [n_packets, L, K] or NULL: the equalised constellation of all K bins
+ *                (OFDM.py:478,480), for parity checks; off for throughput                   */
+GF3_API int gf3_rx_demod(const gf3_plan* plan, const float* samples, const int64_t* pkt_offset,
+                 int64_t n_packets, const float* Hs, const float* He, const double* slope,
+                 const uint8_t* xor2, uint8_t* bits_packed, int64_t bits_stride, float* eq,
+                 void* stream);
+
+/* Known-channel receive (old API, Weekend Challenge.ipynb:162-226): Y/H on bins 1..K, demap.
+ * Uses the plan's geometry with its n_pilots leading/trailing symbols skipped (create the plan
+ * with n_pilots = 0, packet_len = symbols per block).  Hinv[K] = 1/H on bins 1..K.          */
+GF3_API int gf3_rx_known_channel(const gf3_plan* plan, const float* samples, const int64_t* pkt_offset,
+                         int64_t n_packets, const float* Hinv, const uint8_t* xor2,
+                         uint8_t* bits_packed, int64_t bits_stride, float* eq, void* stream);
+
+/* Spectrum of arbitrary symbols: remove_cp + fft + bins 1..K (OFDM.py:407-408, 593, 414-416).
+ *   sym_offset[n_symbols] sample index of each symbol's first CP sample (NULL: contiguous)
+ *   out complex64 [n_symbols, K]                                                            */
+GF3_API int gf3_rx_spectrum(const gf3_plan* plan, const float* samples, const int64_t* sym_offset,
+                    int64_t n_symbols, float* out, void* stream);
+
+/* ---- chirp synchronisation ------------------------------------- */
+/* sync_chirp (OFDM.py:106-109): float32 [chirp_len]. */
+GF3_API int gf3_sync_chirp(const gf3_plan* plan, float* out, void* stream);
+/* Matched filter, the convolution of chirp_method (OFDM.py:357-358):
+ *   r [n_streams, T] float32 (row stride r_stride samples)
+ *   P [n_streams, T + chirp_len - 1] float32 (row stride p_stride), full linear convolution
+ *     with the time-reversed chirp, computed by overlap-save FFT blocks;
+ *   pmax [n_streams] float32: the signed global maximum of each row (np.amax, OFDM.py:359).
+ *   work: device scratch of gf3_xcorr_work_bytes() bytes.                                   */
+GF3_API size_t gf3_xcorr_work_bytes(const gf3_plan* plan, int64_t n_streams, int64_t T);
+GF3_API int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride, int64_t n_streams,
+              int64_t T, float* P, int64_t p_stride, float* pmax, void* work, void* stream);
+/* Peak picking of chirp_method + get_symbols (OFDM.py:359-372, 393-395): normalise by pmax,
+ * candidate mask (D[i]*D[i+1] <= 0) & (P[i+1] > thresh), ascending hold-off of chirp_len,
+ * including the end-of-signal wipe-out quirk (OFDM.py:366-370).
+ *   peaks [n_streams, max_peaks] int64: indices into the reference's `zeros` array
+ *   count [n_streams] int32: detections found (may exceed max_peaks; only max_peaks stored) */
+GF3_API int gf3_peak_pick(const gf3_plan* plan, const float* P, int64_t p_stride, int64_t n_streams,
+                  int64_t T, const float* pmax, int64_t* peaks, int32_t max_peaks, int32_t* count,
+                  void* stream);
+
+/* ---- transmit chain ---------------------------------------------- */
+/* map + build_OFDM_symbol + ifft + add_cp + send_to_stream fused (OFDM.py:191-226, 244-259,
+ * 322-323).  One launch writes whole packets [chirp | g*(P x known) | g*(L x data) | g*(P x
+ * known)] and, per stream, one trailing chirp.
+ *   bits_packed uint8 [n_streams, pk_per_stream, bits_stride]  encoded bits (after
+ *               transmitter.encode), MSB first, L*Nd*2 bits per packet
+ *   filler  complex64 [n_streams, K-Nd]  QPSK on the unused bins (random_qpsk, OFDM.py:201-203)
+ *   known   complex64 [K]
+ *   out     float32 [n_streams, out_stride], out_stride >= pk_per_stream*(chirp_len +
+ *           (2P+L)(N+cp)) + chirp_len                                                       */
+GF3_API int gf3_tx_modulate(const gf3_plan* plan, const uint8_t* bits_packed, int64_t bits_stride,
+                    const float* filler, const float* known, int64_t n_streams,
+                    int64_t pk_per_stream, float* out, int64_t out_stride, void* stream);
+
+/* ---- channel simulator + BER counters ---------------------- */
+/* y = lfilter(taps, 1, x) + sigma * N(0,1) (Philox-4x32-10 counter RNG, Box-Muller).
+ *   taps [n_streams, n_taps] float32 (n_taps <= 64), sigma [n_streams] float32            */
+GF3_API int gf3_channel_sim(const float* x, int64_t x_stride, int64_t n_streams, int64_t T,
+                    const float* taps, int32_t n_taps, const float* sigma, uint64_t seed,
+                    float* y, int64_t y_stride, void* stream);
+/* counter[0] += popcount(a ^ b) over nbits (MSB-first packed), counter[1] += nbits. */
+GF3_API int gf3_ber_count(const uint8_t* a, const uint8_t* b, int64_t nbits, uint64_t* counter,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GF3_B200_H */
