@@ -4,13 +4,14 @@ import numpy as np
 import torch
 
 
-def random_channels(n_streams, n_taps=30, decay=5.0, first_stream=0):
+def random_channels(n_streams, n_taps=30, decay=5.0, first_stream=0, stream_ids=None):
     """Per-stream multipath: h_k ~ N(0, exp(-k/decay)), unit energy, seed 1000 + stream id, with a
     dominant first tap so the matched-filter peak sits on tap 0."""
-    h = np.empty((n_streams, n_taps), dtype=np.float32)
+    ids = np.arange(first_stream, first_stream + n_streams) if stream_ids is None else np.asarray(stream_ids)
+    h = np.empty((len(ids), n_taps), dtype=np.float32)
     k = np.arange(n_taps)
-    for s in range(n_streams):
-        rng = np.random.default_rng(1000 + first_stream + s)
+    for s, sid in enumerate(ids):
+        rng = np.random.default_rng(1000 + int(sid))
         t = rng.normal(0.0, np.sqrt(np.exp(-k / decay)))
         t[0] = abs(t[0]) + 1.0
         h[s] = t / np.sqrt(np.sum(t * t))

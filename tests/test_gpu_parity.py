@@ -320,3 +320,21 @@ def test_dropin_transmit_receive_file_roundtrip(known_sequence, tmp_path, monkey
     # reference's np.vstack([]) raises ValueError (OFDM.py:395,400); same here
     with pytest.raises(ValueError):
         rx.receive(np.concatenate([np.zeros(1000), sig[:600000]]))
+
+
+def test_ber_sweep_sharding_invariance(known_sequence):
+    """configs[4] / SURVEY 8e: the stream-sharded tx -> channel -> sync -> rx sweep gives identical
+    counters however the streams are split across ranks (here: 3 emulated ranks on one GPU)."""
+    _torch()
+    import gf3b200
+    from gf3b200.sweep import make_gpu_count_fn, sweep
+    phy = gf3b200.Phy(N=1024, cp=32, lo=1, hi=512, n_pilots=4, packet_len=12, known_sequence=known_sequence, fit_lo=125, fit_hi=250)
+    count = make_gpu_count_fn(phy)
+    snrs = [4.0, 25.0]
+    full = sweep(count, 10, snrs, 0, 1, chunk=4)
+    parts = sum(sweep(count, 10, snrs, r, 3, chunk=3) for r in range(3))
+    assert np.array_equal(full, parts)
+    assert full[0, 1] == full[1, 1] == 10 * phy.bits_per_packet
+    assert full[1, 2] == 0                                  # every chirp found at 25 dB
+    assert full[1, 0] < full[0, 0]                          # BER falls with SNR
+    assert full[1, 0] / full[1, 1] < 0.02
