@@ -16,11 +16,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
-LIB = os.path.join(LIBDIR, "libgf3b200.so")
+LIB = os.path.join(LIBDIR, os.environ.get("GF3_LIB_NAME", "libgf3b200.so"))   # experiments: alternate name + flags
 SOURCES = ["gf3_lib.cu", "gf3_rx.cu", "gf3_tx.cu", "gf3_sync.cu", "gf3_chan.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("GF3_EXTRA_FLAGS", "").split()
+if "GF3_LIB_NAME" in os.environ:
+    OBJDIR = os.path.join(HERE, "build_" + os.environ["GF3_LIB_NAME"].replace(".so", ""))
 
 
 def _digest():

@@ -14,6 +14,13 @@
 namespace gf3 {
 
 constexpr int kThreads = 256;
+// How the next FFT batch's samples are brought closer while the equaliser phase runs:
+//   0 = nothing (plain loads at the start of the FFT phase)
+//   1 = loads issued into registers before the equaliser phase
+//   2 = one bulk L2 prefetch per symbol (cp.async.bulk.prefetch.L2, TMA engine, no registers)
+#ifndef GF3_PREFETCH
+#define GF3_PREFETCH 0
+#endif
 constexpr float kPi = 3.14159265358979323846f;
 
 struct RxArgs {
@@ -76,9 +83,9 @@ __device__ __forceinline__ float2 expmj(double a) {
 //   phase B: thread <-> bin pair (k, M-k): real-FFT untangling, equaliser, demap -> 2-bit codes
 //   flush  : 16 codes -> one 32-bit word of MSB-first packed bits, coalesced store
 // ------------------------------------------------------------------------------------------
-template <class P, bool KNOWN_CH, bool WANT_EQ>
-__global__ void __launch_bounds__(kThreads, 2) rx_demod_kernel(const RxArgs a) {
-    constexpr int NT = kThreads, T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP;
+template <class P, int NT, bool KNOWN_CH, bool WANT_EQ>
+__global__ void __launch_bounds__(NT, 512 / NT) rx_demod_kernel(const RxArgs a) {
+    constexpr int T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP;
     constexpr int SF = NT / T;                        // symbols per FFT batch
     constexpr int FLUSH = SF > 16 ? SF : 16;          // symbols per packed-bit flush (32*Nd bits: word aligned)
     constexpr int BATCHES = FLUSH / SF;
@@ -90,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 2) rx_demod_kernel(const RxArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* zbuf = reinterpret_cast<float2*>(smem_raw);
     float2* tw = zbuf + SF * MP;
-    uint8_t* stage = reinterpret_cast<uint8_t*>(tw + P::TW_TOTAL);
+    uint8_t* stage = reinterpret_cast<uint8_t*>(tw + P::TW_TOTAL);            // [FLUSH*Nd] 2-bit codes, one per byte
 
     const int tid = threadIdx.x;
     const int64_t pkt = blockIdx.x / a.ctas_per_packet;
@@ -101,13 +108,37 @@ __global__ void __launch_bounds__(kThreads, 2) rx_demod_kernel(const RxArgs a) {
 
     for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
 
+    // XOR decode (OFDM.py:541-544) is applied per packed 32-bit word at flush time: word w of a
+    // chunk covers codes 16w..16w+15, i.e. data carriers (16w+i) mod Nd -- the same for every chunk
+    const bool use_xor = a.xor2 != nullptr;
+    const int stage_bytes = ((FLUSH * Nd + 15) & ~15) + 16;
+    uint32_t* xorw = reinterpret_cast<uint32_t*>(stage + stage_bytes);       // [FLUSH*Nd/16 + 1]
+    if (use_xor && a.bits != nullptr) {
+        const int wpc = (FLUSH * Nd + 15) >> 4;
+        for (int w = tid; w < wpc; w += NT) {
+            uint32_t word = 0;
+            int c = (16 * w) % Nd;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (16 * w + i < FLUSH * Nd) {
+                    const uint32_t code = a.xor2[c] & 3u;
+                    word |= code << (8 * (i >> 2) + 6 - 2 * (i & 3));      // byte i/4, MSB-first inside the byte
+                }
+                c = (c + 1 == Nd) ? 0 : c + 1;
+            }
+            xorw[w] = word;
+        }
+    }
+
     const float* pkt_base = a.samples + (a.pkt_offset ? a.pkt_offset[pkt] : pkt * a.pkt_stride);
     const int symlen = N + a.cp;
 
     // ---- per-thread constants for phase B
     const int jb = tid % TB, sb = tid / TB;
     float2 w2[PP], u1[PP], u2[PP], G1[PP], G2[PP];
-    int flags[PP];                                      // bit0..1 xor(k) | bit2..3 xor(km) | bit4 k is data | bit5 km is data | bit6 km exists
+    int zo1[PP], zo2[PP], kk[PP];                       // padded smem offsets of Z[k], Z[M-k]; k itself
+    const bool want_bits = a.bits != nullptr;
+    int flags[PP];                                      // bit4 k is a data bin | bit5 km is a data bin | bit6 km exists (k != M/2)
     const float2* Hs = KNOWN_CH ? a.Hs : a.Hs + pkt * K;
     const double slope = KNOWN_CH ? 0.0 : a.slope[pkt];
     const double inv_lp = 1.0 / (double)(L + a.P);
@@ -115,14 +146,17 @@ __global__ void __launch_bounds__(kThreads, 2) rx_demod_kernel(const RxArgs a) {
     for (int pp = 0; pp < PP; ++pp) {
         const int j = jb + pp * TB;
         const int k = j == 0 ? M / 2 : j, km = M - k;
+        kk[pp] = k;
+        zo1[pp] = zpad<P>(k);
+        zo2[pp] = zpad<P>(km);
         float s, c;
         sincospif(2.0f * (float)k / (float)N, &s, &c);
         w2[pp] = make_float2(-s, -c);                   // -j * exp(-2 pi i k / N)
         int f = 0;
-        if (k >= a.lo && k < a.hi) f |= 16 | (a.xor2 ? a.xor2[k - a.lo] & 3 : 0);
+        if (k >= a.lo && k < a.hi) f |= 16;
         if (j != 0) {
             f |= 64;
-            if (km >= a.lo && km < a.hi) f |= 32 | ((a.xor2 ? a.xor2[km - a.lo] & 3 : 0) << 2);
+            if (km >= a.lo && km < a.hi) f |= 32;
         }
         flags[pp] = f;
         if constexpr (!KNOWN_CH) {
@@ -132,9 +166,26 @@ __global__ void __launch_bounds__(kThreads, 2) rx_demod_kernel(const RxArgs a) {
     }
     __syncthreads();
 
+    // phase-A identity of this thread: symbol group ga, lane ta inside the group
+    const int ga = tid / T, ta = tid % T;
+    float2 x[R];
+    auto load_batch = [&](int chunk, int b) {
+        // symbols past the end of the packet are clamped to the last one: their spectra are
+        // computed but never used (phase B only walks valid symbols), and no zero-fill is needed
+        int l = chunk * FLUSH + b * SF + ga;
+        l = l < L ? l : L - 1;
+        load_symbol<P>(x, pkt_base + (int64_t)(a.P + l) * symlen + a.cp, ta);
+    };
+#if GF3_PREFETCH == 1
+    load_batch(c_first, 0);
+#endif
+
     for (int chunk = c_first; chunk < c_last; ++chunk) {
         const int l0 = chunk * FLUSH;
         const int nsym = min(FLUSH, L - l0);
+        if ((nsym * Nd) & 15) {                       // last word of the chunk is partial: its missing codes are 0
+            if (tid < 16) stage[nsym * Nd + tid] = 0;
+        }
         // (re)seed the rotating equaliser taps exactly at the chunk start
 #pragma unroll
         for (int pp = 0; pp < PP; ++pp) {
@@ -154,60 +205,68 @@ __global__ void __launch_bounds__(kThreads, 2) rx_demod_kernel(const RxArgs a) {
 #pragma unroll 1
         for (int b = 0; b < BATCHES; ++b) {
             // ---------------- phase A: FFT of SF symbols
-            {
-                const int g = tid / T, t = tid % T;
-                const int l = l0 + b * SF + g;
-                float2 x[R];
-                if (l < L) {
-                    load_symbol<P>(x, pkt_base + (int64_t)(a.P + l) * symlen + a.cp, t);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < R; ++i) x[i] = make_float2(0.f, 0.f);
-                }
-                fft_forward<P, NT>(x, zbuf + g * MP, tw, t, g);
-            }
+#if GF3_PREFETCH != 1
+            load_batch(chunk, b);
+#endif
+            fft_forward<P, NT>(x, zbuf + ga * MP, tw, ta, ga);
             __syncthreads();
+#if GF3_PREFETCH == 1
+            // prefetch the next batch's samples: the loads fly while phase B computes
+            load_batch(b + 1 < BATCHES ? chunk : chunk + 1, b + 1 < BATCHES ? b + 1 : 0);
+#elif GF3_PREFETCH == 2
+            if (ta == 0) {
+                const int nc = b + 1 < BATCHES ? chunk : chunk + 1, nb = b + 1 < BATCHES ? b + 1 : 0;
+                const int nl = nc * FLUSH + nb * SF + ga;
+                if (nc < c_last && nl < L) {
+                    const float* sp = pkt_base + (int64_t)(a.P + nl) * symlen + a.cp;
+                    const uintptr_t lo16 = reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo16), "r"(N * 4 + 16) : "memory");
+                }
+            }
+#endif
             // ---------------- phase B: untangle, equalise, demap
-#pragma unroll 1
-            for (int it = 0; it < SF / SB; ++it) {
-                const int ls = b * SF + sb + SB * it;          // symbol index inside the chunk
-                const int l = l0 + ls;
-                const float2* zs = zbuf + (sb + SB * it) * MP;
-                float eq_w = 0.f;
-                if constexpr (WANT_EQ && !KNOWN_CH) eq_w = (float)(((double)l + 0.5 * (double)a.P) * inv_lp);
+            // thread <-> PP bin pairs; walks the batch's symbols sb, sb+SB, ... with pointer increments
+            {
+                const int ls0 = b * SF + sb;                                   // first symbol (inside the chunk) of this thread
+                int n_it = (nsym - ls0 + SB - 1) / SB;                          // valid symbols for this thread in this batch
+                n_it = n_it < 0 ? 0 : (n_it > SF / SB ? SF / SB : n_it);
+                const float2* zs = zbuf + sb * MP;
+                uint8_t* st = stage + ls0 * Nd - a.lo;
+                float2* eqp = nullptr;
+                if constexpr (WANT_EQ) eqp = a.eq + ((int64_t)pkt * L + l0 + ls0) * K - 1;
+#pragma unroll 2
+                for (int it = 0; it < n_it; ++it) {
 #pragma unroll
-                for (int pp = 0; pp < PP; ++pp) {
-                    const int j = jb + pp * TB;
-                    const int k = j == 0 ? M / 2 : j, km = M - k;
-                    const float2 z1 = zs[zpad<P>(k)], z2 = zs[zpad<P>(km)];
-                    const float2 s = make_float2(z1.x + z2.x, z1.y - z2.y);    // Z[k] + conj Z[M-k]
-                    const float2 d = make_float2(z1.x - z2.x, z1.y + z2.y);    // Z[k] - conj Z[M-k]
-                    const float2 tt = cmul(w2[pp], d);
-                    const float2 x1 = cadd(s, tt);                             // 2 X[k]
-                    const float2 x2 = make_float2(s.x - tt.x, tt.y - s.y);     // 2 X[M-k] = conj(s - tt)
-                    const float2 y1 = cmul(x1, G1[pp]);
-                    const float2 y2 = cmul(x2, G2[pp]);
-                    if constexpr (!KNOWN_CH) {
-                        G1[pp] = cmul(G1[pp], u1[pp]);
-                        G2[pp] = cmul(G2[pp], u2[pp]);
-                    }
-                    if (l < L) {
+                    for (int pp = 0; pp < PP; ++pp) {
+                        const float2 z1 = zs[zo1[pp]], z2 = zs[zo2[pp]];
+                        const float2 s = make_float2(z1.x + z2.x, z1.y - z2.y);    // Z[k] + conj Z[M-k]
+                        const float2 d = make_float2(z1.x - z2.x, z1.y + z2.y);    // Z[k] - conj Z[M-k]
+                        const float2 tt = cmul(w2[pp], d);
+                        const float2 x1 = cadd(s, tt);                             // 2 X[k]
+                        const float2 x2 = make_float2(s.x - tt.x, tt.y - s.y);     // 2 X[M-k] = conj(s - tt)
+                        const float2 y1 = cmul(x1, G1[pp]);
+                        const float2 y2 = cmul(x2, G2[pp]);
+                        if constexpr (!KNOWN_CH) {
+                            G1[pp] = cmul(G1[pp], u1[pp]);
+                            G2[pp] = cmul(G2[pp], u2[pp]);
+                        }
                         const int f = flags[pp];
-                        if (a.bits) {
+                        if (want_bits) {
                             if (f & 16) {
-                                const unsigned code = ((__float_as_uint(y1.y) >> 31) << 1) | (__float_as_uint(y1.x) >> 31);
-                                stage[ls * Nd + (k - a.lo)] = (uint8_t)(code ^ (f & 3));
+                                const unsigned code = ((__float_as_uint(y1.y) >> 30) & 2u) | (__float_as_uint(y1.x) >> 31);
+                                st[kk[pp]] = (uint8_t)code;
                             }
                             if (f & 32) {
-                                const unsigned code = ((__float_as_uint(y2.y) >> 31) << 1) | (__float_as_uint(y2.x) >> 31);
-                                stage[ls * Nd + (km - a.lo)] = (uint8_t)(code ^ ((f >> 2) & 3));
+                                const unsigned code = ((__float_as_uint(y2.y) >> 30) & 2u) | (__float_as_uint(y2.x) >> 31);
+                                st[M - kk[pp]] = (uint8_t)code;
                             }
                         }
                         if constexpr (WANT_EQ) {
-                            float2* eqp = a.eq + ((int64_t)pkt * L + l) * K;
+                            const int k = kk[pp], km = M - k;
                             float sc1 = 0.5f, sc2 = 0.5f;
                             if constexpr (!KNOWN_CH) {
                                 // |H| = |Hs| + (|He| - |Hs|) w  (OFDM.py:471); G carries conj(Hs) unnormalised
+                                const float eq_w = (float)(((double)(l0 + ls0 + it * SB) + 0.5 * (double)a.P) * inv_lp);
                                 const float2 hs1 = Hs[k - 1], he1 = a.He[pkt * K + k - 1];
                                 const float a1 = sqrtf(hs1.x * hs1.x + hs1.y * hs1.y);
                                 const float e1 = sqrtf(he1.x * he1.x + he1.y * he1.y);
@@ -219,38 +278,44 @@ __global__ void __launch_bounds__(kThreads, 2) rx_demod_kernel(const RxArgs a) {
                                     sc2 = 0.5f / (a2 * (a2 + (e2 - a2) * eq_w));
                                 }
                             }
-                            eqp[k - 1] = make_float2(y1.x * sc1, y1.y * sc1);
-                            if (f & 64) eqp[km - 1] = make_float2(y2.x * sc2, y2.y * sc2);
+                            eqp[k] = make_float2(y1.x * sc1, y1.y * sc1);
+                            if (f & 64) eqp[km] = make_float2(y2.x * sc2, y2.y * sc2);
                         }
                     }
+                    zs += SB * MP;
+                    st += SB * Nd;
+                    if constexpr (WANT_EQ) eqp += (int64_t)SB * K;
                 }
             }
             __syncthreads();
         }
 
         // ---------------- flush: 16 two-bit codes -> one 32-bit word (MSB-first bytes)
-        if (a.bits) {
+        // four codes c0..c3 (one per byte of u) -> (c0<<6 | c1<<4 | c2<<2 | c3) is the top byte of
+        // u * 0x40100401 (no carries: every partial product lands on its own 2-bit field)
+        if (want_bits) {
             const int ncodes = nsym * Nd;
             const int nwords = (ncodes + 15) >> 4;
             uint32_t* out = reinterpret_cast<uint32_t*>(a.bits + pkt * a.bits_stride) + (int64_t)l0 * Nd / 16;
-            const bool last = (l0 + nsym >= L);
-            const int stride_words = (int)(a.bits_stride / 4) - (int)((int64_t)l0 * Nd / 16);
-            const int wtotal = last ? stride_words : nwords;     // last chunk also zeroes the pad
-            for (int w = tid; w < wtotal; w += NT) {
-                uint32_t word = 0;
-                if (w < nwords) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(stage + 16 * w);
-                    uint32_t u[4] = {v.x, v.y, v.z, v.w};
-                    const int rem = ncodes - 16 * w;                  // valid codes in this word
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        uint32_t um = u[m];
-                        if (rem < 4 * (m + 1)) um &= (rem <= 4 * m) ? 0u : (0xFFFFFFFFu >> (8 * (4 * (m + 1) - rem)));
-                        const uint32_t byte = ((um << 6) | (um >> 4) | (um >> 14) | (um >> 24)) & 0xFFu;
-                        word |= byte << (8 * m);
+            for (int w = tid; w < nwords; w += NT) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stage + 16 * w);
+                const uint32_t t0 = v.x * 0x40100401u, t1 = v.y * 0x40100401u, t2 = v.z * 0x40100401u, t3 = v.w * 0x40100401u;
+                uint32_t word = __byte_perm(__byte_perm(t0, t1, 0x0073), __byte_perm(t2, t3, 0x0073), 0x5410);
+                if (use_xor) {
+                    uint32_t xw = xorw[w];
+                    const int r = ncodes - 16 * w;                  // codes in this word (< 16 only for the very last one)
+                    if (r < 16) {                                   // keep the pad bits of a partial word zero
+                        const int fb = r >> 2, rm = r & 3;
+                        const uint32_t m = (fb ? (0xFFFFFFFFu >> (32 - 8 * fb)) : 0u) | (rm ? (((0xFF00u >> (2 * rm)) & 0xFFu) << (8 * fb)) : 0u);
+                        xw &= m;
                     }
+                    word ^= xw;
                 }
                 out[w] = word;
+            }
+            if (l0 + nsym >= L) {                                   // last chunk of the packet: clear the row's pad words
+                const int stride_words = (int)(a.bits_stride / 4) - (int)((int64_t)l0 * Nd / 16);
+                for (int w = nwords + tid; w < stride_words; w += NT) out[w] = 0u;
             }
             __syncthreads();
         }
@@ -413,9 +478,19 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------ launchers
+#ifndef GF3_DEMOD_THREADS
+#define GF3_DEMOD_THREADS 128
+#endif
+// plans whose symbol group already spans >= 128 threads keep 256-thread CTAs (fewer bin pairs,
+// hence less equaliser state, per thread)
+template <class P> struct DemodThreads { static constexpr int value = P::T >= 128 ? 256 : GF3_DEMOD_THREADS; };
+
 template <class P, bool KNOWN_CH, bool WANT_EQ>
 static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaStream_t st) {
-    constexpr int SF = kThreads / P::T, FLUSH = SF > 16 ? SF : 16;
+    // CTA size: one symbol group needs P::T threads; smaller CTAs (more of them per SM) decorrelate
+    // the load / FFT / equalise phases of co-resident CTAs
+    constexpr int NT = (P::T > DemodThreads<P>::value) ? P::T : DemodThreads<P>::value;
+    constexpr int SF = NT / P::T, FLUSH = SF > 16 ? SF : 16;
     const int Nd = a.hi - a.lo;
     a.chunks_per_packet = (a.L + FLUSH - 1) / FLUSH;
     // enough CTAs for ~8 waves of 2 CTAs/SM, otherwise one CTA walks the whole packet
@@ -425,13 +500,14 @@ static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaS
     if (split > a.chunks_per_packet) split = a.chunks_per_packet;
     a.chunks_per_cta = (int)((a.chunks_per_packet + split - 1) / split);
     a.ctas_per_packet = (a.chunks_per_packet + a.chunks_per_cta - 1) / a.chunks_per_cta;
-    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (((size_t)FLUSH * Nd + 15) & ~(size_t)15) + 16;
-    auto kern = rx_demod_kernel<P, KNOWN_CH, WANT_EQ>;
+    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (((size_t)FLUSH * Nd + 15) & ~(size_t)15) + 16
+                        + (((size_t)FLUSH * Nd + 15) / 16 + 1) * sizeof(uint32_t);
+    auto kern = rx_demod_kernel<P, NT, KNOWN_CH, WANT_EQ>;
     GF3_REQUIRE(smem <= 227 * 1024, "rx_demod: %zu bytes of shared memory needed (> 227 KB)", smem);
     GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = n_packets * a.ctas_per_packet;
     GF3_REQUIRE(grid <= 0x7fffffff, "rx_demod: grid too large");
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
+    kern<<<(unsigned)grid, NT, smem, st>>>(a);
     GF3_LAUNCH_CHECK();
     return GF3_OK;
 }

@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(HERE), "lib", "libgf3b200.so")
+# GF3_LIB_PATH selects an alternate build of the same library (kernel-tuning experiments only)
+LIB_PATH = os.environ.get("GF3_LIB_PATH") or os.path.join(os.path.dirname(HERE), "lib", "libgf3b200.so")
 
 GF3_OK, GF3_ERR_INVALID, GF3_ERR_CUDA, GF3_ERR_NODEVICE = 0, -1, -2, -3
 
