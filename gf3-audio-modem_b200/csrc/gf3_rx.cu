@@ -361,22 +361,49 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
 
     for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
 
-    // ---- 1. time-domain sums of the pilot symbols
-    for (int col = tid; col < 2 * M; col += NT) {
-        const int blk = col / M, m = col % M;
-        const float* s0 = pkt_base + (int64_t)(blk ? a.P + a.L : 0) * symlen + a.cp + 2 * m;
-        float2 acc = make_float2(0.f, 0.f);
-        const bool al = (reinterpret_cast<uintptr_t>(s0) & 7) == 0 && (symlen % 2 == 0);
+    // ---- 1. time-domain sums of the pilot symbols (pure streaming: keep many 16-byte loads in flight)
+    {
+        const float* blk0 = pkt_base + a.cp;
+        const float* blk1 = pkt_base + (int64_t)(a.P + a.L) * symlen + a.cp;
+        const bool al16 = ((reinterpret_cast<uintptr_t>(blk0) | reinterpret_cast<uintptr_t>(blk1)) & 15) == 0 && (symlen % 4 == 0);
+        if (al16) {
+            constexpr int U = 10;
+            for (int q = tid; q < 2 * (N / 4); q += NT) {          // float4 column q of block q / (N/4)
+                const int blk = q / (N / 4), c4 = q % (N / 4);
+                const float* s0 = (blk ? blk1 : blk0) + 4 * c4;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p0 = 0; p0 < a.P; p0 += U) {
+                    float4 v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int p = p0 + u < a.P ? p0 + u : a.P - 1;
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(s0 + (int64_t)p * symlen));
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (p0 + u < a.P) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+                }
+                *reinterpret_cast<float4*>(&avg[blk * M + 2 * c4]) = acc;
+            }
+        } else {
+            for (int col = tid; col < 2 * M; col += NT) {
+                const int blk = col / M, m = col % M;
+                const float* s0 = (blk ? blk1 : blk0) + 2 * m;
+                float2 acc = make_float2(0.f, 0.f);
+                const bool al = (reinterpret_cast<uintptr_t>(s0) & 7) == 0 && (symlen % 2 == 0);
 #pragma unroll 4
-        for (int p = 0; p < a.P; ++p) {
-            const float* s = s0 + (int64_t)p * symlen;
-            float2 v;
-            if (al) v = ldg_stream2(s);
-            else { v.x = ldg_stream1(s); v.y = ldg_stream1(s + 1); }
-            acc.x += v.x;
-            acc.y += v.y;
+                for (int p = 0; p < a.P; ++p) {
+                    const float* s = s0 + (int64_t)p * symlen;
+                    float2 v;
+                    if (al) v = ldg_stream2(s);
+                    else { v.x = ldg_stream1(s); v.y = ldg_stream1(s + 1); }
+                    acc.x += v.x;
+                    acc.y += v.y;
+                }
+                avg[col] = acc;
+            }
         }
-        avg[col] = acc;
     }
     __syncthreads();
 
@@ -396,6 +423,9 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
     __syncthreads();
 
     // ---- 3. untangle, divide by the known symbol, write Hs/He, phases to smem
+    // Only phases inside the fit window are needed: np.unwrap's jumps before the window shift
+    // unwrap(He) - unwrap(Hs) by a constant there, which does not change the fitted slope.
+    const int flo = max(0, min(a.fit_lo, K)), fhi = max(flo, min(a.fit_hi, K));
     const float invP = 0.5f / (float)a.P;              // x1/x2 below are 2X
     for (int item = tid; item < 2 * (M / 2); item += NT) {
         const int blk = item / (M / 2), j = item % (M / 2);
@@ -416,27 +446,26 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
             float2 h = cmul(x1, cconj(kn));
             h.x *= invP; h.y *= invP;
             Hout[k - 1] = h;
-            phi[blk * K + k - 1] = atan2((double)h.y, (double)h.x);
+            if (k - 1 >= flo && k - 1 < fhi) phi[blk * K + k - 1] = atan2((double)h.y, (double)h.x);
         }
         if (j != 0) {
             const float2 kn = a.known[km - 1];
             float2 h = cmul(x2, cconj(kn));
             h.x *= invP; h.y *= invP;
             Hout[km - 1] = h;
-            phi[blk * K + km - 1] = atan2((double)h.y, (double)h.x);
+            if (km - 1 >= flo && km - 1 < fhi) phi[blk * K + km - 1] = atan2((double)h.y, (double)h.x);
         }
     }
     __syncthreads();
 
     // ---- 4. unwrap both phase rows, difference, LS slope over [fit_lo, fit_hi) (0-based carrier index)
-    const int flo = max(0, min(a.fit_lo, K)), fhi = max(flo, min(a.fit_hi, K));
     const int nfit = fhi - flo;
-    constexpr int SEG = (K + NT - 1) / NT;
-    const int i0 = tid * SEG, i1 = min(K, i0 + SEG);
+    const int SEG = (nfit + NT - 1) / NT;
+    const int i0 = flo + tid * SEG, i1 = min(fhi, i0 + SEG);
     const double PI = 3.14159265358979323846;
     // np.unwrap: a jump dd > pi subtracts 2 pi, dd < -pi adds 2 pi, |dd| == pi is left alone
     int local = 0;
-    for (int i = max(i0, 1); i < i1; ++i) {
+    for (int i = max(i0, flo + 1); i < i1; ++i) {
         const double de = phi[K + i] - phi[K + i - 1], ds = phi[i] - phi[i - 1];
         local += (de > PI ? -1 : de < -PI ? 1 : 0) - (ds > PI ? -1 : ds < -PI ? 1 : 0);
     }
@@ -455,7 +484,7 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
     double sxy = 0.0;
     int run = prefix;
     for (int i = i0; i < i1; ++i) {
-        if (i >= 1) {
+        if (i >= flo + 1) {
             const double de = phi[K + i] - phi[K + i - 1], ds = phi[i] - phi[i - 1];
             run += (de > PI ? -1 : de < -PI ? 1 : 0) - (ds > PI ? -1 : ds < -PI ? 1 : 0);
         }
