@@ -32,44 +32,112 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ float2 mul_nj(float2 a) { return make_float2(a.y, -a.x); }   // a * (-j)
 
-// cos(k*pi/16), k = 0..8 (exact to double precision, rounded to float at use)
-__host__ __device__ constexpr double cos_pi16_q(int k) {
-    return k == 0 ? 1.0
-         : k == 1 ? 0.98078528040323044913
-         : k == 2 ? 0.92387953251128675613
-         : k == 3 ? 0.83146961230254523708
-         : k == 4 ? 0.70710678118654752440
-         : k == 5 ? 0.55557023301960222474
-         : k == 6 ? 0.38268343236508977173
-         : k == 7 ? 0.19509032201612826785
-                  : 0.0;
-}
-// cos(i*pi/16) for any integer i
-__host__ __device__ constexpr double cos_pi16(int i) {
-    int k = ((i % 32) + 32) % 32;
-    return k <= 8 ? cos_pi16_q(k) : k <= 16 ? -cos_pi16_q(16 - k) : k <= 24 ? -cos_pi16_q(k - 16) : cos_pi16_q(32 - k);
-}
-__host__ __device__ constexpr double sin_pi16(int i) { return cos_pi16(i - 8); }
+// ---------------------------------------------------------------- packed f32x2 arithmetic
+// Blackwell issues FFMA2 / FADD2 / FMUL2 (two fp32 lanes per instruction).  On B200 a scalar
+// 3-register FFMA runs at half rate while FFMA2 reaches the full 128 FMA/clk/SM, and FADD2 / FMUL2
+// take half the issue slots of their scalar forms (tools/microbench/f32x2.cu).  The data-symbol
+// kernel therefore carries TWO independent half-size FFTs of a symbol in the two lanes.
+// ptxas folds the negations below into operand modifiers and uses the scalar-broadcast operand form
+// for (s, s) pairs.
+typedef unsigned long long pk64;
+__device__ __forceinline__ pk64 pk_pack(float2 a) { pk64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ float2 pk_unpack(pk64 v) { float2 r; asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) { pk64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b))); return pk_unpack(d); }
+__device__ __forceinline__ float2 pk_sub(float2 a, float2 b) { pk64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b))); return pk_unpack(d); }
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) { pk64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b))); return pk_unpack(d); }
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) { pk64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b)), "l"(pk_pack(c))); return pk_unpack(d); }
+__device__ __forceinline__ float2 pk_neg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 pk_bc(float s) { return make_float2(s, s); }
 
-// a * exp(-j * IDX * pi/16)   (IDX compile-time; multiples of 45 degrees need no general multiply)
-template <int IDX>
-__device__ __forceinline__ float2 mul_w32(float2 a) {
-    constexpr int k = ((IDX % 32) + 32) % 32;
-    if constexpr (k == 0) return a;
-    else if constexpr (k == 8) return make_float2(a.y, -a.x);
-    else if constexpr (k == 16) return make_float2(-a.x, -a.y);
-    else if constexpr (k == 24) return make_float2(-a.y, a.x);
-    else if constexpr (k % 8 == 4) {
+// two complex numbers, structure-of-arrays: lane x and lane y are independent
+struct cpk { float2 re, im; };
+__device__ __forceinline__ cpk cadd(cpk a, cpk b) { return cpk{pk_add(a.re, b.re), pk_add(a.im, b.im)}; }
+__device__ __forceinline__ cpk csub(cpk a, cpk b) { return cpk{pk_sub(a.re, b.re), pk_sub(a.im, b.im)}; }
+__device__ __forceinline__ cpk mul_nj(cpk a) { return cpk{a.im, pk_neg(a.re)}; }
+// both lanes times the same complex scalar w
+__device__ __forceinline__ cpk cmul_s(cpk a, float2 w) {
+    const float2 wr = pk_bc(w.x), wi = pk_bc(w.y);
+    return cpk{pk_fma(pk_neg(a.im), wi, pk_mul(a.re, wr)), pk_fma(a.re, wi, pk_mul(a.im, wr))};
+}
+// lane-wise complex product
+__device__ __forceinline__ cpk cmul(cpk a, cpk b) {
+    return cpk{pk_fma(pk_neg(a.im), b.im, pk_mul(a.re, b.re)), pk_fma(a.re, b.im, pk_mul(a.im, b.re))};
+}
+
+// Compile-time cos / sin of 2*pi*num/den (exact quadrant reduction on the integers, Taylor series
+// on [0, pi/4]); evaluated in double, rounded to float where used, so in-register twiddles become
+// instruction immediates.
+__host__ __device__ constexpr double cx_taylor_sin(double x) {
+    double term = x, sum = x;
+    for (int k = 1; k < 12; ++k) { term *= -x * x / ((2 * k) * (2 * k + 1)); sum += term; }
+    return sum;
+}
+__host__ __device__ constexpr double cx_taylor_cos(double x) {
+    double term = 1.0, sum = 1.0;
+    for (int k = 1; k < 12; ++k) { term *= -x * x / ((2 * k - 1) * (2 * k)); sum += term; }
+    return sum;
+}
+// first-quadrant helper: angle = (r/den) * pi/2 with 0 <= r < den
+__host__ __device__ constexpr double cx_q_cos(long long r, long long den) {
+    const double hp = 1.57079632679489661923;
+    return 2 * r <= den ? cx_taylor_cos(hp * (double)r / (double)den) : cx_taylor_sin(hp * (double)(den - r) / (double)den);
+}
+__host__ __device__ constexpr double cx_q_sin(long long r, long long den) {
+    const double hp = 1.57079632679489661923;
+    return 2 * r <= den ? cx_taylor_sin(hp * (double)r / (double)den) : cx_taylor_cos(hp * (double)(den - r) / (double)den);
+}
+__host__ __device__ constexpr double cx_cos2pi(long long num, long long den) {
+    const long long n = ((num % den) + den) % den, q = (4 * n) / den, r = 4 * n - q * den;
+    return q == 0 ? cx_q_cos(r, den) : q == 1 ? -cx_q_sin(r, den) : q == 2 ? -cx_q_cos(r, den) : cx_q_sin(r, den);
+}
+__host__ __device__ constexpr double cx_sin2pi(long long num, long long den) {
+    const long long n = ((num % den) + den) % den, q = (4 * n) / den, r = 4 * n - q * den;
+    return q == 0 ? cx_q_sin(r, den) : q == 1 ? cx_q_cos(r, den) : q == 2 ? -cx_q_sin(r, den) : -cx_q_cos(r, den);
+}
+
+// a * exp(-2*pi*j * NUM/DEN)   (compile-time; multiples of 45 degrees need no general multiply)
+template <int NUM, int DEN>
+__device__ __forceinline__ float2 mul_w(float2 a) {
+    constexpr int n = ((NUM % DEN) + DEN) % DEN;
+    if constexpr (n == 0) return a;
+    else if constexpr (4 * n == DEN) return make_float2(a.y, -a.x);        // -j
+    else if constexpr (2 * n == DEN) return make_float2(-a.x, -a.y);       // -1
+    else if constexpr (4 * n == 3 * DEN) return make_float2(-a.y, a.x);    // +j
+    else if constexpr ((8 * n) % DEN == 0) {
         constexpr float h = 0.70710678118654752440f;
-        // (c - js) with |c| = |s| = sqrt(1/2)
-        constexpr float c = (k == 4 || k == 28) ? h : -h;
-        constexpr float s = (k == 4 || k == 12) ? h : -h;
-        return make_float2(c * a.x + s * a.y, c * a.y - s * a.x);
+        constexpr int o = (8 * n) / DEN;                                   // 1, 3, 5, 7
+        constexpr float c = (o == 1 || o == 7) ? h : -h;                   // cos
+        constexpr float sn = (o == 1 || o == 3) ? h : -h;                  // sin
+        return make_float2(c * a.x + sn * a.y, c * a.y - sn * a.x);
     } else {
-        constexpr float c = (float)cos_pi16(k);
-        constexpr float s = (float)sin_pi16(k);
-        return make_float2(fmaf(c, a.x, s * a.y), fmaf(c, a.y, -s * a.x));
+        constexpr float c = (float)cx_cos2pi(n, DEN);
+        constexpr float sn = (float)cx_sin2pi(n, DEN);
+        return make_float2(fmaf(c, a.x, sn * a.y), fmaf(c, a.y, -sn * a.x));
+    }
+}
+
+template <int NUM, int DEN>
+__device__ __forceinline__ cpk mul_w(cpk a) {
+    constexpr int n = ((NUM % DEN) + DEN) % DEN;
+    if constexpr (n == 0) return a;
+    else if constexpr (4 * n == DEN) return cpk{a.im, pk_neg(a.re)};                // -j
+    else if constexpr (2 * n == DEN) return cpk{pk_neg(a.re), pk_neg(a.im)};        // -1
+    else if constexpr (4 * n == 3 * DEN) return cpk{pk_neg(a.im), a.re};            // +j
+    else if constexpr ((8 * n) % DEN == 0) {
+        constexpr float h = 0.70710678118654752440f;
+        constexpr int o = (8 * n) / DEN;
+        constexpr float c = (o == 1 || o == 7) ? h : -h;
+        constexpr float sn = (o == 1 || o == 3) ? h : -h;
+        // (c re + s im, c im - s re) with |c| = |s|
+        const float2 p = (c * sn > 0.f) ? pk_add(a.re, a.im) : pk_sub(a.re, a.im);   // re + (s/c) im
+        const float2 q = (c * sn > 0.f) ? pk_sub(a.im, a.re) : pk_add(a.im, a.re);   // im - (s/c) re
+        return cpk{pk_mul(p, pk_bc(c)), pk_mul(q, pk_bc(c))};
+    } else {
+        constexpr float c = (float)cx_cos2pi(n, DEN);
+        constexpr float sn = (float)cx_sin2pi(n, DEN);
+        return cpk{pk_fma(a.im, pk_bc(sn), pk_mul(a.re, pk_bc(c))), pk_fma(a.re, pk_bc(-sn), pk_mul(a.im, pk_bc(c)))};
     }
 }
 
@@ -77,21 +145,22 @@ __device__ __forceinline__ float2 mul_w32(float2 a) {
 // Forward DFT (e^{-2 pi i nk/R}), natural order in and out, on v[0..R).
 template <int R> struct Dft;
 
+// (V = float2: one complex number; V = cpk: two independent ones in the f32x2 lanes)
 template <> struct Dft<1> {
-    static __device__ __forceinline__ void run(float2*) {}
+    template <class V> static __device__ __forceinline__ void run(V*) {}
 };
 template <> struct Dft<2> {
-    static __device__ __forceinline__ void run(float2* v) {
-        float2 a = v[0], b = v[1];
+    template <class V> static __device__ __forceinline__ void run(V* v) {
+        V a = v[0], b = v[1];
         v[0] = cadd(a, b);
         v[1] = csub(a, b);
     }
 };
 template <> struct Dft<4> {
-    static __device__ __forceinline__ void run(float2* v) {
-        float2 s02 = cadd(v[0], v[2]), d02 = csub(v[0], v[2]);
-        float2 s13 = cadd(v[1], v[3]), d13 = csub(v[1], v[3]);
-        float2 jd = make_float2(d13.y, -d13.x);   // -j * d13
+    template <class V> static __device__ __forceinline__ void run(V* v) {
+        V s02 = cadd(v[0], v[2]), d02 = csub(v[0], v[2]);
+        V s13 = cadd(v[1], v[3]), d13 = csub(v[1], v[3]);
+        V jd = mul_nj(d13);   // -j * d13
         v[0] = cadd(s02, s13);
         v[1] = cadd(d02, jd);
         v[2] = csub(s02, s13);
@@ -99,36 +168,39 @@ template <> struct Dft<4> {
     }
 };
 // Cooley-Tukey in registers: R = A*B, n = B*n1 + n2, k = k1 + A*k2.
-template <int R, int A, int B>
-__device__ __forceinline__ void dft_ct(float2* v) {
-    static_assert(A * B == R && 32 % R == 0, "bad split");
-    float2 y[B][A];
+template <int R, int A, int B, class V>
+__device__ __forceinline__ void dft_ct(V* v) {
+    static_assert(A * B == R, "bad split");
+    V y[B][A];
     static_for<B>([&](auto n2c) {
         constexpr int n2 = decltype(n2c)::value;
-        float2 tmp[A];
+        V tmp[A];
         static_for<A>([&](auto n1c) { constexpr int n1 = decltype(n1c)::value; tmp[n1] = v[B * n1 + n2]; });
         Dft<A>::run(tmp);
         static_for<A>([&](auto k1c) {
             constexpr int k1 = decltype(k1c)::value;
-            y[n2][k1] = mul_w32<n2 * k1 * (32 / R)>(tmp[k1]);
+            y[n2][k1] = mul_w<n2 * k1, R>(tmp[k1]);
         });
     });
     static_for<A>([&](auto k1c) {
         constexpr int k1 = decltype(k1c)::value;
-        float2 tmp[B];
+        V tmp[B];
         static_for<B>([&](auto n2c) { constexpr int n2 = decltype(n2c)::value; tmp[n2] = y[n2][k1]; });
         Dft<B>::run(tmp);
         static_for<B>([&](auto k2c) { constexpr int k2 = decltype(k2c)::value; v[k1 + A * k2] = tmp[k2]; });
     });
 }
 template <> struct Dft<8> {
-    static __device__ __forceinline__ void run(float2* v) { dft_ct<8, 2, 4>(v); }
+    template <class V> static __device__ __forceinline__ void run(V* v) { dft_ct<8, 2, 4, V>(v); }
 };
 template <> struct Dft<16> {
-    static __device__ __forceinline__ void run(float2* v) { dft_ct<16, 4, 4>(v); }
+    template <class V> static __device__ __forceinline__ void run(V* v) { dft_ct<16, 4, 4, V>(v); }
 };
 template <> struct Dft<32> {
-    static __device__ __forceinline__ void run(float2* v) { dft_ct<32, 4, 8>(v); }
+    template <class V> static __device__ __forceinline__ void run(V* v) { dft_ct<32, 4, 8, V>(v); }
+};
+template <> struct Dft<64> {
+    template <class V> static __device__ __forceinline__ void run(V* v) { dft_ct<64, 8, 8, V>(v); }
 };
 
 // ---------------------------------------------------------------- FFT plans
@@ -138,7 +210,7 @@ template <int LOGN_, int R_, int NPASS_, int R0_, int R1_, int R2_>
 struct FftPlanT {
     static constexpr int LOGN = LOGN_, N = 1 << LOGN_, M = N / 2, R = R_, T = M / R_;
     static constexpr int NPASS = NPASS_;
-    static constexpr int LOGPAD = (R_ == 32 ? 5 : R_ == 16 ? 4 : 3);
+    static constexpr int LOGPAD = (R_ == 64 ? 6 : R_ == 32 ? 5 : R_ == 16 ? 4 : 3);
     static constexpr int MP = M + (M >> LOGPAD);   // padded complex points per symbol
     __host__ __device__ static constexpr int rad(int p) { return p == 0 ? R0_ : p == 1 ? R1_ : R2_; }
     __host__ __device__ static constexpr int ns(int p) { return p == 0 ? 1 : p == 1 ? R0_ : R0_ * R1_; }
@@ -159,6 +231,9 @@ GF3_PLAN(9, 16, 2, 16, 16, 1)    // N=512   M=256   T=16
 GF3_PLAN(10, 32, 2, 32, 16, 1)   // N=1024  M=512   T=16
 GF3_PLAN(11, 32, 2, 32, 32, 1)   // N=2048  M=1024  T=32
 GF3_PLAN(12, 16, 3, 16, 16, 8)   // N=4096  M=2048  T=128
+// N=4096 with one warp per symbol: 64 points per thread, 64 x 32, a single exchange and only
+// __syncwarp between passes (used by the data-symbol kernel; needs ~200 registers per thread)
+struct FftPlanWarp12 : FftPlanT<12, 64, 2, 64, 32, 1> {};
 #undef GF3_PLAN
 
 template <class P>
@@ -176,27 +251,38 @@ __device__ __forceinline__ void group_sync(int grp) {
     }
 }
 
+// Padded offset of a compile-time stride: for S a multiple of 2^LOGPAD,
+//   zpad(b + i*S) = zpad(b) + i*(S + (S >> LOGPAD))          (no carry between the two terms),
+// and for S == 1 with b a multiple of 2^LOGPAD and i < 2^LOGPAD, zpad(b + i) = zpad(b) + i.
+// Folding this by hand keeps every shared-memory access of a pass at base + immediate.
+template <class P, int S>
+__host__ __device__ constexpr int zstride() {
+    static_assert(S == 1 || S % (1 << P::LOGPAD) == 0, "stride must be 1 or a multiple of the padding period");
+    return S == 1 ? 1 : S + (S >> P::LOGPAD);
+}
+
 // One Stockham pass.  x[q*RAD + i]: thread-local data; zs: this symbol's padded smem buffer;
 // tw: twiddle table in smem; t: thread index within the symbol group.
 template <class P, int NTHREADS, int PASS>
 __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__ zs,
                                          const float2* __restrict__ tw, int t, int grp) {
     constexpr int RAD = P::rad(PASS), NS = P::ns(PASS), Q = P::R / RAD, STRIDE = P::M / RAD;
+    static_assert(NS != 1 || RAD == (1 << P::LOGPAD), "first pass radix must equal the padding period");
     if constexpr (PASS > 0) {
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
-            const int j = t + q * P::T;
+            const float2* src = zs + zpad<P>(t + q * P::T);
             static_for<RAD>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
-                x[q * RAD + i] = zs[zpad<P>(j + i * STRIDE)];
+                x[q * RAD + i] = src[i * zstride<P, STRIDE>()];
             });
         });
-        const float2* twp = tw + P::tw_off(PASS);
+        const float2* twp = tw + P::tw_off(PASS) + t;
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             static_for<RAD - 1>([&](auto ic) {
                 constexpr int i = decltype(ic)::value + 1;
-                x[q * RAD + i] = cmul(x[q * RAD + i], twp[(q * (RAD - 1) + (i - 1)) * P::T + t]);
+                x[q * RAD + i] = cmul(x[q * RAD + i], twp[(q * (RAD - 1) + (i - 1)) * P::T]);
             });
         });
         group_sync<P, NTHREADS>(grp);   // every thread of the symbol has read before anyone overwrites
@@ -209,9 +295,10 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
         constexpr int q = decltype(qc)::value;
         const int j = t + q * P::T;
         const int base = (j / NS) * (NS * RAD) + (j % NS);
+        float2* dst = zs + zpad<P>(base);
         static_for<RAD>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
-            zs[zpad<P>(base + i * NS)] = x[q * RAD + i];
+            dst[i * zstride<P, NS>()] = x[q * RAD + i];
         });
     });
     group_sync<P, NTHREADS>(grp);
@@ -225,6 +312,103 @@ __device__ __forceinline__ void fft_forward(float2 (&x)[P::R], float2* __restric
     fft_pass<P, NTHREADS, 0>(x, zs, tw, t, grp);
     fft_pass<P, NTHREADS, 1>(x, zs, tw, t, grp);
     if constexpr (P::NPASS > 2) fft_pass<P, NTHREADS, 2>(x, zs, tw, t, grp);
+}
+
+// ---------------------------------------------------------------- packed (two-lane) plans
+// N real samples -> M = N/2 complex points -> one radix-2 decimation-in-frequency stage in scalar
+// arithmetic (u = z[h] + z[h+H], v = (z[h] - z[h+H]) W_M^h) -> two H = M/2 point FFTs, U and V,
+// carried in the two f32x2 lanes through the same Stockham passes.  U[k] = Z[2k], V[k] = Z[2k+1].
+// Shared-memory entries are float4 (U.re, V.re, U.im, V.im).
+template <int LOGN_, int R_, int NPASS_, int R0_, int R1_, int R2_>
+struct PkPlanT {
+    static constexpr int LOGN = LOGN_, N = 1 << LOGN_, M = N / 2, H = M / 2, R = R_, T = H / R_;
+    static constexpr int NPASS = NPASS_;
+    static constexpr int LOGPAD = (R_ == 32 ? 5 : R_ == 16 ? 4 : 3);
+    static constexpr int HP = H + (H >> LOGPAD);      // padded float4 entries per symbol
+    __host__ __device__ static constexpr int rad(int p) { return p == 0 ? R0_ : p == 1 ? R1_ : R2_; }
+    __host__ __device__ static constexpr int ns(int p) { return p == 0 ? 1 : p == 1 ? R0_ : R0_ * R1_; }
+    static constexpr int TWD = H;                     // first-stage twiddles W_M^h, h < H
+    static constexpr int TW1 = (R_ / R1_) * (R1_ - 1) * T;
+    static constexpr int TW2 = NPASS_ > 2 ? (R_ / R2_) * (R2_ - 1) * T : 0;
+    __host__ __device__ static constexpr int tw_off(int p) { return p <= 1 ? TWD : TWD + TW1; }
+    static constexpr int TW_TOTAL = TWD + TW1 + TW2;
+    static_assert(R0_ == R_ && R0_ * R1_ * R2_ == H, "radices must multiply to H and start with R");
+};
+struct PkPlan10 : PkPlanT<10, 16, 2, 16, 16, 1> {};   // N=1024: H=256,  T=16 (half warp per symbol)
+struct PkPlan12 : PkPlanT<12, 16, 3, 16, 16, 4> {};   // N=4096: H=1024, T=64 (two warps per symbol)
+
+template <class P> struct PkPad {   // adapter so zpad / zstride work on entry indices of a packed plan
+    static constexpr int LOGPAD = P::LOGPAD;
+};
+
+template <class P, int NTHREADS, int PASS>
+__device__ __forceinline__ void pk_fft_pass(cpk (&x)[P::R], float4* __restrict__ zs,
+                                            const float2* __restrict__ tw, int t, int grp) {
+    constexpr int RAD = P::rad(PASS), NS = P::ns(PASS), Q = P::R / RAD, STRIDE = P::H / RAD;
+    static_assert(NS != 1 || RAD == (1 << P::LOGPAD), "first pass radix must equal the padding period");
+    if constexpr (PASS > 0) {
+        static_for<Q>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            const float4* src = zs + zpad<P>(t + q * P::T);
+            static_for<RAD>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                const float4 e = src[i * zstride<P, STRIDE>()];
+                x[q * RAD + i] = cpk{make_float2(e.x, e.y), make_float2(e.z, e.w)};
+            });
+        });
+        const float2* twp = tw + P::tw_off(PASS) + t;
+        static_for<Q>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            static_for<RAD - 1>([&](auto ic) {
+                constexpr int i = decltype(ic)::value + 1;
+                x[q * RAD + i] = cmul_s(x[q * RAD + i], twp[(q * (RAD - 1) + (i - 1)) * P::T]);
+            });
+        });
+        group_sync<P, NTHREADS>(grp);
+    }
+    static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        Dft<RAD>::run(&x[q * RAD]);
+    });
+    static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        const int j = t + q * P::T;
+        const int base = (j / NS) * (NS * RAD) + (j % NS);
+        float4* dst = zs + zpad<P>(base);
+        static_for<RAD>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const cpk v = x[q * RAD + i];
+            dst[i * zstride<P, NS>()] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y);
+        });
+    });
+    group_sync<P, NTHREADS>(grp);
+}
+
+// Both half-size FFTs of one symbol.  On entry x[i] = (u, v)[t + i*T]; on exit the natural-order
+// spectra U, V sit in zs (padded entry indexing).
+template <class P, int NTHREADS>
+__device__ __forceinline__ void pk_fft_forward(cpk (&x)[P::R], float4* __restrict__ zs,
+                                               const float2* __restrict__ tw, int t, int grp) {
+    pk_fft_pass<P, NTHREADS, 0>(x, zs, tw, t, grp);
+    pk_fft_pass<P, NTHREADS, 1>(x, zs, tw, t, grp);
+    if constexpr (P::NPASS > 2) pk_fft_pass<P, NTHREADS, 2>(x, zs, tw, t, grp);
+}
+
+template <class P>
+inline void fill_pk_twiddles(float2* out) {
+    const double PI2 = 2.0 * 3.14159265358979323846;
+    for (int h = 0; h < P::H; ++h) out[h] = make_float2((float)cos(-PI2 * h / P::M), (float)sin(-PI2 * h / P::M));
+    for (int pass = 1; pass < P::NPASS; ++pass) {
+        const int RAD = P::rad(pass), NS = P::ns(pass), Q = P::R / RAD;
+        float2* o = out + P::tw_off(pass);
+        for (int q = 0; q < Q; ++q)
+            for (int i = 1; i < RAD; ++i)
+                for (int t = 0; t < P::T; ++t) {
+                    const int j = t + q * P::T;
+                    const double ang = -PI2 * (double)((j % NS) * i) / (double)(NS * RAD);
+                    o[(q * (RAD - 1) + (i - 1)) * P::T + t] = make_float2((float)cos(ang), (float)sin(ang));
+                }
+    }
 }
 
 // Host-side: fill the twiddle table of plan P (double precision, rounded to float).

@@ -19,7 +19,13 @@ constexpr int kThreads = 256;
 //   1 = loads issued into registers before the equaliser phase
 //   2 = one bulk L2 prefetch per symbol (cp.async.bulk.prefetch.L2, TMA engine, no registers)
 #ifndef GF3_PREFETCH
-#define GF3_PREFETCH 0
+#define GF3_PREFETCH (-1)      // -1: per-plan default (see rx_demod_kernel)
+#endif
+#ifndef GF3_PK_L2_PREFETCH
+#define GF3_PK_L2_PREFETCH 1
+#endif
+#ifndef GF3_PREFETCH_WARP64
+#define GF3_PREFETCH_WARP64 0
 #endif
 constexpr float kPi = 3.14159265358979323846f;
 
@@ -37,6 +43,7 @@ struct RxArgs {
     int64_t pkt_stride;          // (2P+L)(N+cp), used when pkt_offset == null
     int cp, lo, hi, P, L;
     int chunks_per_packet, chunks_per_cta, ctas_per_packet;
+    int flush;                   // symbols per flush chunk
 };
 
 // streaming 8-byte load that does not pollute L1
@@ -67,6 +74,14 @@ __device__ __forceinline__ void load_symbol(float2 (&x)[P::R], const float* __re
     }
 }
 
+// 128-bit shared-memory load that the compiler may not split into (bank-conflicting) 32-bit loads
+__device__ __forceinline__ float4 lds128(const float4* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 // exp(-j * a) for a double-precision phase a (reduced in double, evaluated in float)
 __device__ __forceinline__ float2 expmj(double a) {
     const double inv2pi = 0.15915494309189533577;
@@ -83,16 +98,22 @@ __device__ __forceinline__ float2 expmj(double a) {
 //   phase B: thread <-> bin pair (k, M-k): real-FFT untangling, equaliser, demap -> 2-bit codes
 //   flush  : 16 codes -> one 32-bit word of MSB-first packed bits, coalesced store
 // ------------------------------------------------------------------------------------------
-template <class P, int NT, bool KNOWN_CH, bool WANT_EQ>
-__global__ void __launch_bounds__(NT, 512 / NT) rx_demod_kernel(const RxArgs a) {
+template <class P, int NT, int MINB, bool KNOWN_CH, bool WANT_EQ>
+__global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
     constexpr int T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP;
     constexpr int SF = NT / T;                        // symbols per FFT batch
-    constexpr int FLUSH = SF > 16 ? SF : 16;          // symbols per packed-bit flush (32*Nd bits: word aligned)
-    constexpr int BATCHES = FLUSH / SF;
+    // symbols per packed-bit flush: a multiple of SF with FLUSH*Nd % 16 == 0, so every chunk starts
+    // on a 32-bit word of the packet's bit stream (chosen by the launcher)
+    const int FLUSH = a.flush;
+    const int BATCHES = FLUSH / SF;
     constexpr int TB = (M / 2 < NT) ? M / 2 : NT;     // threads per symbol in phase B
     constexpr int SB = NT / TB;                       // symbols handled concurrently in phase B
     constexpr int PP = (M / 2) / TB;                  // bin pairs per thread
     constexpr int K = M - 1;
+    // multi-warp symbol groups (N = 4096) have few loads per thread in flight and only two CTAs per
+    // SM: issue the next batch's loads before the equaliser phase.  Half-warp groups (R = 32) have
+    // no registers to spare for that and four CTAs per SM already overlap.
+    constexpr int PREFETCH = (GF3_PREFETCH >= 0) ? GF3_PREFETCH : (T >= 128 ? 1 : (R >= 64 ? GF3_PREFETCH_WARP64 : 0));
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* zbuf = reinterpret_cast<float2*>(smem_raw);
@@ -176,9 +197,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) rx_demod_kernel(const RxArgs a) 
         l = l < L ? l : L - 1;
         load_symbol<P>(x, pkt_base + (int64_t)(a.P + l) * symlen + a.cp, ta);
     };
-#if GF3_PREFETCH == 1
-    load_batch(c_first, 0);
-#endif
+    if constexpr (PREFETCH == 1) load_batch(c_first, 0);
 
     for (int chunk = c_first; chunk < c_last; ++chunk) {
         const int l0 = chunk * FLUSH;
@@ -205,16 +224,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) rx_demod_kernel(const RxArgs a) 
 #pragma unroll 1
         for (int b = 0; b < BATCHES; ++b) {
             // ---------------- phase A: FFT of SF symbols
-#if GF3_PREFETCH != 1
-            load_batch(chunk, b);
-#endif
+            if constexpr (PREFETCH != 1) load_batch(chunk, b);
             fft_forward<P, NT>(x, zbuf + ga * MP, tw, ta, ga);
             __syncthreads();
-#if GF3_PREFETCH == 1
-            // prefetch the next batch's samples: the loads fly while phase B computes
-            load_batch(b + 1 < BATCHES ? chunk : chunk + 1, b + 1 < BATCHES ? b + 1 : 0);
-#elif GF3_PREFETCH == 2
-            if (ta == 0) {
+            if constexpr (PREFETCH == 1) {
+                // prefetch the next batch's samples: the loads fly while phase B computes
+                load_batch(b + 1 < BATCHES ? chunk : chunk + 1, b + 1 < BATCHES ? b + 1 : 0);
+            } else if constexpr (PREFETCH == 2) {
+              if (ta == 0) {
                 const int nc = b + 1 < BATCHES ? chunk : chunk + 1, nb = b + 1 < BATCHES ? b + 1 : 0;
                 const int nl = nc * FLUSH + nb * SF + ga;
                 if (nc < c_last && nl < L) {
@@ -222,8 +239,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) rx_demod_kernel(const RxArgs a) 
                     const uintptr_t lo16 = reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15;
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo16), "r"(N * 4 + 16) : "memory");
                 }
+              }
             }
-#endif
             // ---------------- phase B: untangle, equalise, demap
             // thread <-> PP bin pairs; walks the batch's symbols sb, sb+SB, ... with pointer increments
             {
@@ -318,6 +335,300 @@ __global__ void __launch_bounds__(NT, 512 / NT) rx_demod_kernel(const RxArgs a) 
                 for (int w = nwords + tid; w < stride_words; w += NT) out[w] = 0u;
             }
             __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Packed data-symbol kernel (N = 1024 and N = 4096): same structure as rx_demod_kernel, but every
+// symbol's M-point FFT is split by one scalar radix-2 DIF stage into two M/2-point FFTs that ride
+// in the two lanes of FFMA2 / FADD2 / FMUL2, and the untangle / equalise / demap phase processes
+// FOUR bins per thread per step: lanes (2j, 2j+1) and their mirrors (M-2j, M-2j-1).  That halves
+// the FP32 issue slots of the kernel, which is instruction-issue bound (profiles/).
+// ------------------------------------------------------------------------------------------
+template <class P, int NT, int MINB, bool KNOWN_CH, bool WANT_EQ>
+__global__ void __launch_bounds__(NT, MINB) rx_demod_pk_kernel(const RxArgs a) {
+    // Warp-specialised: the first NT/2 threads (producers) load samples and run the FFTs of batch s
+    // into Z buffer s&1; the other NT/2 threads (consumers) untangle / equalise / demap batch s-1 from
+    // the other buffer and flush the packed bits.  They meet only on named barriers (full / empty per
+    // buffer), so loads, FFT math and equaliser math of different batches overlap inside one CTA.
+    constexpr int T = P::T, R = P::R, H = P::H, M = P::M, N = P::N, HP = P::HP, K = M - 1;
+    constexpr int NP = NT / 2, NC = NT - NP;          // producer / consumer threads
+    constexpr int SF = NP / T;                        // symbols per FFT batch
+    constexpr int ITEMS = H / 2;                      // smem entries walked per symbol in phase B
+    constexpr int TB = ITEMS < NC ? ITEMS : NC;       // consumer threads per symbol
+    constexpr int SB = NC / TB;                       // symbols handled concurrently in phase B
+    constexpr int PPK = ITEMS / TB;                   // entries per thread
+    static_assert(SF >= 1 && SF % SB == 0, "bad producer/consumer split");
+    enum { BAR_FULL0 = 1, BAR_FULL1 = 2, BAR_EMPTY0 = 3, BAR_EMPTY1 = 4, BAR_CONS = 5 };
+    const int FLUSH = a.flush;
+    const int BATCHES = FLUSH / SF;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* zbuf = reinterpret_cast<float4*>(smem_raw);                         // [2][SF][HP] (U.re, V.re, U.im, V.im)
+    float2* tw = reinterpret_cast<float2*>(zbuf + 2 * SF * HP);                 // [TW_TOTAL]
+    uint8_t* stage = reinterpret_cast<uint8_t*>(tw + P::TW_TOTAL);
+
+    const int tid = threadIdx.x;
+    const int64_t pkt = blockIdx.x / a.ctas_per_packet;
+    const int c_first = (blockIdx.x % a.ctas_per_packet) * a.chunks_per_cta;
+    const int c_last = min(c_first + a.chunks_per_cta, a.chunks_per_packet);
+    const int Nd = a.hi - a.lo;
+    const int L = a.L;
+
+    for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
+
+    const bool use_xor = a.xor2 != nullptr;
+    const bool want_bits = a.bits != nullptr;
+    const int stage_bytes = ((FLUSH * Nd + 15) & ~15) + 16;
+    uint32_t* xorw = reinterpret_cast<uint32_t*>(stage + stage_bytes);
+    if (use_xor && want_bits) {
+        const int wpc = (FLUSH * Nd + 15) >> 4;
+        for (int w = tid; w < wpc; w += NT) {
+            uint32_t word = 0;
+            int c = (16 * w) % Nd;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (16 * w + i < FLUSH * Nd) {
+                    const uint32_t code = a.xor2[c] & 3u;
+                    word |= code << (8 * (i >> 2) + 6 - 2 * (i & 3));
+                }
+                c = (c + 1 == Nd) ? 0 : c + 1;
+            }
+            xorw[w] = word;
+        }
+    }
+
+    const float* pkt_base = a.samples + (a.pkt_offset ? a.pkt_offset[pkt] : pkt * a.pkt_stride);
+    const int symlen = N + a.cp;
+
+    // ---- per-thread constants for phase B.  Entry j carries bins (2j, 2j+1); their mirrors
+    // (M-2j, M-2j-1) are lane x of entry H-j and lane y of entry H-1-j.
+    const bool producer = tid < NP;
+    const int ctid = producer ? 0 : tid - NP;          // consumer thread index
+    const int jb = ctid % TB, sb = ctid / TB;
+    cpk w2[PPK], u1[PPK], u2[PPK], G1[PPK], G2[PPK];
+    int zo[PPK], zmx[PPK], zmy[PPK], jj[PPK], flags[PPK];   // flags: 1 own.x 2 own.y 4 mir.x 8 mir.y are data bins
+    const float2* Hs = KNOWN_CH ? a.Hs : a.Hs + pkt * K;
+    const double slope = KNOWN_CH ? 0.0 : a.slope[pkt];
+    const double inv_lp = 1.0 / (double)(L + a.P);
+    auto is_data = [&](int k) { return k >= a.lo && k < a.hi; };
+    auto rot = [&](int k, double w) { return expmj(slope * (double)(k - 1) * w); };
+#pragma unroll
+    for (int pp = 0; pp < PPK; ++pp) {
+        const int j = jb + pp * TB;
+        jj[pp] = j;
+        zo[pp] = zpad<P>(j);
+        zmx[pp] = zpad<P>((H - j) % H);
+        zmy[pp] = zpad<P>(H - 1 - j);
+        const int kx = 2 * j, ky = 2 * j + 1, mx = M - 2 * j, my = M - 2 * j - 1;
+        float sx, cx, sy, cy;
+        sincospif(2.0f * (float)kx / (float)N, &sx, &cx);
+        sincospif(2.0f * (float)ky / (float)N, &sy, &cy);
+        w2[pp] = cpk{make_float2(-sx, -sy), make_float2(-cx, -cy)};          // -j exp(-2 pi i k / N)
+        flags[pp] = (is_data(kx) ? 1 : 0) | (is_data(ky) ? 2 : 0) | ((j != 0 && is_data(mx)) ? 4 : 0) | (is_data(my) ? 8 : 0);
+        if constexpr (!KNOWN_CH) {
+            const double st = inv_lp * (double)SB;
+            const float2 ax = rot(kx, st), ay = rot(ky, st), bx = rot(mx, st), by = rot(my, st);
+            u1[pp] = cpk{make_float2(ax.x, ay.x), make_float2(ax.y, ay.y)};
+            u2[pp] = cpk{make_float2(bx.x, by.x), make_float2(bx.y, by.y)};
+        }
+    }
+    // bin M/2 (self-paired, = lane x of entry H/2) is walked by the thread that owns entry 0
+    float2 Gh = make_float2(0.f, 0.f), uh = make_float2(1.f, 0.f);
+    if constexpr (!KNOWN_CH) uh = rot(M / 2, inv_lp * (double)SB);
+    const bool half_data = is_data(M / 2);
+    __syncthreads();
+
+    const int ga = tid / T, ta = tid % T;               // producer identity: symbol group, lane in the group
+    const int n_chunks = c_last - c_first;
+    const int n_steps = n_chunks * BATCHES;
+
+    if (producer) {
+        // =============================== PRODUCERS: samples -> two packed H-point FFTs -> Z buffer
+#pragma unroll 1
+        for (int s = 0; s < n_steps; ++s) {
+            const int chunk = c_first + s / BATCHES, b = s % BATCHES;
+            int l = chunk * FLUSH + b * SF + ga;
+            l = l < L ? l : L - 1;                          // clamped: spectra of invalid symbols are never used
+            const float* sp = pkt_base + (int64_t)(a.P + l) * symlen + a.cp;
+            float2 za[R], zb[R];
+            if ((reinterpret_cast<uintptr_t>(sp) & 7) == 0) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    za[i] = ldg_stream2(sp + 2 * (ta + i * T));
+                    zb[i] = ldg_stream2(sp + 2 * (ta + i * T + H));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    za[i].x = ldg_stream1(sp + 2 * (ta + i * T));
+                    za[i].y = ldg_stream1(sp + 2 * (ta + i * T) + 1);
+                    zb[i].x = ldg_stream1(sp + 2 * (ta + i * T + H));
+                    zb[i].y = ldg_stream1(sp + 2 * (ta + i * T + H) + 1);
+                }
+            }
+            if (GF3_PK_L2_PREFETCH && ta == 0 && s + 1 < n_steps) {
+                // bulk L2 prefetch (TMA engine, no registers) of this group's symbol of the NEXT step
+                const int nc = c_first + (s + 1) / BATCHES, nb = (s + 1) % BATCHES;
+                const int nl = nc * FLUSH + nb * SF + ga;
+                if (nl < L) {
+                    const float* np_ = pkt_base + (int64_t)(a.P + nl) * symlen + a.cp;
+                    const uintptr_t lo16 = reinterpret_cast<uintptr_t>(np_) & ~(uintptr_t)15;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo16), "r"(N * 4 + 16) : "memory");
+                }
+            }
+            // the loads above are in flight while we wait for the consumers to release this buffer
+            if (s >= 2) asm volatile("bar.sync %0, %1;" ::"r"((s & 1) ? BAR_EMPTY1 : BAR_EMPTY0), "n"(NT) : "memory");
+            cpk x[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const float2 u = cadd(za[i], zb[i]);
+                const float2 v = cmul(csub(za[i], zb[i]), tw[ta + i * T]);      // W_M^h, h = ta + i*T
+                x[i] = cpk{make_float2(u.x, v.x), make_float2(u.y, v.y)};
+            }
+            pk_fft_forward<P, NP>(x, zbuf + ((s & 1) * SF + ga) * HP, tw, ta, ga);
+            asm volatile("bar.arrive %0, %1;" ::"r"((s & 1) ? BAR_FULL1 : BAR_FULL0), "n"(NT) : "memory");
+        }
+        return;
+    }
+
+    // =============================== CONSUMERS: untangle, equalise, demap, pack, store
+#pragma unroll 1
+    for (int chunk = c_first; chunk < c_last; ++chunk) {
+        const int l0 = chunk * FLUSH;
+        const int nsym = min(FLUSH, L - l0);
+        if ((nsym * Nd) & 15) {
+            if (ctid < 16) stage[nsym * Nd + ctid] = 0;
+        }
+        // (re)seed the rotating equaliser taps exactly at the chunk start
+        {
+            const double wl = ((double)(l0 + sb) + 0.5 * (double)a.P) * inv_lp;          // OFDM.py:471,474
+            auto seed = [&](int k) -> float2 {
+                if (k < 1 || k > K) return make_float2(0.f, 0.f);
+                const float2 h = Hs[k - 1];
+                if constexpr (KNOWN_CH) return h;
+                else return cmul(cconj(h), rot(k, wl));
+            };
+#pragma unroll
+            for (int pp = 0; pp < PPK; ++pp) {
+                const int j = jj[pp];
+                const float2 gx = seed(2 * j), gy = seed(2 * j + 1), hx = seed(M - 2 * j), hy = seed(M - 2 * j - 1);
+                G1[pp] = cpk{make_float2(gx.x, gy.x), make_float2(gx.y, gy.y)};
+                G2[pp] = cpk{make_float2(hx.x, hy.x), make_float2(hx.y, hy.y)};
+            }
+            Gh = seed(M / 2);
+        }
+
+#pragma unroll 1
+        for (int b = 0; b < BATCHES; ++b) {
+            const int s = (chunk - c_first) * BATCHES + b;
+            asm volatile("bar.sync %0, %1;" ::"r"((s & 1) ? BAR_FULL1 : BAR_FULL0), "n"(NT) : "memory");
+            {
+                const int ls0 = b * SF + sb;
+                int n_it = (nsym - ls0 + SB - 1) / SB;
+                n_it = n_it < 0 ? 0 : (n_it > SF / SB ? SF / SB : n_it);
+                const float4* zs = zbuf + ((s & 1) * SF + sb) * HP;
+                uint8_t* st = stage + ls0 * Nd - a.lo;
+                float2* eqp = nullptr;
+                if constexpr (WANT_EQ) eqp = a.eq + ((int64_t)pkt * L + l0 + ls0) * K - 1;
+#pragma unroll 1
+                for (int it = 0; it < n_it; ++it) {
+#pragma unroll
+                    for (int pp = 0; pp < PPK; ++pp) {
+                        const float4 eo = lds128(zs + zo[pp]), ea = lds128(zs + zmx[pp]), eb = lds128(zs + zmy[pp]);
+                        const cpk z1{make_float2(eo.x, eo.y), make_float2(eo.z, eo.w)};
+                        const cpk z2{make_float2(ea.x, eb.y), make_float2(ea.z, eb.w)};
+                        const cpk s{pk_add(z1.re, z2.re), pk_sub(z1.im, z2.im)};       // Z[k] + conj Z[M-k]
+                        const cpk d{pk_sub(z1.re, z2.re), pk_add(z1.im, z2.im)};       // Z[k] - conj Z[M-k]
+                        const cpk tt = cmul(w2[pp], d);
+                        const cpk x1 = cadd(s, tt);                                     // 2 X[k]
+                        const cpk x2{pk_sub(s.re, tt.re), pk_sub(tt.im, s.im)};         // 2 X[M-k] = conj(s - tt)
+                        const cpk y1 = cmul(x1, G1[pp]);
+                        const cpk y2 = cmul(x2, G2[pp]);
+                        if constexpr (!KNOWN_CH) {
+                            G1[pp] = cmul(G1[pp], u1[pp]);
+                            G2[pp] = cmul(G2[pp], u2[pp]);
+                        }
+                        const int f = flags[pp];
+                        const int kx = 2 * jj[pp];
+                        if (want_bits) {
+                            if (f & 1) st[kx] = (uint8_t)(((__float_as_uint(y1.im.x) >> 30) & 2u) | (__float_as_uint(y1.re.x) >> 31));
+                            if (f & 2) st[kx + 1] = (uint8_t)(((__float_as_uint(y1.im.y) >> 30) & 2u) | (__float_as_uint(y1.re.y) >> 31));
+                            if (f & 4) st[M - kx] = (uint8_t)(((__float_as_uint(y2.im.x) >> 30) & 2u) | (__float_as_uint(y2.re.x) >> 31));
+                            if (f & 8) st[M - kx - 1] = (uint8_t)(((__float_as_uint(y2.im.y) >> 30) & 2u) | (__float_as_uint(y2.re.y) >> 31));
+                        }
+                        if constexpr (WANT_EQ) {
+                            const float eq_w = KNOWN_CH ? 0.f : (float)(((double)(l0 + ls0 + it * SB) + 0.5 * (double)a.P) * inv_lp);
+                            auto put = [&](int k, float yr, float yi) {
+                                if (k < 1 || k > K) return;
+                                float sc = 0.5f;
+                                if constexpr (!KNOWN_CH) {
+                                    const float2 hs = Hs[k - 1], he = a.He[pkt * K + k - 1];
+                                    const float a1 = sqrtf(hs.x * hs.x + hs.y * hs.y), e1 = sqrtf(he.x * he.x + he.y * he.y);
+                                    sc = 0.5f / (a1 * (a1 + (e1 - a1) * eq_w));       // |H| = |Hs| + (|He|-|Hs|) w  (OFDM.py:471)
+                                }
+                                eqp[k] = make_float2(yr * sc, yi * sc);
+                            };
+                            put(kx, y1.re.x, y1.im.x);
+                            put(kx + 1, y1.re.y, y1.im.y);
+                            if (kx != 0) put(M - kx, y2.re.x, y2.im.x);
+                            put(M - kx - 1, y2.re.y, y2.im.y);
+                        }
+                    }
+                    if (jb == 0) {      // bin M/2: 2 X[M/2] = 2 conj(Z[M/2]), Z[M/2] = U[H/2]
+                        const float4 e = zs[zpad<P>(H / 2)];
+                        const float2 xh = make_float2(2.f * e.x, -2.f * e.z);
+                        const float2 yh = cmul(xh, Gh);
+                        if constexpr (!KNOWN_CH) Gh = cmul(Gh, uh);
+                        if (want_bits && half_data)
+                            st[M / 2] = (uint8_t)(((__float_as_uint(yh.y) >> 30) & 2u) | (__float_as_uint(yh.x) >> 31));
+                        if constexpr (WANT_EQ) {
+                            float sc = 0.5f;
+                            if constexpr (!KNOWN_CH) {
+                                const float eq_w = (float)(((double)(l0 + ls0 + it * SB) + 0.5 * (double)a.P) * inv_lp);
+                                const float2 hs = Hs[M / 2 - 1], he = a.He[pkt * K + M / 2 - 1];
+                                const float a1 = sqrtf(hs.x * hs.x + hs.y * hs.y), e1 = sqrtf(he.x * he.x + he.y * he.y);
+                                sc = 0.5f / (a1 * (a1 + (e1 - a1) * eq_w));
+                            }
+                            eqp[M / 2] = make_float2(yh.x * sc, yh.y * sc);
+                        }
+                    }
+                    zs += SB * HP;
+                    st += SB * Nd;
+                    if constexpr (WANT_EQ) eqp += (int64_t)SB * K;
+                }
+            }
+            if (s + 2 < n_steps) asm volatile("bar.arrive %0, %1;" ::"r"((s & 1) ? BAR_EMPTY1 : BAR_EMPTY0), "n"(NT) : "memory");
+        }
+
+        // ---------------- flush (consumer threads only)
+        if (want_bits) {
+            asm volatile("bar.sync %0, %1;" ::"r"((int)BAR_CONS), "n"(NC) : "memory");
+            const int ncodes = nsym * Nd;
+            const int nwords = (ncodes + 15) >> 4;
+            uint32_t* out = reinterpret_cast<uint32_t*>(a.bits + pkt * a.bits_stride) + (int64_t)l0 * Nd / 16;
+            for (int w = ctid; w < nwords; w += NC) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stage + 16 * w);
+                const uint32_t t0 = v.x * 0x40100401u, t1 = v.y * 0x40100401u, t2 = v.z * 0x40100401u, t3 = v.w * 0x40100401u;
+                uint32_t word = __byte_perm(__byte_perm(t0, t1, 0x0073), __byte_perm(t2, t3, 0x0073), 0x5410);
+                if (use_xor) {
+                    uint32_t xw = xorw[w];
+                    const int r = ncodes - 16 * w;
+                    if (r < 16) {
+                        const int fb = r >> 2, rm = r & 3;
+                        const uint32_t m = (fb ? (0xFFFFFFFFu >> (32 - 8 * fb)) : 0u) | (rm ? (((0xFF00u >> (2 * rm)) & 0xFFu) << (8 * fb)) : 0u);
+                        xw &= m;
+                    }
+                    word ^= xw;
+                }
+                out[w] = word;
+            }
+            if (l0 + nsym >= L) {
+                const int stride_words = (int)(a.bits_stride / 4) - (int)((int64_t)l0 * Nd / 16);
+                for (int w = nwords + ctid; w < stride_words; w += NC) out[w] = 0u;
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"((int)BAR_CONS), "n"(NC) : "memory");
         }
     }
 }
@@ -510,28 +821,82 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
 #ifndef GF3_DEMOD_THREADS
 #define GF3_DEMOD_THREADS 128
 #endif
-// plans whose symbol group already spans >= 128 threads keep 256-thread CTAs (fewer bin pairs,
-// hence less equaliser state, per thread)
-template <class P> struct DemodThreads { static constexpr int value = P::T >= 128 ? 256 : GF3_DEMOD_THREADS; };
+// Plan used by the data-symbol kernel for each symbol size, its CTA size and CTAs per SM.
+template <int LOGN> struct DemodCfg { using Plan = FftPlan<LOGN>; static constexpr int NT = GF3_DEMOD_THREADS, MINB = 512 / GF3_DEMOD_THREADS; };
+template <> struct DemodCfg<12> { using Plan = FftPlanWarp12; static constexpr int NT = 128, MINB = 2; };   // ~255 registers / thread
 
-template <class P, bool KNOWN_CH, bool WANT_EQ>
+// Packed (two-lane) configuration per symbol size; Plan = void: use the scalar kernel.
+template <int LOGN> struct DemodPkCfg { using Plan = void; static constexpr int NT = 128, MINB = 4; };
+#ifndef GF3_NO_PACKED
+#ifndef GF3_PK_NT
+#define GF3_PK_NT 128
+#define GF3_PK_MINB 4
+#endif
+template <> struct DemodPkCfg<10> { using Plan = PkPlan10; static constexpr int NT = GF3_PK_NT, MINB = GF3_PK_MINB; };
+#endif
+
+template <int LOGN, bool KNOWN_CH, bool WANT_EQ>
+static int launch_demod_pk(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaStream_t st) {
+    using P = typename DemodPkCfg<LOGN>::Plan;
+    if constexpr (std::is_same<P, void>::value) {
+        return GF3_ERR_INVALID;
+    } else {
+        constexpr int NT = (2 * P::T > DemodPkCfg<LOGN>::NT) ? 2 * P::T : DemodPkCfg<LOGN>::NT;
+        constexpr int MINB = DemodPkCfg<LOGN>::MINB;
+        constexpr int SF = (NT / 2) / P::T;             // producer half of the CTA
+        const int Nd = a.hi - a.lo;
+        int flush = SF;
+        while ((flush * Nd) % 16 != 0 || flush < 8) flush += SF;
+        a.flush = flush;
+        a.tw = plan->d_tw_pk;
+        a.chunks_per_packet = (a.L + flush - 1) / flush;
+        const int64_t want = (int64_t)plan->sm_count * MINB * 8;
+        int64_t split = (want + n_packets - 1) / n_packets;
+        if (split < 1) split = 1;
+        if (split > a.chunks_per_packet) split = a.chunks_per_packet;
+        a.chunks_per_cta = (int)((a.chunks_per_packet + split - 1) / split);
+        a.ctas_per_packet = (a.chunks_per_packet + a.chunks_per_cta - 1) / a.chunks_per_cta;
+        const size_t smem = (size_t)2 * SF * P::HP * sizeof(float4) + (size_t)P::TW_TOTAL * sizeof(float2)
+                            + (((size_t)flush * Nd + 15) & ~(size_t)15) + 16 + (((size_t)flush * Nd + 15) / 16 + 1) * sizeof(uint32_t);
+        auto kern = rx_demod_pk_kernel<P, NT, MINB, KNOWN_CH, WANT_EQ>;
+        GF3_REQUIRE(smem <= 227 * 1024, "rx_demod: %zu bytes of shared memory needed (> 227 KB)", smem);
+        GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t grid = n_packets * a.ctas_per_packet;
+        GF3_REQUIRE(grid <= 0x7fffffff, "rx_demod: grid too large");
+        kern<<<(unsigned)grid, NT, smem, st>>>(a);
+        GF3_LAUNCH_CHECK();
+        return GF3_OK;
+    }
+}
+
+template <int LOGN, bool KNOWN_CH, bool WANT_EQ>
 static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaStream_t st) {
-    // CTA size: one symbol group needs P::T threads; smaller CTAs (more of them per SM) decorrelate
-    // the load / FFT / equalise phases of co-resident CTAs
-    constexpr int NT = (P::T > DemodThreads<P>::value) ? P::T : DemodThreads<P>::value;
-    constexpr int SF = NT / P::T, FLUSH = SF > 16 ? SF : 16;
+    if constexpr (!std::is_same<typename DemodPkCfg<LOGN>::Plan, void>::value) {
+        if (plan->d_tw_pk && plan->use_packed) return launch_demod_pk<LOGN, KNOWN_CH, WANT_EQ>(plan, a, n_packets, st);
+    }
+    using P = typename DemodCfg<LOGN>::Plan;
+    // CTA size: one symbol group needs P::T threads; small CTAs (several per SM) decorrelate the
+    // load / FFT / equalise phases of co-resident CTAs
+    constexpr int NT = (P::T > DemodCfg<LOGN>::NT) ? P::T : DemodCfg<LOGN>::NT;
+    constexpr int MINB = DemodCfg<LOGN>::MINB;
+    constexpr int SF = NT / P::T;
     const int Nd = a.hi - a.lo;
-    a.chunks_per_packet = (a.L + FLUSH - 1) / FLUSH;
-    // enough CTAs for ~8 waves of 2 CTAs/SM, otherwise one CTA walks the whole packet
-    const int64_t want = (int64_t)plan->sm_count * 2 * 8;
+    // smallest flush period: multiple of SF, FLUSH*Nd % 16 == 0, at least 8 symbols (amortise the flush)
+    int flush = SF;
+    while ((flush * Nd) % 16 != 0 || flush < 8) flush += SF;
+    a.flush = flush;
+    a.tw = (LOGN == 12) ? plan->d_tw_demod : plan->d_tw;
+    a.chunks_per_packet = (a.L + flush - 1) / flush;
+    // enough CTAs for ~8 waves, otherwise one CTA walks the whole packet
+    const int64_t want = (int64_t)plan->sm_count * MINB * 8;
     int64_t split = (want + n_packets - 1) / n_packets;
     if (split < 1) split = 1;
     if (split > a.chunks_per_packet) split = a.chunks_per_packet;
     a.chunks_per_cta = (int)((a.chunks_per_packet + split - 1) / split);
     a.ctas_per_packet = (a.chunks_per_packet + a.chunks_per_cta - 1) / a.chunks_per_cta;
-    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (((size_t)FLUSH * Nd + 15) & ~(size_t)15) + 16
-                        + (((size_t)FLUSH * Nd + 15) / 16 + 1) * sizeof(uint32_t);
-    auto kern = rx_demod_kernel<P, NT, KNOWN_CH, WANT_EQ>;
+    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (((size_t)flush * Nd + 15) & ~(size_t)15) + 16
+                        + (((size_t)flush * Nd + 15) / 16 + 1) * sizeof(uint32_t);
+    auto kern = rx_demod_kernel<P, NT, MINB, KNOWN_CH, WANT_EQ>;
     GF3_REQUIRE(smem <= 227 * 1024, "rx_demod: %zu bytes of shared memory needed (> 227 KB)", smem);
     GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = n_packets * a.ctas_per_packet;
@@ -592,11 +957,11 @@ static int demod_common(const gf3_plan* plan, const float* samples, const int64_
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (known_ch) {
-        if (eq) { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P, true, true>(plan, a, n_packets, st))); }
-        else    { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P, true, false>(plan, a, n_packets, st))); }
+        if (eq) { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P::LOGN, true, true>(plan, a, n_packets, st))); }
+        else    { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P::LOGN, true, false>(plan, a, n_packets, st))); }
     } else {
-        if (eq) { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P, false, true>(plan, a, n_packets, st))); }
-        else    { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P, false, false>(plan, a, n_packets, st))); }
+        if (eq) { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P::LOGN, false, true>(plan, a, n_packets, st))); }
+        else    { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P::LOGN, false, false>(plan, a, n_packets, st))); }
     }
     return GF3_OK;
 }

@@ -338,3 +338,25 @@ def test_ber_sweep_sharding_invariance(known_sequence):
     assert full[1, 2] == 0                                  # every chirp found at 25 dB
     assert full[1, 0] < full[0, 0]                          # BER falls with SNR
     assert full[1, 0] / full[1, 1] < 0.02
+
+
+def test_packed_f32x2_variant_matches_scalar_kernel(known_sequence, monkeypatch):
+    """The opt-in packed (FFMA2/FADD2, warp-specialised) data-symbol kernel for N = 1024 must give
+    the same bits and the same constellation as the default kernel, on aligned and odd offsets."""
+    torch = _torch()
+    import gf3b200
+    g = load_golden("stage_w1024.npz")
+    p = oracle_params(g["cfg"], known_sequence)
+    r = torch.from_numpy(g["r_i16"].astype(np.float32)).cuda()
+    starts = (g["peaks"] + 2)[:-1]
+    off = torch.from_numpy(starts.astype(np.int64)).cuda()
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GF3_DEMOD_PACKED", mode)
+        phy = _phy(p)
+        Hs, He, slope = phy.rx_estimate(r, len(starts), off)
+        bits, eq = phy.rx_demod(r, len(starts), Hs, He, slope, off, xor=True, want_eq=True)
+        res[mode] = (phy.unpack_bits(bits), eq.cpu().numpy())
+        _check_bits(res[mode][0], g["bits"], g["eq"][:, p.data_carriers - 1], "packed=" + mode)
+    assert np.array_equal(res["0"][0], res["1"][0])
+    assert _rel_err(res["1"][1].reshape(-1, p.K), g["eq"]).max() < EQ_RTOL
