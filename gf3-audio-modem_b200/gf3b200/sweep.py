@@ -14,6 +14,11 @@ import sys
 
 import numpy as np
 
+if __package__ in (None, ""):          # run as a script (torchrun path/to/sweep.py): make relative imports work
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import gf3b200  # noqa: F401
+    __package__ = "gf3b200"
+
 
 def shard_streams(n_streams, rank, world):
     """Stream ids owned by `rank`: id % world == rank."""
