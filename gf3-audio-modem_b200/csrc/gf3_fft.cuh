@@ -231,9 +231,6 @@ GF3_PLAN(9, 16, 2, 16, 16, 1)    // N=512   M=256   T=16
 GF3_PLAN(10, 32, 2, 32, 16, 1)   // N=1024  M=512   T=16
 GF3_PLAN(11, 32, 2, 32, 32, 1)   // N=2048  M=1024  T=32
 GF3_PLAN(12, 16, 3, 16, 16, 8)   // N=4096  M=2048  T=128
-// N=4096 with one warp per symbol: 64 points per thread, 64 x 32, a single exchange and only
-// __syncwarp between passes (used by the data-symbol kernel; needs ~200 registers per thread)
-struct FftPlanWarp12 : FftPlanT<12, 64, 2, 64, 32, 1> {};
 #undef GF3_PLAN
 
 template <class P>

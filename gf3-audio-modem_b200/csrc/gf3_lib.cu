@@ -125,12 +125,6 @@ extern "C" int gf3_plan_create(const gf3_params* p, gf3_plan** out) {
         GF3_CHECK_CUDA(cudaMalloc(&plan->d_tw_pk, h.size() * sizeof(float2)));
         GF3_CHECK_CUDA(cudaMemcpy(plan->d_tw_pk, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
     }
-    if (plan->logN == 12) {
-        std::vector<float2> h;
-        fill_tw_vec<FftPlanWarp12>(h);
-        GF3_CHECK_CUDA(cudaMalloc(&plan->d_tw_demod, h.size() * sizeof(float2)));
-        GF3_CHECK_CUDA(cudaMemcpy(plan->d_tw_demod, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    }
     const int K = p->N / 2 - 1;
     std::vector<float2> ones(K, make_float2(1.f, 0.f));
     GF3_CHECK_CUDA(cudaMalloc(&plan->d_ones, K * sizeof(float2)));
@@ -145,7 +139,6 @@ extern "C" int gf3_plan_destroy(gf3_plan* plan) {
     if (!plan) return GF3_OK;
     sync_plan_free(plan);
     if (plan->d_tw) cudaFree(plan->d_tw);
-    if (plan->d_tw_demod) cudaFree(plan->d_tw_demod);
     if (plan->d_tw_pk) cudaFree(plan->d_tw_pk);
     if (plan->d_ones) cudaFree(plan->d_ones);
     delete plan;

@@ -24,9 +24,6 @@ constexpr int kThreads = 256;
 #ifndef GF3_PK_L2_PREFETCH
 #define GF3_PK_L2_PREFETCH 1
 #endif
-#ifndef GF3_PREFETCH_WARP64
-#define GF3_PREFETCH_WARP64 0
-#endif
 constexpr float kPi = 3.14159265358979323846f;
 
 struct RxArgs {
@@ -113,7 +110,7 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
     // multi-warp symbol groups (N = 4096) have few loads per thread in flight and only two CTAs per
     // SM: issue the next batch's loads before the equaliser phase.  Half-warp groups (R = 32) have
     // no registers to spare for that and four CTAs per SM already overlap.
-    constexpr int PREFETCH = (GF3_PREFETCH >= 0) ? GF3_PREFETCH : (T >= 128 ? 1 : (R >= 64 ? GF3_PREFETCH_WARP64 : 0));
+    constexpr int PREFETCH = (GF3_PREFETCH >= 0) ? GF3_PREFETCH : (T >= 128 ? 1 : 0);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* zbuf = reinterpret_cast<float2*>(smem_raw);
@@ -205,7 +202,9 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
         if ((nsym * Nd) & 15) {                       // last word of the chunk is partial: its missing codes are 0
             if (tid < 16) stage[nsym * Nd + tid] = 0;
         }
-        // (re)seed the rotating equaliser taps exactly at the chunk start
+        // (re)seed the rotating equaliser taps exactly (fp64 phase) at the first chunk and then every 64
+        // symbols; in between the per-bin recurrence simply continues across chunk boundaries
+        if (chunk == c_first || (l0 % 64) == 0)
 #pragma unroll
         for (int pp = 0; pp < PP; ++pp) {
             const int j = jb + pp * TB;
@@ -361,6 +360,7 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_pk_kernel(const RxArgs a) {
     constexpr int PPK = ITEMS / TB;                   // entries per thread
     static_assert(SF >= 1 && SF % SB == 0, "bad producer/consumer split");
     enum { BAR_FULL0 = 1, BAR_FULL1 = 2, BAR_EMPTY0 = 3, BAR_EMPTY1 = 4, BAR_CONS = 5 };
+    constexpr int RESEED = 64;                        // symbols between exact re-seeds of the equaliser recurrence
     const int FLUSH = a.flush;
     const int BATCHES = FLUSH / SF;
 
@@ -444,15 +444,18 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_pk_kernel(const RxArgs a) {
     const int n_chunks = c_last - c_first;
     const int n_steps = n_chunks * BATCHES;
 
+    // 256-thread CTAs = two warpgroups: the producer warpgroup takes registers from the consumer one
+    // (setmaxnreg), enough to keep the NEXT step's 2R loads in flight during the current FFT.
+    constexpr bool DBUF = (NT == 256);
     if (producer) {
         // =============================== PRODUCERS: samples -> two packed H-point FFTs -> Z buffer
-#pragma unroll 1
-        for (int s = 0; s < n_steps; ++s) {
+        if constexpr (DBUF) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+        float2 za[R], zb[R];
+        auto issue_loads = [&](int s) {
             const int chunk = c_first + s / BATCHES, b = s % BATCHES;
             int l = chunk * FLUSH + b * SF + ga;
             l = l < L ? l : L - 1;                          // clamped: spectra of invalid symbols are never used
             const float* sp = pkt_base + (int64_t)(a.P + l) * symlen + a.cp;
-            float2 za[R], zb[R];
             if ((reinterpret_cast<uintptr_t>(sp) & 7) == 0) {
 #pragma unroll
                 for (int i = 0; i < R; ++i) {
@@ -468,17 +471,24 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_pk_kernel(const RxArgs a) {
                     zb[i].y = ldg_stream1(sp + 2 * (ta + i * T + H) + 1);
                 }
             }
-            if (GF3_PK_L2_PREFETCH && ta == 0 && s + 1 < n_steps) {
-                // bulk L2 prefetch (TMA engine, no registers) of this group's symbol of the NEXT step
-                const int nc = c_first + (s + 1) / BATCHES, nb = (s + 1) % BATCHES;
-                const int nl = nc * FLUSH + nb * SF + ga;
-                if (nl < L) {
-                    const float* np_ = pkt_base + (int64_t)(a.P + nl) * symlen + a.cp;
-                    const uintptr_t lo16 = reinterpret_cast<uintptr_t>(np_) & ~(uintptr_t)15;
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo16), "r"(N * 4 + 16) : "memory");
+        };
+        if constexpr (DBUF) issue_loads(0);
+#pragma unroll 1
+        for (int s = 0; s < n_steps; ++s) {
+            if constexpr (!DBUF) {
+                issue_loads(s);
+                if (GF3_PK_L2_PREFETCH && ta == 0 && s + 1 < n_steps) {
+                    // bulk L2 prefetch (TMA engine, no registers) of this group's symbol of the NEXT step
+                    const int nc = c_first + (s + 1) / BATCHES, nb = (s + 1) % BATCHES;
+                    const int nl = nc * FLUSH + nb * SF + ga;
+                    if (nl < L) {
+                        const float* np_ = pkt_base + (int64_t)(a.P + nl) * symlen + a.cp;
+                        const uintptr_t lo16 = reinterpret_cast<uintptr_t>(np_) & ~(uintptr_t)15;
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo16), "r"(N * 4 + 16) : "memory");
+                    }
                 }
             }
-            // the loads above are in flight while we wait for the consumers to release this buffer
+            // the loads are in flight while we wait for the consumers to release this buffer
             if (s >= 2) asm volatile("bar.sync %0, %1;" ::"r"((s & 1) ? BAR_EMPTY1 : BAR_EMPTY0), "n"(NT) : "memory");
             cpk x[R];
 #pragma unroll
@@ -487,11 +497,15 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_pk_kernel(const RxArgs a) {
                 const float2 v = cmul(csub(za[i], zb[i]), tw[ta + i * T]);      // W_M^h, h = ta + i*T
                 x[i] = cpk{make_float2(u.x, v.x), make_float2(u.y, v.y)};
             }
+            if constexpr (DBUF) {
+                if (s + 1 < n_steps) issue_loads(s + 1);     // fly during the FFT below
+            }
             pk_fft_forward<P, NP>(x, zbuf + ((s & 1) * SF + ga) * HP, tw, ta, ga);
             asm volatile("bar.arrive %0, %1;" ::"r"((s & 1) ? BAR_FULL1 : BAR_FULL0), "n"(NT) : "memory");
         }
         return;
     }
+    if constexpr (DBUF) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
 
     // =============================== CONSUMERS: untangle, equalise, demap, pack, store
 #pragma unroll 1
@@ -501,8 +515,9 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_pk_kernel(const RxArgs a) {
         if ((nsym * Nd) & 15) {
             if (ctid < 16) stage[nsym * Nd + ctid] = 0;
         }
-        // (re)seed the rotating equaliser taps exactly at the chunk start
-        {
+        // (re)seed the rotating equaliser taps exactly (fp64 phase) at the first chunk and then every
+        // RESEED symbols; in between the per-bin recurrence simply continues across chunk boundaries
+        if (chunk == c_first || (l0 % RESEED) == 0) {
             const double wl = ((double)(l0 + sb) + 0.5 * (double)a.P) * inv_lp;          // OFDM.py:471,474
             auto seed = [&](int k) -> float2 {
                 if (k < 1 || k > K) return make_float2(0.f, 0.f);
@@ -823,7 +838,9 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
 #endif
 // Plan used by the data-symbol kernel for each symbol size, its CTA size and CTAs per SM.
 template <int LOGN> struct DemodCfg { using Plan = FftPlan<LOGN>; static constexpr int NT = GF3_DEMOD_THREADS, MINB = 512 / GF3_DEMOD_THREADS; };
-template <> struct DemodCfg<12> { using Plan = FftPlanWarp12; static constexpr int NT = 128, MINB = 2; };   // ~255 registers / thread
+// N = 4096: 128 threads per symbol (16 x 16 x 8), two symbols per 256-thread CTA.  (A warp-per-symbol
+// 64 x 32 plan with ~255 registers / thread was measured slower: 8 warps per SM cannot hide latency.)
+template <> struct DemodCfg<12> { using Plan = FftPlan<12>; static constexpr int NT = 256, MINB = 2; };
 
 // Packed (two-lane) configuration per symbol size; Plan = void: use the scalar kernel.
 template <int LOGN> struct DemodPkCfg { using Plan = void; static constexpr int NT = 128, MINB = 4; };
@@ -855,6 +872,9 @@ static int launch_demod_pk(const gf3_plan* plan, RxArgs a, int64_t n_packets, cu
         if (split < 1) split = 1;
         if (split > a.chunks_per_packet) split = a.chunks_per_packet;
         a.chunks_per_cta = (int)((a.chunks_per_packet + split - 1) / split);
+        // CTA boundaries sit on multiples of the 64-symbol re-seed period, so the equaliser recurrence
+        // (and hence every output bit) is independent of how a launch is split into CTAs
+        { const int rc = flush >= 64 ? 1 : 64 / flush; a.chunks_per_cta = (a.chunks_per_cta + rc - 1) / rc * rc; }
         a.ctas_per_packet = (a.chunks_per_packet + a.chunks_per_cta - 1) / a.chunks_per_cta;
         const size_t smem = (size_t)2 * SF * P::HP * sizeof(float4) + (size_t)P::TW_TOTAL * sizeof(float2)
                             + (((size_t)flush * Nd + 15) & ~(size_t)15) + 16 + (((size_t)flush * Nd + 15) / 16 + 1) * sizeof(uint32_t);
@@ -885,7 +905,7 @@ static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaS
     int flush = SF;
     while ((flush * Nd) % 16 != 0 || flush < 8) flush += SF;
     a.flush = flush;
-    a.tw = (LOGN == 12) ? plan->d_tw_demod : plan->d_tw;
+    a.tw = plan->d_tw;
     a.chunks_per_packet = (a.L + flush - 1) / flush;
     // enough CTAs for ~8 waves, otherwise one CTA walks the whole packet
     const int64_t want = (int64_t)plan->sm_count * MINB * 8;
@@ -893,6 +913,9 @@ static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaS
     if (split < 1) split = 1;
     if (split > a.chunks_per_packet) split = a.chunks_per_packet;
     a.chunks_per_cta = (int)((a.chunks_per_packet + split - 1) / split);
+    // CTA boundaries sit on multiples of the 64-symbol re-seed period, so the equaliser recurrence
+    // (and hence every output bit) is independent of how a launch is split into CTAs
+    { const int rc = flush >= 64 ? 1 : 64 / flush; a.chunks_per_cta = (a.chunks_per_cta + rc - 1) / rc * rc; }
     a.ctas_per_packet = (a.chunks_per_packet + a.chunks_per_cta - 1) / a.chunks_per_cta;
     const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (((size_t)flush * Nd + 15) & ~(size_t)15) + 16
                         + (((size_t)flush * Nd + 15) / 16 + 1) * sizeof(uint32_t);
