@@ -255,9 +255,12 @@ class receiver(transmitter):
         """Device matched filter + peak picking; returns (peak indices into `zeros`, len(zeros))."""
         import torch
         phy = self.phy
-        r = np.ascontiguousarray(np.asarray(r, dtype=np.float32)).reshape(1, -1)
-        T = r.shape[1]
-        d_r = torch.from_numpy(r).to(phy.device)
+        r = np.asarray(r)
+        if r.dtype in (np.uint8, np.int16):      # PCM as recorded: narrow samples cross PCIe, exact conversion on the device
+            d_r = phy.pcm_to_f32(torch.from_numpy(np.ascontiguousarray(r).reshape(1, -1)).to(phy.device))
+        else:
+            d_r = torch.from_numpy(np.ascontiguousarray(r, dtype=np.float32).reshape(1, -1)).to(phy.device)
+        T = d_r.shape[1]
         P, pmax = phy.xcorr(d_r)
         max_peaks = max(4, T // max(1, phy.chirp_len) + 2)
         peaks, count = phy.peak_pick(P, pmax, T, max_peaks)

@@ -98,9 +98,38 @@ __global__ void __launch_bounds__(256) ber_count_kernel(const uint8_t* __restric
     }
 }
 
+// PCM samples -> float32 (exact value conversion), 16 samples per thread step, 128-bit stores
+template <typename T>
+__global__ void __launch_bounds__(256) pcm_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 3 < n && (reinterpret_cast<uintptr_t>(out + i) & 15) == 0) {
+            float4 v = make_float4((float)in[i], (float)in[i + 1], (float)in[i + 2], (float)in[i + 3]);
+            *reinterpret_cast<float4*>(out + i) = v;
+        } else {
+            for (int e = 0; e < 4 && i + e < n; ++e) out[i + e] = (float)in[i + e];
+        }
+    }
+}
+
 }  // namespace gf3
 
 using namespace gf3;
+
+extern "C" int gf3_pcm_to_f32(const void* pcm, int32_t format, int64_t n, float* out, void* stream) {
+    GF3_REQUIRE(pcm && out, "pcm_to_f32: null argument");
+    GF3_REQUIRE(format == 0 || format == 1, "pcm_to_f32: format must be 0 (uint8) or 1 (int16)");
+    GF3_REQUIRE(n >= 0, "pcm_to_f32: negative length");
+    if (n == 0) return GF3_OK;
+    int64_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (format == 0) pcm_to_f32_kernel<uint8_t><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(pcm), out, n);
+    else pcm_to_f32_kernel<int16_t><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const int16_t*>(pcm), out, n);
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}
 
 extern "C" int gf3_channel_sim(const float* x, int64_t x_stride, int64_t n_streams, int64_t T,
                                const float* taps, int32_t n_taps, const float* sigma, uint64_t seed,

@@ -26,8 +26,19 @@ __device__ __forceinline__ void static_for(F&& f) {
 }
 
 // ---------------------------------------------------------------- complex helpers
+// packed f32x2 add / sub (FADD2): one issue slot for both components of a complex number
+typedef unsigned long long pk64;
+__device__ __forceinline__ pk64 pk_pack(float2 a) { pk64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ float2 pk_unpack(pk64 v) { float2 r; asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) { pk64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b))); return pk_unpack(d); }
+__device__ __forceinline__ float2 pk_sub(float2 a, float2 b) { pk64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b))); return pk_unpack(d); }
+#ifndef GF3_SCALAR_CADD
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return pk_add(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return pk_sub(a, b); }
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
@@ -41,11 +52,6 @@ __device__ __forceinline__ float2 mul_nj(float2 a) { return make_float2(a.y, -a.
 // kernel therefore carries TWO independent half-size FFTs of a symbol in the two lanes.
 // ptxas folds the negations below into operand modifiers and uses the scalar-broadcast operand form
 // for (s, s) pairs.
-typedef unsigned long long pk64;
-__device__ __forceinline__ pk64 pk_pack(float2 a) { pk64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
-__device__ __forceinline__ float2 pk_unpack(pk64 v) { float2 r; asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
-__device__ __forceinline__ float2 pk_add(float2 a, float2 b) { pk64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b))); return pk_unpack(d); }
-__device__ __forceinline__ float2 pk_sub(float2 a, float2 b) { pk64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b))); return pk_unpack(d); }
 __device__ __forceinline__ float2 pk_mul(float2 a, float2 b) { pk64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b))); return pk_unpack(d); }
 __device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) { pk64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b)), "l"(pk_pack(c))); return pk_unpack(d); }
 __device__ __forceinline__ float2 pk_neg(float2 a) { return make_float2(-a.x, -a.y); }
@@ -97,6 +103,80 @@ __host__ __device__ constexpr double cx_sin2pi(long long num, long long den) {
     return q == 0 ? cx_q_sin(r, den) : q == 1 ? cx_q_cos(r, den) : q == 2 ? -cx_q_sin(r, den) : -cx_q_cos(r, den);
 }
 
+// exp(-2*pi*j*n/64) in the two pair forms a packed complex multiply needs: A = (c, -s), B = (s, c)
+// (x + jy)(c - js) = x*A + y*B.  Read through the constant bank into uniform registers.
+__constant__ float4 gf3_w64ab[64] = {
+    {1.000000000e+00f, 0.000000000e+00f, 0.000000000e+00f, 1.000000000e+00f},
+    {9.951847267e-01f, -9.801714033e-02f, 9.801714033e-02f, 9.951847267e-01f},
+    {9.807852804e-01f, -1.950903220e-01f, 1.950903220e-01f, 9.807852804e-01f},
+    {9.569403357e-01f, -2.902846773e-01f, 2.902846773e-01f, 9.569403357e-01f},
+    {9.238795325e-01f, -3.826834324e-01f, 3.826834324e-01f, 9.238795325e-01f},
+    {8.819212643e-01f, -4.713967368e-01f, 4.713967368e-01f, 8.819212643e-01f},
+    {8.314696123e-01f, -5.555702330e-01f, 5.555702330e-01f, 8.314696123e-01f},
+    {7.730104534e-01f, -6.343932842e-01f, 6.343932842e-01f, 7.730104534e-01f},
+    {7.071067812e-01f, -7.071067812e-01f, 7.071067812e-01f, 7.071067812e-01f},
+    {6.343932842e-01f, -7.730104534e-01f, 7.730104534e-01f, 6.343932842e-01f},
+    {5.555702330e-01f, -8.314696123e-01f, 8.314696123e-01f, 5.555702330e-01f},
+    {4.713967368e-01f, -8.819212643e-01f, 8.819212643e-01f, 4.713967368e-01f},
+    {3.826834324e-01f, -9.238795325e-01f, 9.238795325e-01f, 3.826834324e-01f},
+    {2.902846773e-01f, -9.569403357e-01f, 9.569403357e-01f, 2.902846773e-01f},
+    {1.950903220e-01f, -9.807852804e-01f, 9.807852804e-01f, 1.950903220e-01f},
+    {9.801714033e-02f, -9.951847267e-01f, 9.951847267e-01f, 9.801714033e-02f},
+    {0.000000000e+00f, -1.000000000e+00f, 1.000000000e+00f, 0.000000000e+00f},
+    {-9.801714033e-02f, -9.951847267e-01f, 9.951847267e-01f, -9.801714033e-02f},
+    {-1.950903220e-01f, -9.807852804e-01f, 9.807852804e-01f, -1.950903220e-01f},
+    {-2.902846773e-01f, -9.569403357e-01f, 9.569403357e-01f, -2.902846773e-01f},
+    {-3.826834324e-01f, -9.238795325e-01f, 9.238795325e-01f, -3.826834324e-01f},
+    {-4.713967368e-01f, -8.819212643e-01f, 8.819212643e-01f, -4.713967368e-01f},
+    {-5.555702330e-01f, -8.314696123e-01f, 8.314696123e-01f, -5.555702330e-01f},
+    {-6.343932842e-01f, -7.730104534e-01f, 7.730104534e-01f, -6.343932842e-01f},
+    {-7.071067812e-01f, -7.071067812e-01f, 7.071067812e-01f, -7.071067812e-01f},
+    {-7.730104534e-01f, -6.343932842e-01f, 6.343932842e-01f, -7.730104534e-01f},
+    {-8.314696123e-01f, -5.555702330e-01f, 5.555702330e-01f, -8.314696123e-01f},
+    {-8.819212643e-01f, -4.713967368e-01f, 4.713967368e-01f, -8.819212643e-01f},
+    {-9.238795325e-01f, -3.826834324e-01f, 3.826834324e-01f, -9.238795325e-01f},
+    {-9.569403357e-01f, -2.902846773e-01f, 2.902846773e-01f, -9.569403357e-01f},
+    {-9.807852804e-01f, -1.950903220e-01f, 1.950903220e-01f, -9.807852804e-01f},
+    {-9.951847267e-01f, -9.801714033e-02f, 9.801714033e-02f, -9.951847267e-01f},
+    {-1.000000000e+00f, 0.000000000e+00f, 0.000000000e+00f, -1.000000000e+00f},
+    {-9.951847267e-01f, 9.801714033e-02f, -9.801714033e-02f, -9.951847267e-01f},
+    {-9.807852804e-01f, 1.950903220e-01f, -1.950903220e-01f, -9.807852804e-01f},
+    {-9.569403357e-01f, 2.902846773e-01f, -2.902846773e-01f, -9.569403357e-01f},
+    {-9.238795325e-01f, 3.826834324e-01f, -3.826834324e-01f, -9.238795325e-01f},
+    {-8.819212643e-01f, 4.713967368e-01f, -4.713967368e-01f, -8.819212643e-01f},
+    {-8.314696123e-01f, 5.555702330e-01f, -5.555702330e-01f, -8.314696123e-01f},
+    {-7.730104534e-01f, 6.343932842e-01f, -6.343932842e-01f, -7.730104534e-01f},
+    {-7.071067812e-01f, 7.071067812e-01f, -7.071067812e-01f, -7.071067812e-01f},
+    {-6.343932842e-01f, 7.730104534e-01f, -7.730104534e-01f, -6.343932842e-01f},
+    {-5.555702330e-01f, 8.314696123e-01f, -8.314696123e-01f, -5.555702330e-01f},
+    {-4.713967368e-01f, 8.819212643e-01f, -8.819212643e-01f, -4.713967368e-01f},
+    {-3.826834324e-01f, 9.238795325e-01f, -9.238795325e-01f, -3.826834324e-01f},
+    {-2.902846773e-01f, 9.569403357e-01f, -9.569403357e-01f, -2.902846773e-01f},
+    {-1.950903220e-01f, 9.807852804e-01f, -9.807852804e-01f, -1.950903220e-01f},
+    {-9.801714033e-02f, 9.951847267e-01f, -9.951847267e-01f, -9.801714033e-02f},
+    {0.000000000e+00f, 1.000000000e+00f, -1.000000000e+00f, 0.000000000e+00f},
+    {9.801714033e-02f, 9.951847267e-01f, -9.951847267e-01f, 9.801714033e-02f},
+    {1.950903220e-01f, 9.807852804e-01f, -9.807852804e-01f, 1.950903220e-01f},
+    {2.902846773e-01f, 9.569403357e-01f, -9.569403357e-01f, 2.902846773e-01f},
+    {3.826834324e-01f, 9.238795325e-01f, -9.238795325e-01f, 3.826834324e-01f},
+    {4.713967368e-01f, 8.819212643e-01f, -8.819212643e-01f, 4.713967368e-01f},
+    {5.555702330e-01f, 8.314696123e-01f, -8.314696123e-01f, 5.555702330e-01f},
+    {6.343932842e-01f, 7.730104534e-01f, -7.730104534e-01f, 6.343932842e-01f},
+    {7.071067812e-01f, 7.071067812e-01f, -7.071067812e-01f, 7.071067812e-01f},
+    {7.730104534e-01f, 6.343932842e-01f, -6.343932842e-01f, 7.730104534e-01f},
+    {8.314696123e-01f, 5.555702330e-01f, -5.555702330e-01f, 8.314696123e-01f},
+    {8.819212643e-01f, 4.713967368e-01f, -4.713967368e-01f, 8.819212643e-01f},
+    {9.238795325e-01f, 3.826834324e-01f, -3.826834324e-01f, 9.238795325e-01f},
+    {9.569403357e-01f, 2.902846773e-01f, -2.902846773e-01f, 9.569403357e-01f},
+    {9.807852804e-01f, 1.950903220e-01f, -1.950903220e-01f, 9.807852804e-01f},
+    {9.951847267e-01f, 9.801714033e-02f, -9.801714033e-02f, 9.951847267e-01f}};
+
+// packed complex multiply: a * w with w given as A = (wr, wi), B = (-wi, wr); FMUL2 + FFMA2, the
+// components of a enter through the scalar-broadcast operand form
+__device__ __forceinline__ float2 cmul_ab(float2 a, float4 w) {
+    return pk_fma(make_float2(a.y, a.y), make_float2(w.z, w.w), pk_mul(make_float2(a.x, a.x), make_float2(w.x, w.y)));
+}
+
 // a * exp(-2*pi*j * NUM/DEN)   (compile-time; multiples of 45 degrees need no general multiply)
 template <int NUM, int DEN>
 __device__ __forceinline__ float2 mul_w(float2 a) {
@@ -105,16 +185,23 @@ __device__ __forceinline__ float2 mul_w(float2 a) {
     else if constexpr (4 * n == DEN) return make_float2(a.y, -a.x);        // -j
     else if constexpr (2 * n == DEN) return make_float2(-a.x, -a.y);       // -1
     else if constexpr (4 * n == 3 * DEN) return make_float2(-a.y, a.x);    // +j
-    else if constexpr ((8 * n) % DEN == 0) {
-        constexpr float h = 0.70710678118654752440f;
-        constexpr int o = (8 * n) / DEN;                                   // 1, 3, 5, 7
-        constexpr float c = (o == 1 || o == 7) ? h : -h;                   // cos
-        constexpr float sn = (o == 1 || o == 3) ? h : -h;                  // sin
-        return make_float2(c * a.x + sn * a.y, c * a.y - sn * a.x);
-    } else {
-        constexpr float c = (float)cx_cos2pi(n, DEN);
-        constexpr float sn = (float)cx_sin2pi(n, DEN);
-        return make_float2(fmaf(c, a.x, sn * a.y), fmaf(c, a.y, -sn * a.x));
+    else {
+#ifndef GF3_SCALAR_CMUL
+        static_assert(64 % DEN == 0, "constant twiddle table covers divisors of 64");
+        return cmul_ab(a, gf3_w64ab[n * (64 / DEN)]);
+#else
+        if constexpr ((8 * n) % DEN == 0) {
+            constexpr float h = 0.70710678118654752440f;
+            constexpr int o = (8 * n) / DEN;                                   // 1, 3, 5, 7
+            constexpr float c = (o == 1 || o == 7) ? h : -h;                   // cos
+            constexpr float sn = (o == 1 || o == 3) ? h : -h;                  // sin
+            return make_float2(c * a.x + sn * a.y, c * a.y - sn * a.x);
+        } else {
+            constexpr float c = (float)cx_cos2pi(n, DEN);
+            constexpr float sn = (float)cx_sin2pi(n, DEN);
+            return make_float2(fmaf(c, a.x, sn * a.y), fmaf(c, a.y, -sn * a.x));
+        }
+#endif
     }
 }
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "gf3_tx_modulate": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "gf3_channel_sim": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_uint64, c_void_p, c_int64, c_void_p]),
     "gf3_ber_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "gf3_pcm_to_f32": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None

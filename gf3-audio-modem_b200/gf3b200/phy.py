@@ -221,6 +221,14 @@ class Phy:
         check(self.lib.gf3_ber_count(_ptr(a), _ptr(b), nbits, _ptr(counter), _stream()))
         return counter
 
+    def pcm_to_f32(self, pcm, out=None):
+        """uint8 / int16 PCM device tensor -> float32 (exact values, no DC removal)."""
+        assert pcm.is_cuda and pcm.is_contiguous() and pcm.dtype in (torch.uint8, torch.int16)
+        if out is None:
+            out = torch.empty(pcm.shape, dtype=torch.float32, device=self.device)
+        check(self.lib.gf3_pcm_to_f32(_ptr(pcm), 0 if pcm.dtype == torch.uint8 else 1, pcm.numel(), _ptr(out), _stream()))
+        return out
+
     # ------------------------------------------------------------------ whole receive chain
     def receive_packets(self, samples, n_packets, pkt_offset=None, xor=True, want_eq=False):
         """estimate + demod for n_packets packets whose starts are known."""

@@ -45,7 +45,7 @@ enum {
 
 /* Parameter contract of CamG.__init__ (OFDM.py:18-101), generalised to any power-of-two N. */
 typedef struct gf3_params {
-    int32_t N;            /* OFDM.py:27   ofdm_symbol_size (power of two, 64..8192)        */
+    int32_t N;            /* OFDM.py:27   ofdm_symbol_size (power of two, 64..4096)        */
     int32_t cp;           /* OFDM.py:42   cyclic prefix length (even)                      */
     int32_t lo;           /* OFDM.py:43   lowest data bin, inclusive (>= 1)                */
     int32_t hi;           /* OFDM.py:44,47 highest data bin, EXCLUSIVE (<= N/2)            */
@@ -164,6 +164,10 @@ GF3_API int gf3_tx_modulate(const gf3_plan* plan, const uint8_t* bits_packed, in
 GF3_API int gf3_channel_sim(const float* x, int64_t x_stride, int64_t n_streams, int64_t T,
                     const float* taps, int32_t n_taps, const float* sigma, uint64_t seed,
                     float* y, int64_t y_stride, void* stream);
+/* PCM ingest (Final System Test.ipynb:85-86 does `r = r/1.0` on the wav's native samples): plain
+ * value conversion to float32 on the device, no DC removal (the reference keeps the uint8 offset of
+ * 128), so narrow samples cross PCIe instead of floats.  format: 0 = uint8, 1 = int16.           */
+GF3_API int gf3_pcm_to_f32(const void* pcm, int32_t format, int64_t n, float* out, void* stream);
 /* counter[0] += popcount(a ^ b) over nbits (MSB-first packed), counter[1] += nbits. */
 GF3_API int gf3_ber_count(const uint8_t* a, const uint8_t* b, int64_t nbits, uint64_t* counter,
                   void* stream);

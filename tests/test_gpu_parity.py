@@ -387,3 +387,36 @@ def test_results_independent_of_launch_geometry(known_sequence):
             small = phy.rx_demod(sym[lo_:hi_].reshape(-1), hi_ - lo_, Hs[lo_:hi_].contiguous(), He[lo_:hi_].contiguous(),
                                  slope[lo_:hi_].contiguous())
             assert torch.equal(small, big[lo_:hi_]), (packed, lo_)
+
+
+def test_pcm_ingest(known_sequence, capsys):
+    """uint8 / int16 PCM ingest: exact value conversion on the device; the real recording decoded
+    from its native uint8 samples gives the same bits as from `r/1.0` (Final System Test.ipynb:86)."""
+    torch = _torch()
+    import gf3b200
+    import OFDM
+    from gf3b200.host import HostReceiver
+    phy = gf3b200.Phy(N=256, cp=16, lo=3, hi=100, n_pilots=2, packet_len=8, known_sequence=known_sequence, fit_lo=10, fit_hi=90)
+    rng = np.random.default_rng(0)
+    for dt, lo_, hi_ in ((np.uint8, 0, 256), (np.int16, -32768, 32768)):
+        a = rng.integers(lo_, hi_, 100003).astype(dt)
+        out = phy.pcm_to_f32(torch.from_numpy(a).cuda()).cpu().numpy()
+        assert out.dtype == np.float32 and np.array_equal(out, a.astype(np.float32))
+    g = load_golden("kat1_gr5ch1.npz")
+    rx = OFDM.receiver(mode="A2", encoding="XOR")
+    b1, _, _ = rx.receive(g["wav_u8"])               # native uint8
+    b2, _, _ = rx.receive(g["wav_u8"] / 1.0)         # the notebook's float conversion
+    capsys.readouterr()
+    assert np.array_equal(b1, b2)
+    # host-buffer receiver fed with int16 packets == float32 packets holding the same values
+    gl = load_golden("stage_w1024.npz")
+    phy2 = _phy(oracle_params(gl["cfg"], known_sequence))
+    starts = (gl["peaks"] + 2)[:-1]
+    pk = np.stack([gl["r_i16"][s:s + phy2.pkt_samples] for s in starts])
+    h16 = torch.from_numpy(pk.astype(np.int16)).pin_memory()
+    h32 = torch.from_numpy(pk.astype(np.float32)).pin_memory()
+    o16 = HostReceiver(phy2, len(starts), sample_dtype=torch.int16).run(h16).clone()
+    o32 = HostReceiver(phy2, len(starts)).run(h32).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(o16, o32)
+    assert np.array_equal(phy2.unpack_bits(o16), gl["bits"])
