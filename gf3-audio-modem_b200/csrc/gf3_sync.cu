@@ -46,7 +46,10 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
     const int tid = threadIdx.x;
     for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
     const int g = tid / T, t = tid % T;
-    const int64_t blk_global = (int64_t)blockIdx.x * SF + g;
+    const int64_t n_work = (a.n_streams * a.nblk + SF - 1) / SF;
+    // persistent: the twiddle table (~30 KB) is staged once per CTA, not once per pair of blocks
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
+    const int64_t blk_global = work * SF + g;
     const int64_t stream = blk_global / a.nblk;
     const int b = (int)(blk_global % a.nblk);
     const bool live = stream < a.n_streams;
@@ -55,6 +58,12 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
     {
         const float* row = a.r + (live ? stream : 0) * a.r_stride;
         const int64_t s0 = (int64_t)b * kB - kB + a.in_off;
+        const bool fast = live && !a.reverse && s0 >= 0 && s0 + 2 * kB <= a.T && a.valid_len >= 2 * kB &&
+                          ((reinterpret_cast<uintptr_t>(row + s0) & 7) == 0);
+        if (fast) {      // interior block, 8-byte aligned: vector loads without bounds checks
+#pragma unroll
+            for (int i = 0; i < R; ++i) x[i] = *reinterpret_cast<const float2*>(row + s0 + 2 * (t + i * T));
+        } else {
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             const int loc = 2 * (t + i * T);
@@ -73,6 +82,7 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
             }
             x[i] = make_float2(v0, v1);
         }
+        }
     }
     __syncthreads();
     fft_forward<P, NT>(x, zbuf + g * MP, tw, t, g);
@@ -80,7 +90,7 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
     // untangle: X[k] = (s + w2 d)/2, X[M-k] = conj(s - w2 d)/2
     for (int item = tid; item < SF * (M / 2 + 1); item += NT) {
         const int gg = item / (M / 2 + 1), k = item % (M / 2 + 1), km = M - k;
-        const int64_t bg = (int64_t)blockIdx.x * SF + gg;
+        const int64_t bg = work * SF + gg;
         if (bg / a.nblk >= a.n_streams) continue;
         const float2* zs = zbuf + gg * MP;
         float2* out = a.spec + bg * M;
@@ -99,6 +109,7 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
             if (km != k) out[km] = x2;
         }
     }
+    }
 }
 
 struct AccArgs {
@@ -109,6 +120,7 @@ struct AccArgs {
     float* pmax;             // [n_streams]
     int64_t p_stride, out_len;   // out_len = T + Lc - 1
     int nblk_in, nblk_out, parts;
+    int64_t n_work;          // n_streams * nblk_out
 };
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
@@ -128,8 +140,12 @@ __global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
     __shared__ float wmax[NT / 32];
     const int tid = threadIdx.x;
     for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
-    const int64_t stream = blockIdx.x / a.nblk_out;
-    const int b = (int)(blockIdx.x % a.nblk_out);
+    // persistent: the twiddle table is staged once per CTA; co-resident CTAs work on neighbouring
+    // blocks, so the chirp-partition spectra and the shared input spectra stay hot in L2
+    for (int64_t work = blockIdx.x; work < a.n_work; work += gridDim.x) {
+    const int64_t stream = work / a.nblk_out;
+    const int b = (int)(work % a.nblk_out);
+    __syncthreads();
 
     float2 acc1[PPT], acc2[PPT];
 #pragma unroll
@@ -204,6 +220,7 @@ __global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
         for (int w = 1; w < NT / 32; ++w) m = fmaxf(m, wmax[w]);
         if (m > __int_as_float(0xff800000)) atomic_max_float(a.pmax + stream, m);
     }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -272,8 +289,10 @@ static int run_fwd(const float* r, int64_t r_stride, int64_t n_streams, int64_t 
     f.nblk = nblk; f.reverse = reverse; f.in_off = in_off; f.valid_len = valid_len;
     const size_t smem = (size_t)(SF * SP::MP + SP::TW_TOTAL) * sizeof(float2);
     GF3_CHECK_CUDA(cudaFuncSetAttribute(xcorr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t gx = (n_streams * nblk + SF - 1) / SF;
-    GF3_REQUIRE(gx <= 0x7fffffff, "xcorr: too many blocks in one tile");
+    int64_t gx = (n_streams * nblk + SF - 1) / SF;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (gx > (int64_t)sms * 3 * 4) gx = (int64_t)sms * 3 * 4;       // 3 CTAs / SM resident, ~4 work items each at least
     xcorr_fwd_kernel<<<(unsigned)gx, kSyncThreads, smem, st>>>(f);
     GF3_LAUNCH_CHECK();
     return GF3_OK;
@@ -348,8 +367,9 @@ extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride,
         AccArgs a;
         a.spec = spec; a.H = plan->d_chirp_spec; a.tw = plan->d_sync_tw; a.P = P + s0 * p_stride; a.pmax = pmax + s0;
         a.p_stride = p_stride; a.out_len = g.out_len; a.nblk_in = g.nblk_in; a.nblk_out = g.nblk_out; a.parts = plan->sync_parts;
-        const int64_t grid = ns * g.nblk_out;
-        GF3_REQUIRE(grid <= 0x7fffffff, "xcorr: grid too large");
+        a.n_work = ns * g.nblk_out;
+        int64_t grid = a.n_work;
+        if (grid > (int64_t)plan->sm_count * 4 * 4) grid = (int64_t)plan->sm_count * 4 * 4;
         xcorr_acc_kernel<<<(unsigned)grid, 128, smem, st>>>(a);
         GF3_LAUNCH_CHECK();
     }
