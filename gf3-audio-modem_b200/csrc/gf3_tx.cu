@@ -128,16 +128,21 @@ __global__ void __launch_bounds__(kTxThreads, 2) tx_symbols_kernel(const TxArgs 
     for (int item = tid; item < nsym * M; item += NT) {
         const int s = item / M, m = item % M;
         const float2 y = zbuf[s * MP + zpad<P>(m)];
-        const float v0 = y.x * a.gain, v1 = -y.y * a.gain;
+        const float2 v = make_float2(y.x * a.gain, -y.y * a.gain);
         float* o;
         if constexpr (KNOWN_SYMBOL) o = a.out;
         else o = a.out + stream * a.out_stride + pk * ((int64_t)a.chirp_len + (int64_t)(2 * a.P + a.L) * symlen)
                  + a.chirp_len + (int64_t)(a.P + l_first + s) * symlen;
-        o[a.cp + 2 * m] = v0;
-        o[a.cp + 2 * m + 1] = v1;
-        const int n0 = 2 * m - (N - a.cp);
-        if (n0 >= 0) o[n0] = v0;
-        if (n0 + 1 >= 0) o[n0 + 1] = v1;
+        const int n0 = 2 * m - (N - a.cp);                       // position of this pair inside the cyclic prefix
+        if (((reinterpret_cast<uintptr_t>(o) | (uintptr_t)(a.cp * 4)) & 7) == 0) {       // 8-byte aligned symbol and even CP
+            *reinterpret_cast<float2*>(o + a.cp + 2 * m) = v;
+            if (n0 >= 0) *reinterpret_cast<float2*>(o + n0) = v;
+        } else {
+            o[a.cp + 2 * m] = v.x;
+            o[a.cp + 2 * m + 1] = v.y;
+            if (n0 >= 0) o[n0] = v.x;
+            if (n0 + 1 >= 0) o[n0 + 1] = v.y;
+        }
     }
 }
 
@@ -147,31 +152,29 @@ struct FrameArgs {
     const float* known_time;    // [N + cp], gain applied
     float* out;
     int64_t out_stride, pk_per_stream, n_streams;
-    int symlen, P, L, chirp_len;
+    int symlen, P, L, chirp_len, gx;
 };
 
+// row = blockIdx.x / gx = stream * (pk_per_stream + 1) + packet; the extra "packet" is the trailing chirp
+// (OFDM.py:259).  Each row copies [chirp | P x known | (L data symbols skipped) | P x known].
 __global__ void __launch_bounds__(256) tx_frame_kernel(const FrameArgs a) {
+    const int rows_per_stream = (int)a.pk_per_stream + 1;
+    const int64_t row = blockIdx.x / a.gx;
+    const int bx = blockIdx.x % a.gx;
+    const int64_t stream = row / rows_per_stream;
+    const int pk = (int)(row % rows_per_stream);
     const int64_t pkt_len = (int64_t)a.chirp_len + (int64_t)(2 * a.P + a.L) * a.symlen;
-    const int64_t per_pkt = (int64_t)a.chirp_len + (int64_t)2 * a.P * a.symlen;
-    const int64_t per_stream = per_pkt * a.pk_per_stream + a.chirp_len;
-    const int64_t total = per_stream * a.n_streams;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t stream = i / per_stream;
-        int64_t r = i % per_stream;
-        float* o = a.out + stream * a.out_stride;
-        if (r >= per_pkt * a.pk_per_stream) {                        // trailing chirp (OFDM.py:259)
-            const int64_t n = r - per_pkt * a.pk_per_stream;
-            o[pkt_len * a.pk_per_stream + n] = a.chirp[n];
-            continue;
+    float* o = a.out + stream * a.out_stride + (int64_t)pk * pkt_len;
+    const int seg = (pk == (int)a.pk_per_stream) ? a.chirp_len : a.chirp_len + 2 * a.P * a.symlen;
+    for (int i = bx * blockDim.x + threadIdx.x; i < seg; i += a.gx * blockDim.x) {
+        if (i < a.chirp_len) {
+            o[i] = a.chirp[i];
+        } else {
+            const int r = i - a.chirp_len;
+            const int sidx = r / a.symlen, n = r - sidx * a.symlen;     // sidx in [0, 2P)
+            const int slot = sidx < a.P ? sidx : sidx + a.L;
+            o[a.chirp_len + (int64_t)slot * a.symlen + n] = a.known_time[n];
         }
-        const int64_t pk = r / per_pkt;
-        r %= per_pkt;
-        o += pk * pkt_len;
-        if (r < a.chirp_len) { o[r] = a.chirp[r]; continue; }
-        r -= a.chirp_len;
-        const int64_t s = r / a.symlen, n = r % a.symlen;           // s in [0, 2P)
-        const int64_t slot = s < a.P ? s : s + a.L;
-        o[a.chirp_len + slot * a.symlen + n] = a.known_time[n];
     }
 }
 
@@ -228,12 +231,13 @@ static int launch_tx(const gf3_plan* plan, TxArgs a, const float* known, int64_t
         f.chirp = plan->d_chirp; f.known_time = known_time; f.out = a.out; f.out_stride = a.out_stride;
         f.pk_per_stream = a.pk_per_stream; f.n_streams = n_streams; f.symlen = p.N + p.cp; f.P = a.P; f.L = a.L;
         f.chirp_len = p.chirp_len;
-        const int64_t total = ((int64_t)p.chirp_len + 2LL * a.P * f.symlen) * a.pk_per_stream * n_streams + (int64_t)p.chirp_len * n_streams;
-        int64_t blocks = (total + 256 * 8 - 1) / (256 * 8);
-        const int64_t cap = (int64_t)plan->sm_count * 16;
-        if (blocks > cap) blocks = cap;
-        if (blocks < 1) blocks = 1;
-        tx_frame_kernel<<<(unsigned)blocks, 256, 0, st>>>(f);
+        const int seg = p.chirp_len + 2 * a.P * f.symlen;
+        int gx = (seg + 256 * 4 - 1) / (256 * 4);
+        if (gx < 1) gx = 1;
+        f.gx = gx;
+        const int64_t rows = n_streams * (a.pk_per_stream + 1);
+        GF3_REQUIRE(rows * gx <= 0x7fffffff, "tx_modulate: too many packets in one call");
+        tx_frame_kernel<<<(unsigned)(rows * gx), 256, 0, st>>>(f);
         GF3_LAUNCH_CHECK();
     }
     return GF3_OK;
