@@ -56,8 +56,6 @@ struct gf3_plan {
     int device;
     int sm_count;
     float2* d_tw;        // FFT twiddle table of the N-point symbol plan
-    int use_packed;      // 1: data-symbol kernel uses the packed f32x2 warp-specialised variant (env GF3_DEMOD_PACKED)
-    float2* d_tw_pk;     // twiddles of the packed (two-lane) data-symbol plan, when one exists for this N
     float2* d_ones;      // K ones (unit channel for gf3_rx_spectrum)
     // sync (overlap-save matched filter): block FFT size NB real samples, hop HB
     int sync_logN;       // log2 of the overlap-save FFT length

@@ -345,28 +345,47 @@ __host__ __device__ constexpr int zstride() {
     return S == 1 ? 1 : S + (S >> P::LOGPAD);
 }
 
+#ifndef GF3_FFT_SPLIT
+#define GF3_FFT_SPLIT 0
+#endif
 // One Stockham pass.  x[q*RAD + i]: thread-local data; zs: this symbol's padded smem buffer;
 // tw: twiddle table in smem; t: thread index within the symbol group.
-template <class P, int NTHREADS, int PASS>
+//
+// NATURAL (last pass only): the spectrum is written in natural order WITHOUT padding.  Every store
+// instruction of the last pass writes runs of consecutive bins, which are conflict-free in any
+// layout, and the bin-pair walk of the data-symbol kernel (ascending k, descending M-k) then reads
+// conflict-free too (with padding, 16 descending bins straddle a pad slot and collide 2-way).
+//
+// Half-warp symbol groups (T == 16, Q == 2): both halves of a warp would fetch the SAME 16 twiddles
+// per load instruction (two shared-memory wavefronts for 128 useful bytes).  The upper half-warp
+// therefore takes its two sub-transforms in the opposite order (q ^ 1), so one load instruction
+// fetches 32 distinct twiddles.  Register names stay static; only addresses depend on the half.
+template <class P, int NTHREADS, int PASS, bool NATURAL = false>
 __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__ zs,
                                          const float2* __restrict__ tw, int t, int grp) {
     constexpr int RAD = P::rad(PASS), NS = P::ns(PASS), Q = P::R / RAD, STRIDE = P::M / RAD;
     static_assert(NS != 1 || RAD == (1 << P::LOGPAD), "first pass radix must equal the padding period");
+    static_assert(!NATURAL || PASS == P::NPASS - 1, "natural-order output is for the last pass");
+    constexpr bool SPLIT = GF3_FFT_SPLIT && (P::T == 16 && Q == 2 && PASS > 0);
+    int hq = 0;                                         // 0/1: this thread's sub-transform order is flipped
+    if constexpr (SPLIT) hq = (threadIdx.x >> 4) & 1;
     if constexpr (PASS > 0) {
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
-            const float2* src = zs + zpad<P>(t + q * P::T);
+            const int qq = SPLIT ? (q ^ hq) : q;
+            const float2* src = zs + zpad<P>(t + qq * P::T);
             static_for<RAD>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 x[q * RAD + i] = src[i * zstride<P, STRIDE>()];
             });
         });
-        const float2* twp = tw + P::tw_off(PASS) + t;
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
+            const int qq = SPLIT ? (q ^ hq) : q;
+            const float2* twp = tw + P::tw_off(PASS) + t + qq * ((RAD - 1) * P::T);
             static_for<RAD - 1>([&](auto ic) {
                 constexpr int i = decltype(ic)::value + 1;
-                x[q * RAD + i] = cmul(x[q * RAD + i], twp[(q * (RAD - 1) + (i - 1)) * P::T]);
+                x[q * RAD + i] = cmul(x[q * RAD + i], twp[(i - 1) * P::T]);
             });
         });
         group_sync<P, NTHREADS>(grp);   // every thread of the symbol has read before anyone overwrites
@@ -377,121 +396,38 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
     });
     static_for<Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
-        const int j = t + q * P::T;
+        const int qq = SPLIT ? (q ^ hq) : q;
+        const int j = t + qq * P::T;
         const int base = (j / NS) * (NS * RAD) + (j % NS);
-        float2* dst = zs + zpad<P>(base);
-        static_for<RAD>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            dst[i * zstride<P, NS>()] = x[q * RAD + i];
-        });
+        if constexpr (NATURAL) {
+            float2* dst = zs + base;
+            static_for<RAD>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                dst[i * NS] = x[q * RAD + i];
+            });
+        } else {
+            float2* dst = zs + zpad<P>(base);
+            static_for<RAD>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                dst[i * zstride<P, NS>()] = x[q * RAD + i];
+            });
+        }
     });
     group_sync<P, NTHREADS>(grp);
 }
 
 // Full forward FFT of one symbol.  On entry x[i] = z[t + i*T] (i < R); on exit the natural-order
-// spectrum Z[0..M) sits in zs (padded indexing) and is visible to the symbol's T threads.
-template <class P, int NTHREADS>
+// spectrum Z[0..M) sits in zs (padded indexing, or plain indexing when NATURAL) and is visible to
+// the symbol's T threads.
+template <class P, int NTHREADS, bool NATURAL = false>
 __device__ __forceinline__ void fft_forward(float2 (&x)[P::R], float2* __restrict__ zs,
                                             const float2* __restrict__ tw, int t, int grp) {
     fft_pass<P, NTHREADS, 0>(x, zs, tw, t, grp);
-    fft_pass<P, NTHREADS, 1>(x, zs, tw, t, grp);
-    if constexpr (P::NPASS > 2) fft_pass<P, NTHREADS, 2>(x, zs, tw, t, grp);
-}
-
-// ---------------------------------------------------------------- packed (two-lane) plans
-// N real samples -> M = N/2 complex points -> one radix-2 decimation-in-frequency stage in scalar
-// arithmetic (u = z[h] + z[h+H], v = (z[h] - z[h+H]) W_M^h) -> two H = M/2 point FFTs, U and V,
-// carried in the two f32x2 lanes through the same Stockham passes.  U[k] = Z[2k], V[k] = Z[2k+1].
-// Shared-memory entries are float4 (U.re, V.re, U.im, V.im).
-template <int LOGN_, int R_, int NPASS_, int R0_, int R1_, int R2_>
-struct PkPlanT {
-    static constexpr int LOGN = LOGN_, N = 1 << LOGN_, M = N / 2, H = M / 2, R = R_, T = H / R_;
-    static constexpr int NPASS = NPASS_;
-    static constexpr int LOGPAD = (R_ == 32 ? 5 : R_ == 16 ? 4 : 3);
-    static constexpr int HP = H + (H >> LOGPAD);      // padded float4 entries per symbol
-    __host__ __device__ static constexpr int rad(int p) { return p == 0 ? R0_ : p == 1 ? R1_ : R2_; }
-    __host__ __device__ static constexpr int ns(int p) { return p == 0 ? 1 : p == 1 ? R0_ : R0_ * R1_; }
-    static constexpr int TWD = H;                     // first-stage twiddles W_M^h, h < H
-    static constexpr int TW1 = (R_ / R1_) * (R1_ - 1) * T;
-    static constexpr int TW2 = NPASS_ > 2 ? (R_ / R2_) * (R2_ - 1) * T : 0;
-    __host__ __device__ static constexpr int tw_off(int p) { return p <= 1 ? TWD : TWD + TW1; }
-    static constexpr int TW_TOTAL = TWD + TW1 + TW2;
-    static_assert(R0_ == R_ && R0_ * R1_ * R2_ == H, "radices must multiply to H and start with R");
-};
-struct PkPlan10 : PkPlanT<10, 16, 2, 16, 16, 1> {};   // N=1024: H=256,  T=16 (half warp per symbol)
-struct PkPlan12 : PkPlanT<12, 16, 3, 16, 16, 4> {};   // N=4096: H=1024, T=64 (two warps per symbol)
-
-template <class P> struct PkPad {   // adapter so zpad / zstride work on entry indices of a packed plan
-    static constexpr int LOGPAD = P::LOGPAD;
-};
-
-template <class P, int NTHREADS, int PASS>
-__device__ __forceinline__ void pk_fft_pass(cpk (&x)[P::R], float4* __restrict__ zs,
-                                            const float2* __restrict__ tw, int t, int grp) {
-    constexpr int RAD = P::rad(PASS), NS = P::ns(PASS), Q = P::R / RAD, STRIDE = P::H / RAD;
-    static_assert(NS != 1 || RAD == (1 << P::LOGPAD), "first pass radix must equal the padding period");
-    if constexpr (PASS > 0) {
-        static_for<Q>([&](auto qc) {
-            constexpr int q = decltype(qc)::value;
-            const float4* src = zs + zpad<P>(t + q * P::T);
-            static_for<RAD>([&](auto ic) {
-                constexpr int i = decltype(ic)::value;
-                const float4 e = src[i * zstride<P, STRIDE>()];
-                x[q * RAD + i] = cpk{make_float2(e.x, e.y), make_float2(e.z, e.w)};
-            });
-        });
-        const float2* twp = tw + P::tw_off(PASS) + t;
-        static_for<Q>([&](auto qc) {
-            constexpr int q = decltype(qc)::value;
-            static_for<RAD - 1>([&](auto ic) {
-                constexpr int i = decltype(ic)::value + 1;
-                x[q * RAD + i] = cmul_s(x[q * RAD + i], twp[(q * (RAD - 1) + (i - 1)) * P::T]);
-            });
-        });
-        group_sync<P, NTHREADS>(grp);
-    }
-    static_for<Q>([&](auto qc) {
-        constexpr int q = decltype(qc)::value;
-        Dft<RAD>::run(&x[q * RAD]);
-    });
-    static_for<Q>([&](auto qc) {
-        constexpr int q = decltype(qc)::value;
-        const int j = t + q * P::T;
-        const int base = (j / NS) * (NS * RAD) + (j % NS);
-        float4* dst = zs + zpad<P>(base);
-        static_for<RAD>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            const cpk v = x[q * RAD + i];
-            dst[i * zstride<P, NS>()] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y);
-        });
-    });
-    group_sync<P, NTHREADS>(grp);
-}
-
-// Both half-size FFTs of one symbol.  On entry x[i] = (u, v)[t + i*T]; on exit the natural-order
-// spectra U, V sit in zs (padded entry indexing).
-template <class P, int NTHREADS>
-__device__ __forceinline__ void pk_fft_forward(cpk (&x)[P::R], float4* __restrict__ zs,
-                                               const float2* __restrict__ tw, int t, int grp) {
-    pk_fft_pass<P, NTHREADS, 0>(x, zs, tw, t, grp);
-    pk_fft_pass<P, NTHREADS, 1>(x, zs, tw, t, grp);
-    if constexpr (P::NPASS > 2) pk_fft_pass<P, NTHREADS, 2>(x, zs, tw, t, grp);
-}
-
-template <class P>
-inline void fill_pk_twiddles(float2* out) {
-    const double PI2 = 2.0 * 3.14159265358979323846;
-    for (int h = 0; h < P::H; ++h) out[h] = make_float2((float)cos(-PI2 * h / P::M), (float)sin(-PI2 * h / P::M));
-    for (int pass = 1; pass < P::NPASS; ++pass) {
-        const int RAD = P::rad(pass), NS = P::ns(pass), Q = P::R / RAD;
-        float2* o = out + P::tw_off(pass);
-        for (int q = 0; q < Q; ++q)
-            for (int i = 1; i < RAD; ++i)
-                for (int t = 0; t < P::T; ++t) {
-                    const int j = t + q * P::T;
-                    const double ang = -PI2 * (double)((j % NS) * i) / (double)(NS * RAD);
-                    o[(q * (RAD - 1) + (i - 1)) * P::T + t] = make_float2((float)cos(ang), (float)sin(ang));
-                }
+    if constexpr (P::NPASS > 2) {
+        fft_pass<P, NTHREADS, 1>(x, zs, tw, t, grp);
+        fft_pass<P, NTHREADS, 2, NATURAL>(x, zs, tw, t, grp);
+    } else {
+        fft_pass<P, NTHREADS, 1, NATURAL>(x, zs, tw, t, grp);
     }
 }
 

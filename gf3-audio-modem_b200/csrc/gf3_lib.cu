@@ -112,19 +112,6 @@ extern "C" int gf3_plan_create(const gf3_params* p, gf3_plan** out) {
     GF3_CHECK_CUDA(cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device));
     rc = upload_twiddles(plan->logN, &plan->d_tw);
     if (rc) { delete plan; return rc; }
-    // The packed f32x2 variant of the data-symbol kernel (N = 1024) is opt-in until it beats the scalar
-    // one (profiles/): GF3_DEMOD_PACKED=1 selects it for plans created afterwards.
-    {
-        const char* e = getenv("GF3_DEMOD_PACKED");
-        plan->use_packed = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (plan->logN == 10 || plan->logN == 12) {      // packed two-lane plans of the data-symbol kernel
-        std::vector<float2> h;
-        if (plan->logN == 10) { h.resize(PkPlan10::TW_TOTAL); fill_pk_twiddles<PkPlan10>(h.data()); }
-        else { h.resize(PkPlan12::TW_TOTAL); fill_pk_twiddles<PkPlan12>(h.data()); }
-        GF3_CHECK_CUDA(cudaMalloc(&plan->d_tw_pk, h.size() * sizeof(float2)));
-        GF3_CHECK_CUDA(cudaMemcpy(plan->d_tw_pk, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    }
     const int K = p->N / 2 - 1;
     std::vector<float2> ones(K, make_float2(1.f, 0.f));
     GF3_CHECK_CUDA(cudaMalloc(&plan->d_ones, K * sizeof(float2)));
@@ -139,7 +126,6 @@ extern "C" int gf3_plan_destroy(gf3_plan* plan) {
     if (!plan) return GF3_OK;
     sync_plan_free(plan);
     if (plan->d_tw) cudaFree(plan->d_tw);
-    if (plan->d_tw_pk) cudaFree(plan->d_tw_pk);
     if (plan->d_ones) cudaFree(plan->d_ones);
     delete plan;
     return GF3_OK;

@@ -8,6 +8,8 @@
 //
 // HBM-bound streaming work: no tensor cores, grids sized in waves of the SM count, coalesced
 // 64/128-bit global access, FFT exchanges staged in shared memory.
+#include <stdlib.h>
+
 #include "gf3_common.cuh"
 #include "gf3_fft.cuh"
 
@@ -21,8 +23,17 @@ constexpr int kThreads = 256;
 #ifndef GF3_PREFETCH
 #define GF3_PREFETCH (-1)      // -1: per-plan default (see rx_demod_kernel)
 #endif
-#ifndef GF3_PK_L2_PREFETCH
-#define GF3_PK_L2_PREFETCH 1
+#ifndef GF3_DEMOD_CST
+#define GF3_DEMOD_CST 0
+#endif
+#ifndef GF3_PHASEB_UNROLL
+#define GF3_PHASEB_UNROLL 4
+#endif
+#ifndef GF3_DEMOD_NATURAL
+#define GF3_DEMOD_NATURAL 1
+#endif
+#ifndef GF3_ABL
+#define GF3_ABL 0
 #endif
 constexpr float kPi = 3.14159265358979323846f;
 
@@ -39,7 +50,8 @@ struct RxArgs {
     int64_t bits_stride;
     int64_t pkt_stride;          // (2P+L)(N+cp), used when pkt_offset == null
     int cp, lo, hi, P, L;
-    int chunks_per_packet, chunks_per_cta, ctas_per_packet;
+    int64_t n_packets;
+    int chunks_per_packet;       // flush chunks (work items) per packet = ceil(L / flush)
     int flush;                   // symbols per flush chunk
 };
 
@@ -79,6 +91,57 @@ __device__ __forceinline__ float4 lds128(const float4* p) {
     return v;
 }
 
+// f32x2 arithmetic on values that stay packed in 64-bit register pairs (no repacking per use)
+__device__ __forceinline__ pk64 p_add(pk64 a, pk64 b) { pk64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk64 p_sub(pk64 a, pk64 b) { pk64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk64 p_mul(pk64 a, pk64 b) { pk64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk64 p_fma(pk64 a, pk64 b, pk64 c) { pk64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ pk64 p_neg(pk64 a) { const float2 v = pk_unpack(a); return pk_pack(make_float2(-v.x, -v.y)); }
+__device__ __forceinline__ pk64 p_bc(float s) { return pk_pack(make_float2(s, s)); }
+__device__ __forceinline__ float p_lo(pk64 a) { return pk_unpack(a).x; }
+__device__ __forceinline__ float p_hi(pk64 a) { return pk_unpack(a).y; }
+// Hide how a per-thread constant was derived, so that it is kept in its register pair instead of
+// being rebuilt from a related value (negate + move, or immediates) at every use inside the hot
+// loop.  A volatile round trip through the thread's own shared-memory slot is opaque to both
+// compiler stages.
+__device__ __forceinline__ pk64 p_opaque(pk64 v, void* slot) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
+    asm volatile("st.volatile.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+    pk64 r;
+    asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(r) : "r"(addr) : "memory");
+    return r;
+}
+// predicated one-byte shared-memory store: the address is an operand, so the compiler cannot sink its
+// computation into a branch around the store
+__device__ __forceinline__ void sts_u8_if(unsigned addr, unsigned val, unsigned cond) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u8 [%0], %1;\n\t}" ::"r"(addr), "r"(val), "r"(cond) : "memory");
+}
+// 16-byte shared-memory load the compiler must not hoist out of its phase or re-materialise
+__device__ __forceinline__ ulonglong2 lds_v2(const ulonglong2* p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y)
+                 : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+// Option (GF3_DEMOD_CST=1): plans with many bin pairs per thread (N = 4096: 4) keep the per-thread
+// phase-B constants in shared memory and re-read them every batch instead of holding them in registers
+// through the FFT phase.  Off by default: at N = 4096 the extra 32 KB costs the second CTA per SM.
+template <class P, int NT>
+__host__ __device__ constexpr bool demod_cst_in_smem() {
+    constexpr int TB = (P::M / 2 < NT) ? P::M / 2 : NT;
+    return GF3_DEMOD_CST && (P::M / 2) / TB >= 4;
+}
+template <class P, int NT>
+__host__ __device__ constexpr size_t demod_cst_offset() {      // [zbuf | tw | cst (16-byte aligned) | stage | xorw]
+    return (((size_t)((NT / P::T) * P::MP + P::TW_TOTAL) * sizeof(float2)) + 15) & ~(size_t)15;
+}
+template <class P, int NT>
+__host__ __device__ constexpr size_t demod_cst_bytes() {
+    constexpr int TB = (P::M / 2 < NT) ? P::M / 2 : NT;
+    return demod_cst_in_smem<P, NT>() ? (size_t)2 * ((P::M / 2) / TB) * NT * 16 : 0;
+}
+constexpr int kReseed = 64;     // data symbols per work item = distance between exact re-seeds of the equaliser recurrence
+
 // exp(-j * a) for a double-precision phase a (reduced in double, evaluated in float)
 __device__ __forceinline__ float2 expmj(double a) {
     const double inv2pi = 0.15915494309189533577;
@@ -99,8 +162,8 @@ template <class P, int NT, int MINB, bool KNOWN_CH, bool WANT_EQ>
 __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
     constexpr int T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP;
     constexpr int SF = NT / T;                        // symbols per FFT batch
-    // symbols per packed-bit flush: a multiple of SF with FLUSH*Nd % 16 == 0, so every chunk starts
-    // on a 32-bit word of the packet's bit stream (chosen by the launcher)
+    // symbols per packed-bit flush: a multiple of SF that divides kReseed, with FLUSH*Nd % 16 == 0, so
+    // every chunk starts on a 32-bit word of the packet's bit stream (chosen by the launcher)
     const int FLUSH = a.flush;
     const int BATCHES = FLUSH / SF;
     constexpr int TB = (M / 2 < NT) ? M / 2 : NT;     // threads per symbol in phase B
@@ -109,29 +172,32 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
     constexpr int K = M - 1;
     // multi-warp symbol groups (N = 4096) have few loads per thread in flight and only two CTAs per
     // SM: issue the next batch's loads before the equaliser phase.  Half-warp groups (R = 32) have
-    // no registers to spare for that and four CTAs per SM already overlap.
+    // no registers to spare for that and several CTAs per SM already overlap.
     constexpr int PREFETCH = (GF3_PREFETCH >= 0) ? GF3_PREFETCH : (T >= 128 ? 1 : 0);
+    constexpr bool NAT = GF3_DEMOD_NATURAL != 0;      // last FFT pass leaves the spectrum unpadded (see fft_pass)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* zbuf = reinterpret_cast<float2*>(smem_raw);
     float2* tw = zbuf + SF * MP;
-    uint8_t* stage = reinterpret_cast<uint8_t*>(tw + P::TW_TOTAL);            // [FLUSH*Nd] 2-bit codes, one per byte
+    constexpr bool CST = demod_cst_in_smem<P, NT>();
+    // [2*PP][NT] 16-byte records (wA, wB)[pp], (Ure, Uim)[pp] when CST
+    ulonglong2* cst = reinterpret_cast<ulonglong2*>(smem_raw + demod_cst_offset<P, NT>());
+    uint8_t* stage = smem_raw + demod_cst_offset<P, NT>() + demod_cst_bytes<P, NT>();   // [FLUSH*Nd] 2-bit codes, one per byte
 
     const int tid = threadIdx.x;
-    const int64_t pkt = blockIdx.x / a.ctas_per_packet;
-    const int c_first = (blockIdx.x % a.ctas_per_packet) * a.chunks_per_cta;
-    const int c_last = min(c_first + a.chunks_per_cta, a.chunks_per_packet);
     const int Nd = a.hi - a.lo;
     const int L = a.L;
-
-    for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
-
-    // XOR decode (OFDM.py:541-544) is applied per packed 32-bit word at flush time: word w of a
-    // chunk covers codes 16w..16w+15, i.e. data carriers (16w+i) mod Nd -- the same for every chunk
+    const int symlen = N + a.cp;
     const bool use_xor = a.xor2 != nullptr;
+    const bool want_bits = a.bits != nullptr;
     const int stage_bytes = ((FLUSH * Nd + 15) & ~15) + 16;
     uint32_t* xorw = reinterpret_cast<uint32_t*>(stage + stage_bytes);       // [FLUSH*Nd/16 + 1]
-    if (use_xor && a.bits != nullptr) {
+
+    // ================= once per CTA (the CTA is persistent: it walks a contiguous range of blocks)
+    for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
+    // XOR decode (OFDM.py:541-544) is applied per packed 32-bit word at flush time: word w of a
+    // chunk covers codes 16w..16w+15, i.e. data carriers (16w+i) mod Nd -- the same for every chunk
+    if (use_xor && want_bits) {
         const int wpc = (FLUSH * Nd + 15) >> 4;
         for (int w = tid; w < wpc; w += NT) {
             uint32_t word = 0;
@@ -147,503 +213,338 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
             xorw[w] = word;
         }
     }
-
-    const float* pkt_base = a.samples + (a.pkt_offset ? a.pkt_offset[pkt] : pkt * a.pkt_stride);
-    const int symlen = N + a.cp;
-
-    // ---- per-thread constants for phase B
+    // ---- phase B identity.  A thread owns PP bin pairs (k, M-k), k = jb + pp*TB (k = M/2 takes the
+    // slot of k = 0), and carries the two bins of a pair in the two lanes of FFMA2 / FADD2 / FMUL2.
     const int jb = tid % TB, sb = tid / TB;
-    float2 w2[PP], u1[PP], u2[PP], G1[PP], G2[PP];
-    int zo1[PP], zo2[PP], kk[PP];                       // padded smem offsets of Z[k], Z[M-k]; k itself
-    const bool want_bits = a.bits != nullptr;
-    int flags[PP];                                      // bit4 k is a data bin | bit5 km is a data bin | bit6 km exists (k != M/2)
-    const float2* Hs = KNOWN_CH ? a.Hs : a.Hs + pkt * K;
-    const double slope = KNOWN_CH ? 0.0 : a.slope[pkt];
-    const double inv_lp = 1.0 / (double)(L + a.P);
+    pk64 wA[PP], wB[PP];                                // w = -j e^{-2 pi i k / N} as A = (wr, wi), B = (-wi, wr)
+    pk64 Gre[PP], Gim[PP];                              // rotating equaliser taps: lane x = bin k, lane y = bin M-k
+    pk64 Ure[PP], Uim[PP];                              // per-symbol rotation: e^{-j delta} (exact) or Ure = tan(delta) (fast)
+    pk64* const my_slot = reinterpret_cast<pk64*>(zbuf) + tid;   // scratch for p_opaque (zbuf is not in use yet)
+    const pk64 pm = p_opaque(pk_pack(make_float2(1.f, -1.f)), my_slot);
 #pragma unroll
     for (int pp = 0; pp < PP; ++pp) {
         const int j = jb + pp * TB;
-        const int k = j == 0 ? M / 2 : j, km = M - k;
-        kk[pp] = k;
-        zo1[pp] = zpad<P>(k);
-        zo2[pp] = zpad<P>(km);
+        const int k = j == 0 ? M / 2 : j;
         float s, c;
         sincospif(2.0f * (float)k / (float)N, &s, &c);
-        w2[pp] = make_float2(-s, -c);                   // -j * exp(-2 pi i k / N)
-        int f = 0;
-        if (k >= a.lo && k < a.hi) f |= 16;
-        if (j != 0) {
-            f |= 64;
-            if (km >= a.lo && km < a.hi) f |= 32;
-        }
-        flags[pp] = f;
-        if constexpr (!KNOWN_CH) {
-            u1[pp] = expmj(slope * inv_lp * (double)((k - 1) * SB));
-            u2[pp] = expmj(slope * inv_lp * (double)((km - 1) * SB));
+        wA[pp] = wB[pp] = Ure[pp] = Uim[pp] = Gre[pp] = Gim[pp] = 0ull;
+        if constexpr (CST) {
+            cst[(2 * pp) * NT + tid] = make_ulonglong2(pk_pack(make_float2(-s, -c)), pk_pack(make_float2(c, -s)));
+        } else {
+            wA[pp] = p_opaque(pk_pack(make_float2(-s, -c)), my_slot);   // -j * exp(-2 pi i k / N) = -s - j c
+            wB[pp] = p_opaque(pk_pack(make_float2(c, -s)), my_slot);
         }
     }
+    const double inv_lp = 1.0 / (double)(L + a.P);
     __syncthreads();
 
     // phase-A identity of this thread: symbol group ga, lane ta inside the group
     const int ga = tid / T, ta = tid % T;
     float2 x[R];
-    auto load_batch = [&](int chunk, int b) {
-        // symbols past the end of the packet are clamped to the last one: their spectra are
-        // computed but never used (phase B only walks valid symbols), and no zero-fill is needed
-        int l = chunk * FLUSH + b * SF + ga;
-        l = l < L ? l : L - 1;
-        load_symbol<P>(x, pkt_base + (int64_t)(a.P + l) * symlen + a.cp, ta);
-    };
-    if constexpr (PREFETCH == 1) load_batch(c_first, 0);
 
-    for (int chunk = c_first; chunk < c_last; ++chunk) {
-        const int l0 = chunk * FLUSH;
-        const int nsym = min(FLUSH, L - l0);
-        if ((nsym * Nd) & 15) {                       // last word of the chunk is partial: its missing codes are 0
-            if (tid < 16) stage[nsym * Nd + tid] = 0;
-        }
-        // (re)seed the rotating equaliser taps exactly (fp64 phase) at the first chunk and then every 64
-        // symbols; in between the per-bin recurrence simply continues across chunk boundaries
-        if (chunk == c_first || (l0 % 64) == 0)
-#pragma unroll
-        for (int pp = 0; pp < PP; ++pp) {
-            const int j = jb + pp * TB;
-            const int k = j == 0 ? M / 2 : j, km = M - k;
-            const float2 h1 = Hs[k - 1], h2 = Hs[(j == 0 ? k : km) - 1];
-            if constexpr (KNOWN_CH) {
-                G1[pp] = h1;
-                G2[pp] = h2;
-            } else {
-                const double wl = ((double)(l0 + sb) + 0.5 * (double)a.P) * inv_lp;   // OFDM.py:471,474
-                G1[pp] = cmul(cconj(h1), expmj(slope * (double)(k - 1) * wl));
-                G2[pp] = cmul(cconj(h2), expmj(slope * (double)(km - 1) * wl));
-            }
-        }
+    // ================= work loop.  Work item = one flush chunk: FLUSH consecutive data symbols of one
+    // packet (the last chunk of a packet may be shorter).  Each CTA takes a contiguous, equally sized
+    // range of chunks.  The equaliser recurrence is seeded exactly (fp64 phase) at every multiple of
+    // kReseed symbols; a CTA whose range starts between two such points seeds at the previous one and
+    // replays the recurrence up to its first symbol with the very same FMAs, so no output bit depends
+    // on how the chunks are spread over CTAs.
+    const int cpp = a.chunks_per_packet;
+    const int64_t total_chunks = a.n_packets * cpp;
+    const int64_t c_begin = total_chunks * blockIdx.x / gridDim.x;
+    const int64_t c_end = total_chunks * (blockIdx.x + 1) / gridDim.x;
+    int64_t cur_pkt = -1;
+    const float* pkt_base = nullptr;
+    const float2* Hs = a.Hs;
+    double slope = 0.0;
+    bool fast_rot = false;
+
+    auto sym_ptr = [&](int64_t c, int l_first) -> const float* {
+        // samples (after the cyclic prefix) of this thread's symbol of the batch starting at symbol
+        // l_first of chunk c's packet.  Symbols past the end of the packet are clamped to the last
+        // one: their spectra are computed but never used, and no zero-fill is needed
+        const int64_t pk = c / cpp;
+        const float* base = pk == cur_pkt ? pkt_base : a.samples + (a.pkt_offset ? a.pkt_offset[pk] : pk * a.pkt_stride);
+        int l = l_first + ga;
+        l = l < L ? l : L - 1;
+        return base + (int64_t)(a.P + l) * symlen + a.cp;
+    };
+    if constexpr (PREFETCH == 1) {
+        if (c_begin < c_end) load_symbol<P>(x, sym_ptr(c_begin, (int)(c_begin % cpp) * FLUSH), ta);
+    }
 
 #pragma unroll 1
-        for (int b = 0; b < BATCHES; ++b) {
-            // ---------------- phase A: FFT of SF symbols
-            if constexpr (PREFETCH != 1) load_batch(chunk, b);
-            fft_forward<P, NT>(x, zbuf + ga * MP, tw, ta, ga);
-            __syncthreads();
-            if constexpr (PREFETCH == 1) {
-                // prefetch the next batch's samples: the loads fly while phase B computes
-                load_batch(b + 1 < BATCHES ? chunk : chunk + 1, b + 1 < BATCHES ? b + 1 : 0);
-            } else if constexpr (PREFETCH == 2) {
-              if (ta == 0) {
-                const int nc = b + 1 < BATCHES ? chunk : chunk + 1, nb = b + 1 < BATCHES ? b + 1 : 0;
-                const int nl = nc * FLUSH + nb * SF + ga;
-                if (nc < c_last && nl < L) {
-                    const float* sp = pkt_base + (int64_t)(a.P + nl) * symlen + a.cp;
-                    const uintptr_t lo16 = reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15;
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo16), "r"(N * 4 + 16) : "memory");
+    for (int64_t c = c_begin; c < c_end; ++c) {
+        const int64_t pkt = c / cpp;
+        const int l0 = (int)(c - pkt * cpp) * FLUSH;
+        const int nsym = min(FLUSH, L - l0);
+        if (pkt != cur_pkt) {                           // ---- once per packet
+            cur_pkt = pkt;
+            pkt_base = a.samples + (a.pkt_offset ? a.pkt_offset[pkt] : pkt * a.pkt_stride);
+            if constexpr (!KNOWN_CH) {
+                Hs = a.Hs + pkt * K;
+                slope = a.slope[pkt];
+                // For the bits only the sign of data * G matters, so the per-symbol rotation
+                // G *= e^{-j delta} may be replaced by G *= (1 - j tan(delta)) = e^{-j delta} / cos(delta):
+                // the same angle, two FMAs.  Valid while cos(delta) > 0 and the growth over one re-seed
+                // period stays far inside fp32: |delta| <= 0.7 rad gives at most 1.31^64 = 3e7.  Anything
+                // else (and the constellation output, which needs |G| = |Hs|) takes the exact rotation.
+                fast_rot = !WANT_EQ && fabs(slope) * (double)(K - 1) * (double)SB * inv_lp <= 0.7;
+#pragma unroll
+                for (int pp = 0; pp < PP; ++pp) {
+                    const int j = jb + pp * TB;
+                    const int k = j == 0 ? M / 2 : j, km = M - k;
+                    const float2 r1 = expmj(slope * inv_lp * (double)((k - 1) * SB));
+                    const float2 r2 = expmj(slope * inv_lp * (double)((km - 1) * SB));
+                    pk64 ur, ui = 0ull;
+                    if (fast_rot) {
+                        ur = pk_pack(make_float2(-r1.y / r1.x, -r2.y / r2.x));      // tan(delta)
+                    } else {
+                        ur = pk_pack(make_float2(r1.x, r2.x));
+                        ui = pk_pack(make_float2(r1.y, r2.y));
+                    }
+                    if constexpr (CST) {
+                        cst[(2 * pp + 1) * NT + tid] = make_ulonglong2(ur, ui);
+                    } else {
+                        Ure[pp] = ur;
+                        Uim[pp] = ui;
+                    }
                 }
-              }
             }
-            // ---------------- phase B: untangle, equalise, demap
-            // thread <-> PP bin pairs; walks the batch's symbols sb, sb+SB, ... with pointer increments
-            {
-                const int ls0 = b * SF + sb;                                   // first symbol (inside the chunk) of this thread
-                int n_it = (nsym - ls0 + SB - 1) / SB;                          // valid symbols for this thread in this batch
-                n_it = n_it < 0 ? 0 : (n_it > SF / SB ? SF / SB : n_it);
-                const float2* zs = zbuf + sb * MP;
-                uint8_t* st = stage + ls0 * Nd - a.lo;
-                float2* eqp = nullptr;
-                if constexpr (WANT_EQ) eqp = a.eq + ((int64_t)pkt * L + l0 + ls0) * K - 1;
-#pragma unroll 2
-                for (int it = 0; it < n_it; ++it) {
+        }
+        if (c == c_begin || (l0 % kReseed) == 0) {
+            // ---- seed the rotating equaliser taps (OFDM.py:466-478) for symbol l_seed + sb, then replay
+            const int l_seed = l0 - l0 % kReseed;
+#pragma unroll
+            for (int pp = 0; pp < PP; ++pp) {
+                const int j = jb + pp * TB;
+                const int k = j == 0 ? M / 2 : j, km = M - k;
+                const float2 h1 = Hs[k - 1], h2 = Hs[(j == 0 ? k : km) - 1];
+                float2 g1 = h1, g2 = h2;
+                if constexpr (!KNOWN_CH) {
+                    const double wl = ((double)(l_seed + sb) + 0.5 * (double)a.P) * inv_lp;   // OFDM.py:471,474
+                    g1 = cmul(cconj(h1), expmj(slope * (double)(k - 1) * wl));
+                    g2 = cmul(cconj(h2), expmj(slope * (double)(km - 1) * wl));
+                }
+                Gre[pp] = pk_pack(make_float2(g1.x, g2.x));
+                Gim[pp] = pk_pack(make_float2(g1.y, g2.y));
+            }
+            if constexpr (!KNOWN_CH) {
+                const int steps = (l0 - l_seed) / SB;
+                if (steps > 0) {
 #pragma unroll
                     for (int pp = 0; pp < PP; ++pp) {
-                        const float2 z1 = zs[zo1[pp]], z2 = zs[zo2[pp]];
-                        const float2 s = make_float2(z1.x + z2.x, z1.y - z2.y);    // Z[k] + conj Z[M-k]
-                        const float2 d = make_float2(z1.x - z2.x, z1.y + z2.y);    // Z[k] - conj Z[M-k]
-                        const float2 tt = cmul(w2[pp], d);
-                        const float2 x1 = cadd(s, tt);                             // 2 X[k]
-                        const float2 x2 = make_float2(s.x - tt.x, tt.y - s.y);     // 2 X[M-k] = conj(s - tt)
-                        const float2 y1 = cmul(x1, G1[pp]);
-                        const float2 y2 = cmul(x2, G2[pp]);
-                        if constexpr (!KNOWN_CH) {
-                            G1[pp] = cmul(G1[pp], u1[pp]);
-                            G2[pp] = cmul(G2[pp], u2[pp]);
+                        pk64 ur = Ure[pp], ui = Uim[pp];
+                        if constexpr (CST) {
+                            const ulonglong2 uc = lds_v2(cst + (2 * pp + 1) * NT + tid);
+                            ur = uc.x;
+                            ui = uc.y;
                         }
-                        const int f = flags[pp];
-                        if (want_bits) {
-                            if (f & 16) {
-                                const unsigned code = ((__float_as_uint(y1.y) >> 30) & 2u) | (__float_as_uint(y1.x) >> 31);
-                                st[kk[pp]] = (uint8_t)code;
-                            }
-                            if (f & 32) {
-                                const unsigned code = ((__float_as_uint(y2.y) >> 30) & 2u) | (__float_as_uint(y2.x) >> 31);
-                                st[M - kk[pp]] = (uint8_t)code;
-                            }
-                        }
-                        if constexpr (WANT_EQ) {
-                            const int k = kk[pp], km = M - k;
-                            float sc1 = 0.5f, sc2 = 0.5f;
-                            if constexpr (!KNOWN_CH) {
-                                // |H| = |Hs| + (|He| - |Hs|) w  (OFDM.py:471); G carries conj(Hs) unnormalised
-                                const float eq_w = (float)(((double)(l0 + ls0 + it * SB) + 0.5 * (double)a.P) * inv_lp);
-                                const float2 hs1 = Hs[k - 1], he1 = a.He[pkt * K + k - 1];
-                                const float a1 = sqrtf(hs1.x * hs1.x + hs1.y * hs1.y);
-                                const float e1 = sqrtf(he1.x * he1.x + he1.y * he1.y);
-                                sc1 = 0.5f / (a1 * (a1 + (e1 - a1) * eq_w));
-                                if (f & 64) {
-                                    const float2 hs2 = Hs[km - 1], he2 = a.He[pkt * K + km - 1];
-                                    const float a2 = sqrtf(hs2.x * hs2.x + hs2.y * hs2.y);
-                                    const float e2 = sqrtf(he2.x * he2.x + he2.y * he2.y);
-                                    sc2 = 0.5f / (a2 * (a2 + (e2 - a2) * eq_w));
-                                }
-                            }
-                            eqp[k] = make_float2(y1.x * sc1, y1.y * sc1);
-                            if (f & 64) eqp[km] = make_float2(y2.x * sc2, y2.y * sc2);
-                        }
-                    }
-                    zs += SB * MP;
-                    st += SB * Nd;
-                    if constexpr (WANT_EQ) eqp += (int64_t)SB * K;
-                }
-            }
-            __syncthreads();
-        }
-
-        // ---------------- flush: 16 two-bit codes -> one 32-bit word (MSB-first bytes)
-        // four codes c0..c3 (one per byte of u) -> (c0<<6 | c1<<4 | c2<<2 | c3) is the top byte of
-        // u * 0x40100401 (no carries: every partial product lands on its own 2-bit field)
-        if (want_bits) {
-            const int ncodes = nsym * Nd;
-            const int nwords = (ncodes + 15) >> 4;
-            uint32_t* out = reinterpret_cast<uint32_t*>(a.bits + pkt * a.bits_stride) + (int64_t)l0 * Nd / 16;
-            for (int w = tid; w < nwords; w += NT) {
-                const uint4 v = *reinterpret_cast<const uint4*>(stage + 16 * w);
-                const uint32_t t0 = v.x * 0x40100401u, t1 = v.y * 0x40100401u, t2 = v.z * 0x40100401u, t3 = v.w * 0x40100401u;
-                uint32_t word = __byte_perm(__byte_perm(t0, t1, 0x0073), __byte_perm(t2, t3, 0x0073), 0x5410);
-                if (use_xor) {
-                    uint32_t xw = xorw[w];
-                    const int r = ncodes - 16 * w;                  // codes in this word (< 16 only for the very last one)
-                    if (r < 16) {                                   // keep the pad bits of a partial word zero
-                        const int fb = r >> 2, rm = r & 3;
-                        const uint32_t m = (fb ? (0xFFFFFFFFu >> (32 - 8 * fb)) : 0u) | (rm ? (((0xFF00u >> (2 * rm)) & 0xFFu) << (8 * fb)) : 0u);
-                        xw &= m;
-                    }
-                    word ^= xw;
-                }
-                out[w] = word;
-            }
-            if (l0 + nsym >= L) {                                   // last chunk of the packet: clear the row's pad words
-                const int stride_words = (int)(a.bits_stride / 4) - (int)((int64_t)l0 * Nd / 16);
-                for (int w = nwords + tid; w < stride_words; w += NT) out[w] = 0u;
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Packed data-symbol kernel (N = 1024 and N = 4096): same structure as rx_demod_kernel, but every
-// symbol's M-point FFT is split by one scalar radix-2 DIF stage into two M/2-point FFTs that ride
-// in the two lanes of FFMA2 / FADD2 / FMUL2, and the untangle / equalise / demap phase processes
-// FOUR bins per thread per step: lanes (2j, 2j+1) and their mirrors (M-2j, M-2j-1).  That halves
-// the FP32 issue slots of the kernel, which is instruction-issue bound (profiles/).
-// ------------------------------------------------------------------------------------------
-template <class P, int NT, int MINB, bool KNOWN_CH, bool WANT_EQ>
-__global__ void __launch_bounds__(NT, MINB) rx_demod_pk_kernel(const RxArgs a) {
-    // Warp-specialised: the first NT/2 threads (producers) load samples and run the FFTs of batch s
-    // into Z buffer s&1; the other NT/2 threads (consumers) untangle / equalise / demap batch s-1 from
-    // the other buffer and flush the packed bits.  They meet only on named barriers (full / empty per
-    // buffer), so loads, FFT math and equaliser math of different batches overlap inside one CTA.
-    constexpr int T = P::T, R = P::R, H = P::H, M = P::M, N = P::N, HP = P::HP, K = M - 1;
-    constexpr int NP = NT / 2, NC = NT - NP;          // producer / consumer threads
-    constexpr int SF = NP / T;                        // symbols per FFT batch
-    constexpr int ITEMS = H / 2;                      // smem entries walked per symbol in phase B
-    constexpr int TB = ITEMS < NC ? ITEMS : NC;       // consumer threads per symbol
-    constexpr int SB = NC / TB;                       // symbols handled concurrently in phase B
-    constexpr int PPK = ITEMS / TB;                   // entries per thread
-    static_assert(SF >= 1 && SF % SB == 0, "bad producer/consumer split");
-    enum { BAR_FULL0 = 1, BAR_FULL1 = 2, BAR_EMPTY0 = 3, BAR_EMPTY1 = 4, BAR_CONS = 5 };
-    constexpr int RESEED = 64;                        // symbols between exact re-seeds of the equaliser recurrence
-    const int FLUSH = a.flush;
-    const int BATCHES = FLUSH / SF;
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* zbuf = reinterpret_cast<float4*>(smem_raw);                         // [2][SF][HP] (U.re, V.re, U.im, V.im)
-    float2* tw = reinterpret_cast<float2*>(zbuf + 2 * SF * HP);                 // [TW_TOTAL]
-    uint8_t* stage = reinterpret_cast<uint8_t*>(tw + P::TW_TOTAL);
-
-    const int tid = threadIdx.x;
-    const int64_t pkt = blockIdx.x / a.ctas_per_packet;
-    const int c_first = (blockIdx.x % a.ctas_per_packet) * a.chunks_per_cta;
-    const int c_last = min(c_first + a.chunks_per_cta, a.chunks_per_packet);
-    const int Nd = a.hi - a.lo;
-    const int L = a.L;
-
-    for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
-
-    const bool use_xor = a.xor2 != nullptr;
-    const bool want_bits = a.bits != nullptr;
-    const int stage_bytes = ((FLUSH * Nd + 15) & ~15) + 16;
-    uint32_t* xorw = reinterpret_cast<uint32_t*>(stage + stage_bytes);
-    if (use_xor && want_bits) {
-        const int wpc = (FLUSH * Nd + 15) >> 4;
-        for (int w = tid; w < wpc; w += NT) {
-            uint32_t word = 0;
-            int c = (16 * w) % Nd;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (16 * w + i < FLUSH * Nd) {
-                    const uint32_t code = a.xor2[c] & 3u;
-                    word |= code << (8 * (i >> 2) + 6 - 2 * (i & 3));
-                }
-                c = (c + 1 == Nd) ? 0 : c + 1;
-            }
-            xorw[w] = word;
-        }
-    }
-
-    const float* pkt_base = a.samples + (a.pkt_offset ? a.pkt_offset[pkt] : pkt * a.pkt_stride);
-    const int symlen = N + a.cp;
-
-    // ---- per-thread constants for phase B.  Entry j carries bins (2j, 2j+1); their mirrors
-    // (M-2j, M-2j-1) are lane x of entry H-j and lane y of entry H-1-j.
-    const bool producer = tid < NP;
-    const int ctid = producer ? 0 : tid - NP;          // consumer thread index
-    const int jb = ctid % TB, sb = ctid / TB;
-    cpk w2[PPK], u1[PPK], u2[PPK], G1[PPK], G2[PPK];
-    int zo[PPK], zmx[PPK], zmy[PPK], jj[PPK], flags[PPK];   // flags: 1 own.x 2 own.y 4 mir.x 8 mir.y are data bins
-    const float2* Hs = KNOWN_CH ? a.Hs : a.Hs + pkt * K;
-    const double slope = KNOWN_CH ? 0.0 : a.slope[pkt];
-    const double inv_lp = 1.0 / (double)(L + a.P);
-    auto is_data = [&](int k) { return k >= a.lo && k < a.hi; };
-    auto rot = [&](int k, double w) { return expmj(slope * (double)(k - 1) * w); };
-#pragma unroll
-    for (int pp = 0; pp < PPK; ++pp) {
-        const int j = jb + pp * TB;
-        jj[pp] = j;
-        zo[pp] = zpad<P>(j);
-        zmx[pp] = zpad<P>((H - j) % H);
-        zmy[pp] = zpad<P>(H - 1 - j);
-        const int kx = 2 * j, ky = 2 * j + 1, mx = M - 2 * j, my = M - 2 * j - 1;
-        float sx, cx, sy, cy;
-        sincospif(2.0f * (float)kx / (float)N, &sx, &cx);
-        sincospif(2.0f * (float)ky / (float)N, &sy, &cy);
-        w2[pp] = cpk{make_float2(-sx, -sy), make_float2(-cx, -cy)};          // -j exp(-2 pi i k / N)
-        flags[pp] = (is_data(kx) ? 1 : 0) | (is_data(ky) ? 2 : 0) | ((j != 0 && is_data(mx)) ? 4 : 0) | (is_data(my) ? 8 : 0);
-        if constexpr (!KNOWN_CH) {
-            const double st = inv_lp * (double)SB;
-            const float2 ax = rot(kx, st), ay = rot(ky, st), bx = rot(mx, st), by = rot(my, st);
-            u1[pp] = cpk{make_float2(ax.x, ay.x), make_float2(ax.y, ay.y)};
-            u2[pp] = cpk{make_float2(bx.x, by.x), make_float2(bx.y, by.y)};
-        }
-    }
-    // bin M/2 (self-paired, = lane x of entry H/2) is walked by the thread that owns entry 0
-    float2 Gh = make_float2(0.f, 0.f), uh = make_float2(1.f, 0.f);
-    if constexpr (!KNOWN_CH) uh = rot(M / 2, inv_lp * (double)SB);
-    const bool half_data = is_data(M / 2);
-    __syncthreads();
-
-    const int ga = tid / T, ta = tid % T;               // producer identity: symbol group, lane in the group
-    const int n_chunks = c_last - c_first;
-    const int n_steps = n_chunks * BATCHES;
-
-    // 256-thread CTAs = two warpgroups: the producer warpgroup takes registers from the consumer one
-    // (setmaxnreg), enough to keep the NEXT step's 2R loads in flight during the current FFT.
-    constexpr bool DBUF = (NT == 256);
-    if (producer) {
-        // =============================== PRODUCERS: samples -> two packed H-point FFTs -> Z buffer
-        if constexpr (DBUF) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
-        float2 za[R], zb[R];
-        auto issue_loads = [&](int s) {
-            const int chunk = c_first + s / BATCHES, b = s % BATCHES;
-            int l = chunk * FLUSH + b * SF + ga;
-            l = l < L ? l : L - 1;                          // clamped: spectra of invalid symbols are never used
-            const float* sp = pkt_base + (int64_t)(a.P + l) * symlen + a.cp;
-            if ((reinterpret_cast<uintptr_t>(sp) & 7) == 0) {
-#pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    za[i] = ldg_stream2(sp + 2 * (ta + i * T));
-                    zb[i] = ldg_stream2(sp + 2 * (ta + i * T + H));
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    za[i].x = ldg_stream1(sp + 2 * (ta + i * T));
-                    za[i].y = ldg_stream1(sp + 2 * (ta + i * T) + 1);
-                    zb[i].x = ldg_stream1(sp + 2 * (ta + i * T + H));
-                    zb[i].y = ldg_stream1(sp + 2 * (ta + i * T + H) + 1);
-                }
-            }
-        };
-        if constexpr (DBUF) issue_loads(0);
+                        pk64 gre = Gre[pp], gim = Gim[pp];
 #pragma unroll 1
-        for (int s = 0; s < n_steps; ++s) {
-            if constexpr (!DBUF) {
-                issue_loads(s);
-                if (GF3_PK_L2_PREFETCH && ta == 0 && s + 1 < n_steps) {
-                    // bulk L2 prefetch (TMA engine, no registers) of this group's symbol of the NEXT step
-                    const int nc = c_first + (s + 1) / BATCHES, nb = (s + 1) % BATCHES;
-                    const int nl = nc * FLUSH + nb * SF + ga;
-                    if (nl < L) {
-                        const float* np_ = pkt_base + (int64_t)(a.P + nl) * symlen + a.cp;
-                        const uintptr_t lo16 = reinterpret_cast<uintptr_t>(np_) & ~(uintptr_t)15;
+                        for (int i = 0; i < steps; ++i) {
+                            const pk64 gr = gre;
+                            if (fast_rot) {
+                                gre = p_fma(ur, gim, gr);
+                                gim = p_fma(p_neg(ur), gr, gim);
+                            } else {
+                                gre = p_fma(p_neg(gim), ui, p_mul(gr, ur));
+                                gim = p_fma(gr, ui, p_mul(gim, ur));
+                            }
+                        }
+                        Gre[pp] = gre;
+                        Gim[pp] = gim;
+                    }
+                }
+            }
+        }
+
+        {
+            if ((nsym * Nd) & 15) {                   // last word of the chunk is partial: its missing codes are 0
+                if (tid < 16) stage[nsym * Nd + tid] = 0;
+            }
+#pragma unroll 1
+            for (int b = 0; b < BATCHES; ++b) {
+                // ---------------- phase A: FFT of SF symbols
+#if GF3_ABL & 4
+                {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) x[i] = make_float2(__int_as_float(0x3f800000 | ((tid + i + b) << 8)), __int_as_float(0x3f800000 | ((tid * 3 + i) << 7)));
+                }
+#else
+                if constexpr (PREFETCH != 1) load_symbol<P>(x, sym_ptr(c, l0 + b * SF), ta);
+#endif
+#if GF3_ABL & 2
+                {
+                    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < R; ++i) acc = cadd(acc, x[i]);
+                    zbuf[ga * MP + ta] = acc;
+                }
+#else
+                fft_forward<P, NT, NAT>(x, zbuf + ga * MP, tw, ta, ga);
+#endif
+                __syncthreads();
+                if constexpr (PREFETCH == 1) {
+                    // prefetch the next batch's samples (possibly the first batch of the next chunk of this
+                    // CTA's range): the loads fly while phase B computes
+                    if (b + 1 < BATCHES) {
+                        if (l0 + (b + 1) * SF < L) load_symbol<P>(x, sym_ptr(c, l0 + (b + 1) * SF), ta);
+                    } else if (c + 1 < c_end) {
+                        load_symbol<P>(x, sym_ptr(c + 1, (int)((c + 1) % cpp) * FLUSH), ta);
+                    }
+                } else if constexpr (PREFETCH == 2) {
+                    const int nl = l0 + (b + 1) * SF + ga;
+                    if (ta == 0 && b + 1 < BATCHES && nl < L) {
+                        const float* sp = pkt_base + (int64_t)(a.P + nl) * symlen + a.cp;
+                        const uintptr_t lo16 = reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15;
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo16), "r"(N * 4 + 16) : "memory");
                     }
                 }
-            }
-            // the loads are in flight while we wait for the consumers to release this buffer
-            if (s >= 2) asm volatile("bar.sync %0, %1;" ::"r"((s & 1) ? BAR_EMPTY1 : BAR_EMPTY0), "n"(NT) : "memory");
-            cpk x[R];
+                // ---------------- phase B: untangle, equalise, demap
+                // thread <-> PP bin pairs; walks the batch's symbols sb, sb+SB, ...
+                {
+                    const int ls0 = b * SF + sb;                               // first symbol (inside the chunk) of this thread
+                    int n_it = (nsym - ls0 + SB - 1) / SB;                      // valid symbols for this thread in this batch
+                    n_it = n_it < 0 ? 0 : (n_it > SF / SB ? SF / SB : n_it);
+                    auto phase_b = [&](auto fastc, auto bitsc) {
+                        constexpr bool FAST = decltype(fastc)::value, BITS = decltype(bitsc)::value;
+                        const float2 *zp1[PP], *zp2[PP];
+                        unsigned sp1[PP], sp2[PP];                              // shared-memory byte addresses of the code slots
+                        bool e2[PP];                                            // bin M-k exists (k != M/2)
+                        unsigned dmask = 0;                                     // bit 2pp: bin k carries data, bit 2pp+1: bin M-k does
+                        const unsigned st0 = (unsigned)__cvta_generic_to_shared(stage) + ls0 * Nd - a.lo;
 #pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const float2 u = cadd(za[i], zb[i]);
-                const float2 v = cmul(csub(za[i], zb[i]), tw[ta + i * T]);      // W_M^h, h = ta + i*T
-                x[i] = cpk{make_float2(u.x, v.x), make_float2(u.y, v.y)};
-            }
-            if constexpr (DBUF) {
-                if (s + 1 < n_steps) issue_loads(s + 1);     // fly during the FFT below
-            }
-            pk_fft_forward<P, NP>(x, zbuf + ((s & 1) * SF + ga) * HP, tw, ta, ga);
-            asm volatile("bar.arrive %0, %1;" ::"r"((s & 1) ? BAR_FULL1 : BAR_FULL0), "n"(NT) : "memory");
-        }
-        return;
-    }
-    if constexpr (DBUF) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-
-    // =============================== CONSUMERS: untangle, equalise, demap, pack, store
-#pragma unroll 1
-    for (int chunk = c_first; chunk < c_last; ++chunk) {
-        const int l0 = chunk * FLUSH;
-        const int nsym = min(FLUSH, L - l0);
-        if ((nsym * Nd) & 15) {
-            if (ctid < 16) stage[nsym * Nd + ctid] = 0;
-        }
-        // (re)seed the rotating equaliser taps exactly (fp64 phase) at the first chunk and then every
-        // RESEED symbols; in between the per-bin recurrence simply continues across chunk boundaries
-        if (chunk == c_first || (l0 % RESEED) == 0) {
-            const double wl = ((double)(l0 + sb) + 0.5 * (double)a.P) * inv_lp;          // OFDM.py:471,474
-            auto seed = [&](int k) -> float2 {
-                if (k < 1 || k > K) return make_float2(0.f, 0.f);
-                const float2 h = Hs[k - 1];
-                if constexpr (KNOWN_CH) return h;
-                else return cmul(cconj(h), rot(k, wl));
-            };
-#pragma unroll
-            for (int pp = 0; pp < PPK; ++pp) {
-                const int j = jj[pp];
-                const float2 gx = seed(2 * j), gy = seed(2 * j + 1), hx = seed(M - 2 * j), hy = seed(M - 2 * j - 1);
-                G1[pp] = cpk{make_float2(gx.x, gy.x), make_float2(gx.y, gy.y)};
-                G2[pp] = cpk{make_float2(hx.x, hy.x), make_float2(hx.y, hy.y)};
-            }
-            Gh = seed(M / 2);
-        }
-
-#pragma unroll 1
-        for (int b = 0; b < BATCHES; ++b) {
-            const int s = (chunk - c_first) * BATCHES + b;
-            asm volatile("bar.sync %0, %1;" ::"r"((s & 1) ? BAR_FULL1 : BAR_FULL0), "n"(NT) : "memory");
-            {
-                const int ls0 = b * SF + sb;
-                int n_it = (nsym - ls0 + SB - 1) / SB;
-                n_it = n_it < 0 ? 0 : (n_it > SF / SB ? SF / SB : n_it);
-                const float4* zs = zbuf + ((s & 1) * SF + sb) * HP;
-                uint8_t* st = stage + ls0 * Nd - a.lo;
-                float2* eqp = nullptr;
-                if constexpr (WANT_EQ) eqp = a.eq + ((int64_t)pkt * L + l0 + ls0) * K - 1;
-#pragma unroll 1
-                for (int it = 0; it < n_it; ++it) {
-#pragma unroll
-                    for (int pp = 0; pp < PPK; ++pp) {
-                        const float4 eo = lds128(zs + zo[pp]), ea = lds128(zs + zmx[pp]), eb = lds128(zs + zmy[pp]);
-                        const cpk z1{make_float2(eo.x, eo.y), make_float2(eo.z, eo.w)};
-                        const cpk z2{make_float2(ea.x, eb.y), make_float2(ea.z, eb.w)};
-                        const cpk s{pk_add(z1.re, z2.re), pk_sub(z1.im, z2.im)};       // Z[k] + conj Z[M-k]
-                        const cpk d{pk_sub(z1.re, z2.re), pk_add(z1.im, z2.im)};       // Z[k] - conj Z[M-k]
-                        const cpk tt = cmul(w2[pp], d);
-                        const cpk x1 = cadd(s, tt);                                     // 2 X[k]
-                        const cpk x2{pk_sub(s.re, tt.re), pk_sub(tt.im, s.im)};         // 2 X[M-k] = conj(s - tt)
-                        const cpk y1 = cmul(x1, G1[pp]);
-                        const cpk y2 = cmul(x2, G2[pp]);
-                        if constexpr (!KNOWN_CH) {
-                            G1[pp] = cmul(G1[pp], u1[pp]);
-                            G2[pp] = cmul(G2[pp], u2[pp]);
-                        }
-                        const int f = flags[pp];
-                        const int kx = 2 * jj[pp];
-                        if (want_bits) {
-                            if (f & 1) st[kx] = (uint8_t)(((__float_as_uint(y1.im.x) >> 30) & 2u) | (__float_as_uint(y1.re.x) >> 31));
-                            if (f & 2) st[kx + 1] = (uint8_t)(((__float_as_uint(y1.im.y) >> 30) & 2u) | (__float_as_uint(y1.re.y) >> 31));
-                            if (f & 4) st[M - kx] = (uint8_t)(((__float_as_uint(y2.im.x) >> 30) & 2u) | (__float_as_uint(y2.re.x) >> 31));
-                            if (f & 8) st[M - kx - 1] = (uint8_t)(((__float_as_uint(y2.im.y) >> 30) & 2u) | (__float_as_uint(y2.re.y) >> 31));
-                        }
-                        if constexpr (WANT_EQ) {
-                            const float eq_w = KNOWN_CH ? 0.f : (float)(((double)(l0 + ls0 + it * SB) + 0.5 * (double)a.P) * inv_lp);
-                            auto put = [&](int k, float yr, float yi) {
-                                if (k < 1 || k > K) return;
-                                float sc = 0.5f;
+                        for (int pp = 0; pp < PP; ++pp) {
+                            const int j = jb + pp * TB;
+                            const int k = j == 0 ? M / 2 : j, km = M - k;
+                            zp1[pp] = zbuf + sb * MP + (NAT ? k : zpad<P>(k));
+                            zp2[pp] = zbuf + sb * MP + (NAT ? km : zpad<P>(km));
+                            sp1[pp] = st0 + k;
+                            sp2[pp] = st0 + km;
+                            if constexpr (CST) {
+                                const ulonglong2 wc = lds_v2(cst + (2 * pp) * NT + tid);
+                                wA[pp] = wc.x;
+                                wB[pp] = wc.y;
                                 if constexpr (!KNOWN_CH) {
-                                    const float2 hs = Hs[k - 1], he = a.He[pkt * K + k - 1];
-                                    const float a1 = sqrtf(hs.x * hs.x + hs.y * hs.y), e1 = sqrtf(he.x * he.x + he.y * he.y);
-                                    sc = 0.5f / (a1 * (a1 + (e1 - a1) * eq_w));       // |H| = |Hs| + (|He|-|Hs|) w  (OFDM.py:471)
+                                    const ulonglong2 uc = lds_v2(cst + (2 * pp + 1) * NT + tid);
+                                    Ure[pp] = uc.x;
+                                    Uim[pp] = uc.y;
                                 }
-                                eqp[k] = make_float2(yr * sc, yi * sc);
-                            };
-                            put(kx, y1.re.x, y1.im.x);
-                            put(kx + 1, y1.re.y, y1.im.y);
-                            if (kx != 0) put(M - kx, y2.re.x, y2.im.x);
-                            put(M - kx - 1, y2.re.y, y2.im.y);
-                        }
-                    }
-                    if (jb == 0) {      // bin M/2: 2 X[M/2] = 2 conj(Z[M/2]), Z[M/2] = U[H/2]
-                        const float4 e = zs[zpad<P>(H / 2)];
-                        const float2 xh = make_float2(2.f * e.x, -2.f * e.z);
-                        const float2 yh = cmul(xh, Gh);
-                        if constexpr (!KNOWN_CH) Gh = cmul(Gh, uh);
-                        if (want_bits && half_data)
-                            st[M / 2] = (uint8_t)(((__float_as_uint(yh.y) >> 30) & 2u) | (__float_as_uint(yh.x) >> 31));
-                        if constexpr (WANT_EQ) {
-                            float sc = 0.5f;
-                            if constexpr (!KNOWN_CH) {
-                                const float eq_w = (float)(((double)(l0 + ls0 + it * SB) + 0.5 * (double)a.P) * inv_lp);
-                                const float2 hs = Hs[M / 2 - 1], he = a.He[pkt * K + M / 2 - 1];
-                                const float a1 = sqrtf(hs.x * hs.x + hs.y * hs.y), e1 = sqrtf(he.x * he.x + he.y * he.y);
-                                sc = 0.5f / (a1 * (a1 + (e1 - a1) * eq_w));
                             }
-                            eqp[M / 2] = make_float2(yh.x * sc, yh.y * sc);
+                            e2[pp] = j != 0;
+                            if (k >= a.lo && k < a.hi) dmask |= 1u << (2 * pp);
+                            if (e2[pp] && km >= a.lo && km < a.hi) dmask |= 2u << (2 * pp);
                         }
+                        asm volatile("" : "+r"(dmask));             // keep the mask in a register: no re-derivation per store
+                        float2* eqp = nullptr;
+                        if constexpr (WANT_EQ) eqp = a.eq + ((int64_t)pkt * L + l0 + ls0) * K - 1;
+                        const int st_step = SB * Nd;
+                        int soff = 0;
+                        constexpr int UNR = (SF / SB) < GF3_PHASEB_UNROLL ? (SF / SB) : GF3_PHASEB_UNROLL;
+#pragma unroll UNR
+                        for (int it = 0; it < n_it; ++it) {
+#pragma unroll
+                            for (int pp = 0; pp < PP; ++pp) {
+                                const pk64 z1 = *reinterpret_cast<const pk64*>(zp1[pp] + it * (SB * MP));
+                                const pk64 z2 = *reinterpret_cast<const pk64*>(zp2[pp] + it * (SB * MP));
+                                // s = Z[k] + conj Z[M-k], d = Z[k] - conj Z[M-k]
+                                const pk64 sa = p_add(z1, z2);                      // (s.x, d.y)
+                                const pk64 sd = p_sub(z1, z2);                      // (d.x, s.y)
+                                const pk64 tt = p_fma(p_bc(p_hi(sa)), wB[pp], p_mul(p_bc(p_lo(sd)), wA[pp]));   // w * d
+                                // 2 X[k] = s + tt, 2 X[M-k] = conj(s - tt): real and imaginary parts of the pair
+                                const pk64 xre = p_fma(p_bc(p_lo(tt)), pm, p_bc(p_lo(sa)));
+                                const pk64 xim = p_fma(p_bc(p_hi(sd)), pm, p_bc(p_hi(tt)));
+                                const pk64 yre_ = p_fma(p_neg(xim), Gim[pp], p_mul(xre, Gre[pp]));
+                                const pk64 yim_ = p_fma(xre, Gim[pp], p_mul(xim, Gre[pp]));
+                                if constexpr (!KNOWN_CH) {
+                                    const pk64 gr = Gre[pp];
+                                    if constexpr (FAST) {                          // G *= 1 - j tan(delta)
+                                        Gre[pp] = p_fma(Ure[pp], Gim[pp], gr);
+                                        Gim[pp] = p_fma(p_neg(Ure[pp]), gr, Gim[pp]);
+                                    } else {                                       // G *= e^{-j delta}
+                                        Gre[pp] = p_fma(p_neg(Gim[pp]), Uim[pp], p_mul(gr, Ure[pp]));
+                                        Gim[pp] = p_fma(gr, Uim[pp], p_mul(Gim[pp], Ure[pp]));
+                                    }
+                                }
+                                const float2 yre = pk_unpack(yre_), yim = pk_unpack(yim_);
+                                if constexpr (BITS) {
+                                    // code = 2 * (imag < 0) + (real < 0)  (OFDM.py:484-500 reduced to sign tests)
+                                    sts_u8_if(sp1[pp] + soff, __funnelshift_l(__float_as_uint(yre.x), __float_as_uint(yim.x) >> 31, 1), dmask & (1u << (2 * pp)));
+                                    sts_u8_if(sp2[pp] + soff, __funnelshift_l(__float_as_uint(yre.y), __float_as_uint(yim.y) >> 31, 1), dmask & (2u << (2 * pp)));
+                                }
+                                if constexpr (WANT_EQ) {
+                                    const int k = (int)(sp1[pp] - st0), km = M - k;
+                                    float sc1 = 0.5f, sc2 = 0.5f;
+                                    if constexpr (!KNOWN_CH) {
+                                        // |H| = |Hs| + (|He| - |Hs|) w  (OFDM.py:471); G carries conj(Hs) unnormalised
+                                        const float eq_w = (float)(((double)(l0 + ls0 + it * SB) + 0.5 * (double)a.P) * inv_lp);
+                                        const float2 hs1 = Hs[k - 1], he1 = a.He[pkt * K + k - 1];
+                                        const float a1 = sqrtf(hs1.x * hs1.x + hs1.y * hs1.y);
+                                        const float e1 = sqrtf(he1.x * he1.x + he1.y * he1.y);
+                                        sc1 = 0.5f / (a1 * (a1 + (e1 - a1) * eq_w));
+                                        if (e2[pp]) {
+                                            const float2 hs2 = Hs[km - 1], he2 = a.He[pkt * K + km - 1];
+                                            const float a2 = sqrtf(hs2.x * hs2.x + hs2.y * hs2.y);
+                                            const float e2v = sqrtf(he2.x * he2.x + he2.y * he2.y);
+                                            sc2 = 0.5f / (a2 * (a2 + (e2v - a2) * eq_w));
+                                        }
+                                    }
+                                    eqp[k] = make_float2(yre.x * sc1, yim.x * sc1);
+                                    if (e2[pp]) eqp[km] = make_float2(yre.y * sc2, yim.y * sc2);
+                                }
+                            }
+                            soff += st_step;
+                            if constexpr (WANT_EQ) eqp += (int64_t)SB * K;
+                        }
+                    };
+#if !(GF3_ABL & 1)
+                    if (want_bits) {
+                        if (fast_rot) phase_b(std::true_type{}, std::true_type{});
+                        else phase_b(std::false_type{}, std::true_type{});
+                    } else {
+                        phase_b(std::false_type{}, std::false_type{});
                     }
-                    zs += SB * HP;
-                    st += SB * Nd;
-                    if constexpr (WANT_EQ) eqp += (int64_t)SB * K;
+#endif
                 }
+                __syncthreads();
             }
-            if (s + 2 < n_steps) asm volatile("bar.arrive %0, %1;" ::"r"((s & 1) ? BAR_EMPTY1 : BAR_EMPTY0), "n"(NT) : "memory");
-        }
 
-        // ---------------- flush (consumer threads only)
-        if (want_bits) {
-            asm volatile("bar.sync %0, %1;" ::"r"((int)BAR_CONS), "n"(NC) : "memory");
-            const int ncodes = nsym * Nd;
-            const int nwords = (ncodes + 15) >> 4;
-            uint32_t* out = reinterpret_cast<uint32_t*>(a.bits + pkt * a.bits_stride) + (int64_t)l0 * Nd / 16;
-            for (int w = ctid; w < nwords; w += NC) {
-                const uint4 v = *reinterpret_cast<const uint4*>(stage + 16 * w);
-                const uint32_t t0 = v.x * 0x40100401u, t1 = v.y * 0x40100401u, t2 = v.z * 0x40100401u, t3 = v.w * 0x40100401u;
-                uint32_t word = __byte_perm(__byte_perm(t0, t1, 0x0073), __byte_perm(t2, t3, 0x0073), 0x5410);
+            // ---------------- flush: 16 two-bit codes -> one 32-bit word (MSB-first bytes)
+            // four codes c0..c3 (one per byte of u) -> (c0<<6 | c1<<4 | c2<<2 | c3) is the top byte of
+            // u * 0x40100401 (no carries: every partial product lands on its own 2-bit field)
+            if (want_bits) {
+                const int ncodes = nsym * Nd;
+                const int nwords = (ncodes + 15) >> 4;
+                const int nfull = ncodes >> 4;                      // words made of 16 real codes
+                uint32_t* out = reinterpret_cast<uint32_t*>(a.bits + pkt * a.bits_stride) + (int64_t)l0 * Nd / 16;
+                auto pack16 = [&](int w) -> uint32_t {
+                    const uint4 v = *reinterpret_cast<const uint4*>(stage + 16 * w);
+                    const uint32_t t0 = v.x * 0x40100401u, t1 = v.y * 0x40100401u, t2 = v.z * 0x40100401u, t3 = v.w * 0x40100401u;
+                    return __byte_perm(__byte_perm(t0, t1, 0x0073), __byte_perm(t2, t3, 0x0073), 0x5410);
+                };
                 if (use_xor) {
-                    uint32_t xw = xorw[w];
-                    const int r = ncodes - 16 * w;
-                    if (r < 16) {
+#pragma unroll 2
+                    for (int w = tid; w < nfull; w += NT) out[w] = pack16(w) ^ xorw[w];
+                } else {
+#pragma unroll 2
+                    for (int w = tid; w < nfull; w += NT) out[w] = pack16(w);
+                }
+                if (nwords > nfull && tid == 0) {                   // the chunk's last, partial word: pad bits stay zero
+                    uint32_t word = pack16(nfull);
+                    if (use_xor) {
+                        const int r = ncodes - 16 * nfull;          // codes in this word (1..15)
                         const int fb = r >> 2, rm = r & 3;
                         const uint32_t m = (fb ? (0xFFFFFFFFu >> (32 - 8 * fb)) : 0u) | (rm ? (((0xFF00u >> (2 * rm)) & 0xFFu) << (8 * fb)) : 0u);
-                        xw &= m;
+                        word ^= xorw[nfull] & m;
                     }
-                    word ^= xw;
+                    out[nfull] = word;
                 }
-                out[w] = word;
+                if (l0 + nsym >= L) {                               // last chunk of the packet: clear the row's pad words
+                    const int stride_words = (int)(a.bits_stride / 4) - (int)((int64_t)l0 * Nd / 16);
+                    for (int w = nwords + tid; w < stride_words; w += NT) out[w] = 0u;
+                }
+                __syncthreads();
             }
-            if (l0 + nsym >= L) {
-                const int stride_words = (int)(a.bits_stride / 4) - (int)((int64_t)l0 * Nd / 16);
-                for (int w = nwords + ctid; w < stride_words; w += NC) out[w] = 0u;
-            }
-            asm volatile("bar.sync %0, %1;" ::"r"((int)BAR_CONS), "n"(NC) : "memory");
         }
     }
 }
@@ -837,93 +738,51 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
 #define GF3_DEMOD_THREADS 128
 #endif
 // Plan used by the data-symbol kernel for each symbol size, its CTA size and CTAs per SM.
-template <int LOGN> struct DemodCfg { using Plan = FftPlan<LOGN>; static constexpr int NT = GF3_DEMOD_THREADS, MINB = 512 / GF3_DEMOD_THREADS; };
+#ifndef GF3_DEMOD_MINB
+#define GF3_DEMOD_MINB (512 / GF3_DEMOD_THREADS)
+#endif
+template <int LOGN> struct DemodCfg { using Plan = FftPlan<LOGN>; static constexpr int NT = GF3_DEMOD_THREADS, MINB = GF3_DEMOD_MINB; };
 // N = 4096: 128 threads per symbol (16 x 16 x 8), two symbols per 256-thread CTA.  (A warp-per-symbol
 // 64 x 32 plan with ~255 registers / thread was measured slower: 8 warps per SM cannot hide latency.)
 template <> struct DemodCfg<12> { using Plan = FftPlan<12>; static constexpr int NT = 256, MINB = 2; };
 
-// Packed (two-lane) configuration per symbol size; Plan = void: use the scalar kernel.
-template <int LOGN> struct DemodPkCfg { using Plan = void; static constexpr int NT = 128, MINB = 4; };
-#ifndef GF3_NO_PACKED
-#ifndef GF3_PK_NT
-#define GF3_PK_NT 128
-#define GF3_PK_MINB 4
-#endif
-template <> struct DemodPkCfg<10> { using Plan = PkPlan10; static constexpr int NT = GF3_PK_NT, MINB = GF3_PK_MINB; };
-#endif
-
-template <int LOGN, bool KNOWN_CH, bool WANT_EQ>
-static int launch_demod_pk(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaStream_t st) {
-    using P = typename DemodPkCfg<LOGN>::Plan;
-    if constexpr (std::is_same<P, void>::value) {
-        return GF3_ERR_INVALID;
-    } else {
-        constexpr int NT = (2 * P::T > DemodPkCfg<LOGN>::NT) ? 2 * P::T : DemodPkCfg<LOGN>::NT;
-        constexpr int MINB = DemodPkCfg<LOGN>::MINB;
-        constexpr int SF = (NT / 2) / P::T;             // producer half of the CTA
-        const int Nd = a.hi - a.lo;
-        int flush = SF;
-        while ((flush * Nd) % 16 != 0 || flush < 8) flush += SF;
-        a.flush = flush;
-        a.tw = plan->d_tw_pk;
-        a.chunks_per_packet = (a.L + flush - 1) / flush;
-        const int64_t want = (int64_t)plan->sm_count * MINB * 8;
-        int64_t split = (want + n_packets - 1) / n_packets;
-        if (split < 1) split = 1;
-        if (split > a.chunks_per_packet) split = a.chunks_per_packet;
-        a.chunks_per_cta = (int)((a.chunks_per_packet + split - 1) / split);
-        // CTA boundaries sit on multiples of the 64-symbol re-seed period, so the equaliser recurrence
-        // (and hence every output bit) is independent of how a launch is split into CTAs
-        { const int rc = flush >= 64 ? 1 : 64 / flush; a.chunks_per_cta = (a.chunks_per_cta + rc - 1) / rc * rc; }
-        a.ctas_per_packet = (a.chunks_per_packet + a.chunks_per_cta - 1) / a.chunks_per_cta;
-        const size_t smem = (size_t)2 * SF * P::HP * sizeof(float4) + (size_t)P::TW_TOTAL * sizeof(float2)
-                            + (((size_t)flush * Nd + 15) & ~(size_t)15) + 16 + (((size_t)flush * Nd + 15) / 16 + 1) * sizeof(uint32_t);
-        auto kern = rx_demod_pk_kernel<P, NT, MINB, KNOWN_CH, WANT_EQ>;
-        GF3_REQUIRE(smem <= 227 * 1024, "rx_demod: %zu bytes of shared memory needed (> 227 KB)", smem);
-        GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int64_t grid = n_packets * a.ctas_per_packet;
-        GF3_REQUIRE(grid <= 0x7fffffff, "rx_demod: grid too large");
-        kern<<<(unsigned)grid, NT, smem, st>>>(a);
-        GF3_LAUNCH_CHECK();
-        return GF3_OK;
-    }
-}
-
 template <int LOGN, bool KNOWN_CH, bool WANT_EQ>
 static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaStream_t st) {
-    if constexpr (!std::is_same<typename DemodPkCfg<LOGN>::Plan, void>::value) {
-        if (plan->d_tw_pk && plan->use_packed) return launch_demod_pk<LOGN, KNOWN_CH, WANT_EQ>(plan, a, n_packets, st);
-    }
     using P = typename DemodCfg<LOGN>::Plan;
     // CTA size: one symbol group needs P::T threads; small CTAs (several per SM) decorrelate the
     // load / FFT / equalise phases of co-resident CTAs
     constexpr int NT = (P::T > DemodCfg<LOGN>::NT) ? P::T : DemodCfg<LOGN>::NT;
     constexpr int MINB = DemodCfg<LOGN>::MINB;
     constexpr int SF = NT / P::T;
+    static_assert(kReseed % SF == 0, "FFT batch must divide the re-seed block");
     const int Nd = a.hi - a.lo;
-    // smallest flush period: multiple of SF, FLUSH*Nd % 16 == 0, at least 8 symbols (amortise the flush)
+    // smallest flush period: multiple of SF, FLUSH*Nd % 16 == 0, at least 8 symbols (amortise the
+    // flush); always a power of two <= 16 or SF itself, so it divides the re-seed block
     int flush = SF;
     while ((flush * Nd) % 16 != 0 || flush < 8) flush += SF;
+    GF3_REQUIRE(kReseed % flush == 0, "rx_demod: flush period %d does not divide the re-seed block", flush);
     a.flush = flush;
     a.tw = plan->d_tw;
+    a.n_packets = n_packets;
     a.chunks_per_packet = (a.L + flush - 1) / flush;
-    // enough CTAs for ~8 waves, otherwise one CTA walks the whole packet
-    const int64_t want = (int64_t)plan->sm_count * MINB * 8;
-    int64_t split = (want + n_packets - 1) / n_packets;
-    if (split < 1) split = 1;
-    if (split > a.chunks_per_packet) split = a.chunks_per_packet;
-    a.chunks_per_cta = (int)((a.chunks_per_packet + split - 1) / split);
-    // CTA boundaries sit on multiples of the 64-symbol re-seed period, so the equaliser recurrence
-    // (and hence every output bit) is independent of how a launch is split into CTAs
-    { const int rc = flush >= 64 ? 1 : 64 / flush; a.chunks_per_cta = (a.chunks_per_cta + rc - 1) / rc * rc; }
-    a.ctas_per_packet = (a.chunks_per_packet + a.chunks_per_cta - 1) / a.chunks_per_cta;
-    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (((size_t)flush * Nd + 15) & ~(size_t)15) + 16
+    const size_t smem = demod_cst_offset<P, NT>() + demod_cst_bytes<P, NT>() + (((size_t)flush * Nd + 15) & ~(size_t)15) + 16
                         + (((size_t)flush * Nd + 15) / 16 + 1) * sizeof(uint32_t);
     auto kern = rx_demod_kernel<P, NT, MINB, KNOWN_CH, WANT_EQ>;
     GF3_REQUIRE(smem <= 227 * 1024, "rx_demod: %zu bytes of shared memory needed (> 227 KB)", smem);
     GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t grid = n_packets * a.ctas_per_packet;
-    GF3_REQUIRE(grid <= 0x7fffffff, "rx_demod: grid too large");
+    // persistent CTAs: one full wave (resident CTAs per SM x SMs); each walks a contiguous, equally
+    // sized range of flush chunks, so the per-CTA set-up (twiddles, XOR words, bin constants) is
+    // paid once per CTA and not once per packet
+    int per_sm = 0;
+    GF3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t total_blocks = n_packets * a.chunks_per_packet;
+    int64_t grid = (int64_t)plan->sm_count * per_sm;
+    if (grid > total_blocks) grid = total_blocks;
+    if (const char* co = getenv("GF3_CARVEOUT")) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
+    if (getenv("GF3_DEBUG"))
+        fprintf(stderr, "[gf3] rx_demod N=%d NT=%d smem=%zu B grid=%lld flush=%d blocks=%lld -> %d CTAs/SM\n", P::N, NT, smem,
+                (long long)grid, a.flush, (long long)total_blocks, per_sm);
     kern<<<(unsigned)grid, NT, smem, st>>>(a);
     GF3_LAUNCH_CHECK();
     return GF3_OK;
