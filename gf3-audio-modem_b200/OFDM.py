@@ -205,6 +205,33 @@ class transmitter(CamG):
             return time_data
         return np.hstack([time_data[:, -self.cp_length:], time_data])
 
+    def send_to_stream(self, time_data, sync):
+        """OFDM.py:242-276: frame time-domain symbols (CP included) into packets with the known
+        symbols and the caller's sync waveform; the frame is assembled on the device."""
+        import torch
+        phy = self.phy
+        symlen = self.ofdm_symbol_size + self.cp_length
+        packets = np.asarray(time_data).reshape(-1, self.packet_length, symlen)             # OFDM.py:251 (raises like numpy)
+        self.no_packets = packets.shape[0]
+        sync = np.asarray(sync)
+        d_data = torch.from_numpy(np.ascontiguousarray(packets.real, dtype=np.float32).reshape(self.no_packets, -1)).to(phy.device)
+        d_sync = torch.from_numpy(np.ascontiguousarray(sync.real, dtype=np.float32)).to(phy.device)
+        tx = phy.tx_frame(d_data, d_sync).cpu().numpy().astype(np.float64)
+        # frames for visuals (OFDM.py:262-274): index bookkeeping on the host
+        ls = sync.shape[0]
+        frame_length = tx.shape[0]
+        sync_valid = np.zeros(frame_length); known_valid = np.zeros(frame_length); payload_valid = np.zeros(frame_length)
+        sync_valid[0:ls] = 1
+        if ls:
+            sync_valid[-ls:] = 1
+        for f in np.hstack([np.arange(self.no_pilots), np.arange(self.no_pilots + self.packet_length, 2 * self.no_pilots + self.packet_length)]):
+            known_valid[ls + symlen * f + self.cp_length + np.arange(self.ofdm_symbol_size)] = 1
+        for f in range(self.packet_length):
+            payload_valid[ls + symlen * (self.no_pilots + f) + self.cp_length + np.arange(self.ofdm_symbol_size)] = 1
+        sync_valid = np.tile(sync_valid, self.no_packets); known_valid = np.tile(known_valid, self.no_packets)
+        payload_valid = np.tile(payload_valid, self.no_packets)
+        return tx, sync_valid, known_valid, payload_valid
+
     def _modulate(self, bits_encoded, filler):
         """Fused device transmit chain: encoded bits -> framed waveform (float64 numpy)."""
         import torch
@@ -291,6 +318,31 @@ class receiver(transmitter):
         end_pilots = OFDM_symbols[:, -self.no_pilots:, self.carriers]
         data_symbols = OFDM_symbols[:, self.no_pilots:-self.no_pilots, self.carriers]
         return data_symbols, start_pilots, end_pilots
+
+    def equalise(self, data_symbols, start_pilots, end_pilots):
+        """OFDM.py:422-480 on spectra (what get_data returns), on the device:
+        -> (data_eq[pk*L, K], Hest_start[pk, K], Hest_end[pk, K], Hest[pk, L, K])."""
+        import torch
+        data_symbols = np.asarray(data_symbols)
+        if self.no_pilots == 0:
+            return data_symbols.reshape(-1, self.K)                # OFDM.py:424-425 (different return arity)
+        phy = self.phy
+        to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex64)).to(phy.device)
+        d_start, d_end, d_data = to_dev(start_pilots), to_dev(end_pilots), to_dev(data_symbols)
+        Hs, He, slope = phy.eq_estimate(d_start, d_end)
+        eq, hest = phy.eq_apply(d_data, Hs, He, slope)
+        c128 = lambda t: t.cpu().numpy().astype(np.complex128)
+        return c128(eq).reshape(-1, self.K), c128(Hs), c128(He), c128(hest)
+
+    def demap(self, symbols):
+        """OFDM.py:484-500: minimum-distance QPSK decisions -> (bits[n, carriers, 2], hardDecision)."""
+        import torch
+        if type(symbols) != np.ndarray:                            # noqa: E721  (the reference's own check, OFDM.py:485)
+            raise ValueError("Symbols must be numpy array")
+        phy = self.phy
+        d = torch.from_numpy(np.ascontiguousarray(symbols, dtype=np.complex64)).to(phy.device)
+        bits, hard = phy.demap(d)
+        return bits.cpu().numpy().astype(np.int64), hard.cpu().numpy().astype(np.complex128)
 
     def PS(self, bits):
         return bits.reshape((-1,))

@@ -12,6 +12,7 @@
 
 #include "gf3_common.cuh"
 #include "gf3_fft.cuh"
+#include "gf3_fit.cuh"
 
 namespace gf3 {
 
@@ -22,6 +23,9 @@ constexpr int kThreads = 256;
 //   2 = one bulk L2 prefetch per symbol (cp.async.bulk.prefetch.L2, TMA engine, no registers)
 #ifndef GF3_PREFETCH
 #define GF3_PREFETCH (-1)      // -1: per-plan default (see rx_demod_kernel)
+#endif
+#ifndef GF3_FLUSH_UNROLL
+#define GF3_FLUSH_UNROLL 2
 #endif
 #ifndef GF3_DEMOD_CST
 #define GF3_DEMOD_CST 0
@@ -522,11 +526,12 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                     const uint32_t t0 = v.x * 0x40100401u, t1 = v.y * 0x40100401u, t2 = v.z * 0x40100401u, t3 = v.w * 0x40100401u;
                     return __byte_perm(__byte_perm(t0, t1, 0x0073), __byte_perm(t2, t3, 0x0073), 0x5410);
                 };
+                constexpr int FU = GF3_FLUSH_UNROLL;
                 if (use_xor) {
-#pragma unroll 2
+#pragma unroll FU
                     for (int w = tid; w < nfull; w += NT) out[w] = pack16(w) ^ xorw[w];
                 } else {
-#pragma unroll 2
+#pragma unroll FU
                     for (int w = tid; w < nfull; w += NT) out[w] = pack16(w);
                 }
                 if (nwords > nfull && tid == 0) {                   // the chunk's last, partial word: pad bits stay zero
@@ -686,51 +691,8 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
     __syncthreads();
 
     // ---- 4. unwrap both phase rows, difference, LS slope over [fit_lo, fit_hi) (0-based carrier index)
-    const int nfit = fhi - flo;
-    const int SEG = (nfit + NT - 1) / NT;
-    const int i0 = flo + tid * SEG, i1 = min(fhi, i0 + SEG);
-    const double PI = 3.14159265358979323846;
-    // np.unwrap: a jump dd > pi subtracts 2 pi, dd < -pi adds 2 pi, |dd| == pi is left alone
-    int local = 0;
-    for (int i = max(i0, flo + 1); i < i1; ++i) {
-        const double de = phi[K + i] - phi[K + i - 1], ds = phi[i] - phi[i - 1];
-        local += (de > PI ? -1 : de < -PI ? 1 : 0) - (ds > PI ? -1 : ds < -PI ? 1 : 0);
-    }
-    int incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((tid & 31) >= o) incl += v;
-    }
-    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
-    __syncthreads();
-    int prefix = incl - local;
-    for (int w = 0; w < (tid >> 5); ++w) prefix += warp_tot[w];
-    // walk the segment
-    const double xbar = 0.5 * (double)(nfit - 1);
-    double sxy = 0.0;
-    int run = prefix;
-    for (int i = i0; i < i1; ++i) {
-        if (i >= flo + 1) {
-            const double de = phi[K + i] - phi[K + i - 1], ds = phi[i] - phi[i - 1];
-            run += (de > PI ? -1 : de < -PI ? 1 : 0) - (ds > PI ? -1 : ds < -PI ? 1 : 0);
-        }
-        if (i >= flo && i < fhi) {
-            const double y = (phi[K + i] - phi[i]) + 2.0 * PI * (double)run;
-            sxy += ((double)(i - flo) - xbar) * y;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sxy += __shfl_xor_sync(0xffffffffu, sxy, o);
-    if ((tid & 31) == 0) red[tid >> 5] = sxy;
-    __syncthreads();
-    if (tid == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < NT / 32; ++w) tot += red[w];
-        const double n = (double)nfit;
-        const double sxx = n * (n * n - 1.0) / 12.0;
-        a.slope[pkt] = nfit >= 2 ? tot / sxx : __longlong_as_double(0x7ff8000000000000LL);   // polyfit needs >= 2 points
-    }
+    const double sl = fit_slope<NT>(phi, K, flo, fhi, warp_tot, red);
+    if (tid == 0) a.slope[pkt] = sl;
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -744,7 +706,11 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
 template <int LOGN> struct DemodCfg { using Plan = FftPlan<LOGN>; static constexpr int NT = GF3_DEMOD_THREADS, MINB = GF3_DEMOD_MINB; };
 // N = 4096: 128 threads per symbol (16 x 16 x 8), two symbols per 256-thread CTA.  (A warp-per-symbol
 // 64 x 32 plan with ~255 registers / thread was measured slower: 8 warps per SM cannot hide latency.)
-template <> struct DemodCfg<12> { using Plan = FftPlan<12>; static constexpr int NT = 256, MINB = 2; };
+#ifndef GF3_DEMOD12_THREADS
+#define GF3_DEMOD12_THREADS 256
+#define GF3_DEMOD12_MINB 2
+#endif
+template <> struct DemodCfg<12> { using Plan = FftPlan<12>; static constexpr int NT = GF3_DEMOD12_THREADS, MINB = GF3_DEMOD12_MINB; };
 
 template <int LOGN, bool KNOWN_CH, bool WANT_EQ>
 static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaStream_t st) {

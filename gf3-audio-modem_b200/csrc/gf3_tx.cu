@@ -243,6 +243,60 @@ static int launch_tx(const gf3_plan* plan, TxArgs a, const float* known, int64_t
     return GF3_OK;
 }
 
+// Stage-level send_to_stream (gf3_stage.cu): every packet's [sync | P x known | .. | P x known] and the
+// trailing sync, with the caller's own sync waveform (OFDM.py:244-259).
+template <class P>
+static int launch_frame_known(const gf3_plan* plan, const float* known, const float* sync, int sync_len,
+                              int64_t n_packets, float* out, float* known_time, cudaStream_t st) {
+    constexpr int SF = kTxThreads / P::T;
+    const gf3_params& p = plan->p;
+    const int Nd = p.hi - p.lo;
+    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)SF * ((2 * Nd + 7) / 8 + 1) + 16;
+    TxArgs k;
+    memset(&k, 0, sizeof(k));
+    k.known = reinterpret_cast<const float2*>(known); k.tw = plan->d_tw; k.out = known_time;
+    k.cp = p.cp; k.lo = p.lo; k.hi = p.hi; k.P = p.n_pilots; k.L = p.packet_len; k.chirp_len = sync_len;
+    k.gain = p.tx_gain / (float)p.N;
+    auto kern = tx_symbols_kernel<P, true>;
+    GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, kTxThreads, smem, st>>>(k);
+    GF3_LAUNCH_CHECK();
+    FrameArgs f;
+    f.chirp = sync; f.known_time = known_time; f.out = out;
+    f.pk_per_stream = n_packets; f.n_streams = 1; f.symlen = p.N + p.cp; f.P = p.n_pilots; f.L = p.packet_len;
+    f.chirp_len = sync_len;
+    f.out_stride = 0;
+    const int seg = sync_len + 2 * f.P * f.symlen;
+    int gx = (seg + 256 * 4 - 1) / (256 * 4);
+    if (gx < 1) gx = 1;
+    f.gx = gx;
+    const int64_t rows = n_packets + 1;
+    GF3_REQUIRE(rows * gx <= 0x7fffffff, "tx_frame: too many packets in one call");
+    tx_frame_kernel<<<(unsigned)(rows * gx), 256, 0, st>>>(f);
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}
+
+int tx_frame_known(const gf3_plan* plan, const float* known, const float* sync, int sync_len, int64_t n_packets,
+                   float* out, cudaStream_t st) {
+    const gf3_params& p = plan->p;
+    float* known_time = const_cast<gf3_plan*>(plan)->d_known_time;
+    if (!known_time) {
+        GF3_CHECK_CUDA(cudaMalloc(&known_time, (size_t)(p.N + p.cp) * sizeof(float)));
+        const_cast<gf3_plan*>(plan)->d_known_time = known_time;
+    }
+    switch (plan->logN) {
+        case 6: return launch_frame_known<FftPlan<6>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
+        case 7: return launch_frame_known<FftPlan<7>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
+        case 8: return launch_frame_known<FftPlan<8>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
+        case 9: return launch_frame_known<FftPlan<9>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
+        case 10: return launch_frame_known<FftPlan<10>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
+        case 11: return launch_frame_known<FftPlan<11>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
+        case 12: return launch_frame_known<FftPlan<12>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
+        default: gf3::set_error("unsupported N"); return GF3_ERR_INVALID;
+    }
+}
+
 }  // namespace gf3
 
 using namespace gf3;

@@ -229,6 +229,51 @@ class Phy:
         check(self.lib.gf3_pcm_to_f32(_ptr(pcm), 0 if pcm.dtype == torch.uint8 else 1, pcm.numel(), _ptr(out), _stream()))
         return out
 
+    # ------------------------------------------------------------------ stage-level methods
+    def eq_estimate(self, start, end):
+        """First half of receiver.equalise on spectra (OFDM.py:429-462):
+        start, end complex64 [n_packets, P, K] -> Hs, He [n_packets, K], slope float64 [n_packets]."""
+        assert start.is_cuda and start.dtype == torch.complex64 and start.is_contiguous() and start.shape[1:] == (self.P, self.K)
+        assert end.is_cuda and end.dtype == torch.complex64 and end.is_contiguous() and end.shape == start.shape
+        n = start.shape[0]
+        Hs = torch.empty((n, self.K), dtype=torch.complex64, device=self.device)
+        He = torch.empty_like(Hs)
+        slope = torch.empty((n,), dtype=torch.float64, device=self.device)
+        check(self.lib.gf3_eq_estimate(self._plan, _ptr(start), _ptr(end), n, _ptr(self.known), _ptr(Hs), _ptr(He),
+                                       _ptr(slope), _stream()))
+        return Hs, He, slope
+
+    def eq_apply(self, data, Hs, He, slope, want_hest=True):
+        """Second half of receiver.equalise (OFDM.py:466-478): data complex64 [n_packets, L, K]
+        -> eq (and Hest) complex64 [n_packets, L, K]."""
+        assert data.is_cuda and data.dtype == torch.complex64 and data.is_contiguous() and data.shape[1:] == (self.L, self.K)
+        n = data.shape[0]
+        eq = torch.empty_like(data)
+        hest = torch.empty_like(data) if want_hest else None
+        check(self.lib.gf3_eq_apply(self._plan, _ptr(data), n, _ptr(Hs.contiguous()), _ptr(He.contiguous()),
+                                    _ptr(slope.contiguous()), _ptr(eq), _ptr(hest), _stream()))
+        return (eq, hest) if want_hest else eq
+
+    def demap(self, symbols, want_hard=True):
+        """receiver.demap (OFDM.py:484-500): complex64 [...] -> bits uint8 [..., 2] (and hard decisions)."""
+        assert symbols.is_cuda and symbols.dtype == torch.complex64 and symbols.is_contiguous()
+        n = symbols.numel()
+        bits = torch.empty(symbols.shape + (2,), dtype=torch.uint8, device=self.device)
+        hard = torch.empty_like(symbols) if want_hard else None
+        check(self.lib.gf3_demap(_ptr(symbols), n, _ptr(bits), _ptr(hard), _stream()))
+        return (bits, hard) if want_hard else bits
+
+    def tx_frame(self, data_time, sync):
+        """transmitter.send_to_stream (OFDM.py:244-259): data_time float32 [n_packets, L*(N+cp)],
+        sync float32 [Ls] -> framed waveform float32 [n_packets*(Ls + (2P+L)(N+cp)) + Ls]."""
+        assert data_time.is_cuda and data_time.dtype == torch.float32 and data_time.is_contiguous()
+        assert sync.is_cuda and sync.dtype == torch.float32 and sync.is_contiguous()
+        n = data_time.shape[0]
+        ls = sync.numel()
+        out = torch.empty((n * (ls + self.pkt_samples) + ls,), dtype=torch.float32, device=self.device)
+        check(self.lib.gf3_tx_frame(self._plan, _ptr(data_time), n, _ptr(sync), ls, _ptr(self.known), _ptr(out), _stream()))
+        return out
+
     # ------------------------------------------------------------------ whole receive chain
     def receive_packets(self, samples, n_packets, pkt_offset=None, xor=True, want_eq=False):
         """estimate + demod for n_packets packets whose starts are known."""

@@ -158,6 +158,28 @@ GF3_API int gf3_tx_modulate(const gf3_plan* plan, const uint8_t* bits_packed, in
                     const float* filler, const float* known, int64_t n_streams,
                     int64_t pk_per_stream, float* out, int64_t out_stride, void* stream);
 
+/* ---- stage-level entry points (SURVEY 8a rows 5, 9, 11 as separate public methods) ------ */
+/* receiver.equalise, first half (OFDM.py:429-462) on spectra the caller already holds:
+ *   start, end  complex64 [n_packets, P, K]  bins 1..K of the leading / trailing known symbols
+ *   -> Hs, He complex64 [n_packets, K], slope float64 [n_packets] exactly as gf3_rx_estimate   */
+GF3_API int gf3_eq_estimate(const gf3_plan* plan, const float* start, const float* end, int64_t n_packets,
+                    const float* known, float* Hs, float* He, double* slope, void* stream);
+/* receiver.equalise, second half (OFDM.py:466-478):
+ *   data complex64 [n_packets, L, K] -> eq = data / Hest, Hest = (|Hs| + (|He|-|Hs|) w) *
+ *   exp(j (angle(Hs) + slope n w)), w = (l + P/2)/(L + P); Hest [n_packets, L, K] or NULL        */
+GF3_API int gf3_eq_apply(const gf3_plan* plan, const float* data, int64_t n_packets, const float* Hs,
+                 const float* He, const double* slope, float* eq, float* Hest, void* stream);
+/* receiver.demap (OFDM.py:484-500): minimum-distance QPSK decisions of n symbols.
+ *   bits uint8 [n, 2] = (b0, b1) per symbol; hard complex64 [n] (the chosen constellation points)
+ *   or NULL.  Exact ties resolve as the reference's argmin over its constellation order does.   */
+GF3_API int gf3_demap(const float* symbols, int64_t n, uint8_t* bits, float* hard, void* stream);
+/* transmitter.send_to_stream (OFDM.py:244-259) on symbols already in the time domain:
+ *   data_time float32 [n_packets, L*(N+cp)] (CP included, no gain), sync float32 [sync_len]
+ *   out float32 [n_packets*(sync_len + (2P+L)(N+cp)) + sync_len]:
+ *   per packet [sync | g*(P x known) | g*data | g*(P x known)], then one trailing sync          */
+GF3_API int gf3_tx_frame(const gf3_plan* plan, const float* data_time, int64_t n_packets, const float* sync,
+                 int32_t sync_len, const float* known, float* out, void* stream);
+
 /* ---- channel simulator + BER counters ---------------------- */
 /* y = lfilter(taps, 1, x) + sigma * N(0,1) (Philox-4x32-10 counter RNG, Box-Muller).
  *   taps [n_streams, n_taps] float32 (n_taps <= 64), sigma [n_streams] float32            */

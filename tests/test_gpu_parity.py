@@ -99,6 +99,57 @@ def test_stage_receive_chain(name, known_sequence):
 
 
 @pytest.mark.parametrize("name", STAGE_NAMES)
+def test_stage_level_methods(name, known_sequence):
+    """receiver.equalise / receiver.demap / transmitter.send_to_stream as separate public methods
+    (OFDM.py:422-480, 484-500, 242-276), fed with the oracle's spectra of the golden recordings."""
+    import OFDM
+    g = load_golden("stage_%s.npz" % name)
+    p = oracle_params(g["cfg"], known_sequence)
+    N, cp, lo, hi, P, L = (int(x) for x in g["cfg"][:6])
+    rx = OFDM.receiver("A2", "XOR", no_pilots=P, packet_length=L, ofdm_symbol_size=N, cp_length=cp,
+                       lowest_bin=lo, highest_bin=hi)
+    rx.known_sequence = np.asarray(known_sequence)
+    r = g["r_i16"].astype(np.float64)
+    starts = (g["peaks"] + 2)[:-1]
+    n = (2 * P + L) * (N + cp)
+    rx_cp = np.stack([r[s:s + n] for s in starts]).reshape(len(starts), 2 * P + L, N + cp)
+    data, sp, ep = orc.get_data(p, orc.rx_fft(p, rx_cp))
+    rx.no_packets = len(starts)
+    eq, Hs, He, Hest = rx.equalise(data, sp, ep)
+    ref_eq, rHs, rHe, rHest, _ = orc.equalise(p, data, sp, ep)
+    assert eq.shape == ref_eq.shape and Hest.shape == rHest.shape and eq.dtype == np.complex128
+    hscale = np.max(np.abs(rHs))
+    assert np.max(np.abs(Hs - rHs)) / hscale < 2e-6 and np.max(np.abs(He - rHe)) / hscale < 2e-6
+    assert np.max(np.abs(Hs - g["Hs"])) / hscale < 2e-6            # and the reference's own values
+    dc = p.data_carriers - 1
+    assert _rel_err(eq[:, dc], ref_eq[:, dc]).max() < EQ_RTOL
+    assert _rel_err(Hest[:, :, dc], rHest[:, :, dc]).max() < EQ_RTOL
+    # demap: same decisions as the oracle on the oracle's own constellation, exact ties included
+    pts = np.ascontiguousarray(ref_eq[:, dc])
+    bits, hard = rx.demap(pts)
+    assert bits.dtype == np.int64 and bits.shape == pts.shape + (2,)
+    assert np.array_equal(bits, orc.demap(pts.astype(np.complex64)))
+    assert np.allclose(hard, ((1 - 2 * bits[..., 1]) + 1j * (1 - 2 * bits[..., 0])) / np.sqrt(2))
+    ties = np.array([[0, 1, -1, 1j, -1j, 1 + 1j, -1 - 1j, -0.0 + 2j, 3 - 0.0j, -3 - 0.0j]], dtype=complex)
+    tb, _ = rx.demap(ties)
+    assert np.array_equal(tb, orc.demap_min_distance(ties))
+    with pytest.raises(ValueError):
+        rx.demap([1 + 1j])
+    # send_to_stream: framing of time-domain symbols with the caller's sync waveform
+    rng = np.random.default_rng(3)
+    npk = 2
+    time_data = rng.standard_normal((npk * L, N + cp)) * 0.05
+    sync = orc.sync_chirp(p)
+    tx, sv, kv, pv = rx.send_to_stream(time_data, sync)
+    ref_tx, ref_npk = orc.send_to_stream(p, time_data, sync)
+    assert rx.no_packets == ref_npk == npk and tx.shape == ref_tx.shape
+    assert np.max(np.abs(tx - ref_tx)) < 3e-7 * max(1.0, np.max(np.abs(ref_tx)))
+    plen = len(sync) + (2 * P + L) * (N + cp)
+    assert sv.shape == kv.shape == pv.shape == (npk * (npk * plen + len(sync)),)   # OFDM.py:274 tiles the whole frame
+    assert kv.sum() == npk * 2 * P * N and pv.sum() == npk * L * N and sv.sum() == npk * 2 * len(sync)
+
+
+@pytest.mark.parametrize("name", STAGE_NAMES)
 def test_stage_sync(name, known_sequence):
     """row 6: matched filter + detection rule give the reference's sync indices."""
     torch = _torch()
