@@ -249,6 +249,20 @@ class transmitter(CamG):
         out = phy.tx_modulate(d_bits, d_fill, 1, n_packets)
         return out[0].cpu().numpy().astype(np.float64)
 
+    def graphs(self):
+        """OFDM.py:279-292: plot of the Gray-mapped QPSK constellation (needs matplotlib)."""
+        for b1 in [0, 1]:
+            for b0 in [0, 1]:
+                B = (b1, b0)
+                Q = self.mapping_table[B]
+                plt.plot(Q.real, Q.imag, 'bo')
+                plt.text(Q.real, Q.imag + 0.1, "".join(str(x) for x in B), ha='center')
+        plt.grid(alpha=0.5)
+        plt.xlim(-1, 1)
+        plt.ylim(-1, 1)
+        plt.title("QPSK Constellation with Gray Mapping")
+        plt.show()
+
     def transmit(self, bits, graph_output=False):
         """OFDM.py:296-343."""
         print("-" * 42 + "\nTRANSMIT\n" + "-" * 42)
@@ -357,6 +371,26 @@ class receiver(transmitter):
             return np.bitwise_xor(bits_encoded, known_bits)
         return bits_encoded
 
+    def channel_response(self, Hest):
+        """OFDM.py:553-577: plots of |H|, arg H and the impulse response of a channel estimate
+        (Final System Test.ipynb calls it on receive()'s Hest_start; needs matplotlib)."""
+        f = self.carriers / self.ofdm_symbol_size * self.fs
+        for y, yl, name in ((abs(Hest), "|H(f)|", "plots/Channel_mag"), (np.angle(Hest), "arg(H(f))", "plots/Channel_freq")):
+            plt.plot(f, y, label='Estimated channel')
+            plt.ylabel(yl)
+            plt.xlabel("Frequency")
+            plt.title("Channel Frequency Response Estimate")
+            plt.savefig(name)
+            plt.show()
+        h = np.fft.ifft(Hest)
+        time = np.linspace(0, (len(h)), len(h))
+        plt.plot(time[:500], h.real[:500])
+        plt.title("Channel Impulse Response")
+        plt.ylabel("h")
+        plt.xlabel("time (samples)")
+        plt.savefig("plots/Channel_inpulse")
+        plt.show()
+
     def receive_packets(self, rx_cp, want_eq=False):
         """Device receive chain on already-sliced packets rx_cp[pk, 2P+L, N+cp] (what get_symbols
         returns): returns dict(bits, Hs, He, slope[, eq]).  Rows 8-12 of SURVEY 8a in two launches."""
@@ -370,8 +404,7 @@ class receiver(transmitter):
 
     def _demod_device(self, d_samples, n_packets, d_off, want_eq):
         phy = self.phy
-        Hs, He, slope = phy.rx_estimate(d_samples, n_packets, d_off)
-        res = phy.rx_demod(d_samples, n_packets, Hs, He, slope, d_off, xor=(self.encoding == "XOR"), want_eq=want_eq)
+        res, Hs, He, slope = phy.rx_receive(d_samples, n_packets, d_off, xor=(self.encoding == "XOR"), want_eq=want_eq)
         bits_packed, eq = res if want_eq else (res, None)
         out = dict(bits=phy.unpack_bits(bits_packed), Hs=Hs.cpu().numpy().astype(np.complex128),
                    He=He.cpu().numpy().astype(np.complex128), slope=slope.cpu().numpy())

@@ -7,7 +7,8 @@ namespace gf3 {
 
 // OFDM.py:454-462: phase_diff = unwrap(angle(He)) - unwrap(angle(Hs)) along the bins, then the
 // least-squares slope of phase_diff[fit_lo:fit_hi] against 0, 1, 2, ...  (np.polyfit degree 1).
-//   phi        : [2][K] phases in shared memory, row 0 = angle(Hs), row 1 = angle(He); only the
+//   phi        : phases in shared memory, row 0 = angle(Hs) at phi[i], row 1 = angle(He) at phi[K + i]
+//                (K = row stride; callers that store only the window pass a shifted base); only the
 //                entries inside [flo, fhi) are read.  np.unwrap's jumps before the window shift
 //                unwrap(He) - unwrap(Hs) by a constant there, which does not change the slope.
 //   warp_tot   : int    [NT / 32] shared scratch

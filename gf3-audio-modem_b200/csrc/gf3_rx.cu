@@ -57,6 +57,9 @@ struct RxArgs {
     int64_t n_packets;
     int chunks_per_packet;       // flush chunks (work items) per packet = ceil(L / flush)
     int flush;                   // symbols per flush chunk
+    // fused channel estimate (FUSE_EST): Hs / He / slope above are then OUTPUTS of the same launch
+    const float2* known;         // [K]
+    int fit_lo, fit_hi;
 };
 
 // streaming 8-byte load that does not pollute L1
@@ -144,6 +147,13 @@ __host__ __device__ constexpr size_t demod_cst_bytes() {
     constexpr int TB = (P::M / 2 < NT) ? P::M / 2 : NT;
     return demod_cst_in_smem<P, NT>() ? (size_t)2 * ((P::M / 2) / TB) * NT * 16 : 0;
 }
+// pilot blocks the fused estimate processes at a time: both when their sums and spectra fit the
+// data-symbol kernel's spectrum buffer, else one after the other (N = 4096)
+template <class P, int NT>
+__host__ __device__ constexpr int demod_est_par() {
+    return (2 * (P::M + P::MP) <= (NT / P::T) * P::MP && 2 * P::T <= NT) ? 2 : 1;
+}
+constexpr int GF3_FUSE_UNFIT = 1;      // internal: the fused estimate does not fit this geometry, use two launches
 constexpr int kReseed = 64;     // data symbols per work item = distance between exact re-seeds of the equaliser recurrence
 
 // exp(-j * a) for a double-precision phase a (reduced in double, evaluated in float)
@@ -157,13 +167,132 @@ __device__ __forceinline__ float2 expmj(double a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Channel estimate of ONE packet by all NT threads of a CTA (OFDM.py:407-418,593,429-462): the
+// same four steps as rx_estimate_kernel below, callable from inside the data-symbol kernel so that
+// the whole receive chain of a packet is one launch.
+//   1. time-domain sum of the P leading / trailing known symbols (the FFT is linear)
+//   2. real FFT of the sum, 3. divide by the known symbol -> Hs / He (global) and the fit-window
+//   phases (shared), 4. unwrap + least-squares slope.
+// Scratch: work = float2[>= PAR * (M + MP)] where PAR (1 or 2) pilot blocks are processed at a time;
+// phi = double[2 * (fit_hi - fit_lo)].  Contains __syncthreads; the slope is returned to every thread.
+// ------------------------------------------------------------------------------------------
+template <class P, int NT, int PAR>
+__device__ __noinline__ double estimate_packet(const float* pkt_base, int symlen, int cp, int Pn, int Ln,
+                                               const float2* __restrict__ known, float2* __restrict__ Hs,
+                                               float2* __restrict__ He, int fit_lo, int fit_hi, float2* work,
+                                               double* phi, const float2* tw, int* warp_tot, double* red,
+                                               double* s_slope) {
+    constexpr int T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP, K = M - 1;
+    static_assert(PAR * T <= NT, "not enough threads for the pilot-block FFTs");
+    const int tid = threadIdx.x;
+    const int flo = max(0, min(fit_lo, K)), fhi = max(flo, min(fit_hi, K)), nfit = fhi - flo;
+    float2* avg = work;                    // [PAR][M]
+    float2* zb = work + PAR * M;           // [PAR][MP]
+    const float invP = 0.5f / (float)Pn;   // the untangled values are 2X
+#pragma unroll 1
+    for (int b0 = 0; b0 < 2; b0 += PAR) {
+        // ---- 1. sums (pure streaming: many 16-byte loads in flight)
+        const float* base0 = pkt_base + cp;
+        const float* base1 = pkt_base + (int64_t)(Pn + Ln) * symlen + cp;
+        const bool al16 = ((reinterpret_cast<uintptr_t>(base0) | reinterpret_cast<uintptr_t>(base1)) & 15) == 0 && (symlen % 4 == 0);
+        if (al16) {
+            constexpr int U = 10;
+            for (int q = tid; q < PAR * (N / 4); q += NT) {
+                const int bl = q / (N / 4), c4 = q % (N / 4);
+                const float* s0 = ((b0 + bl) ? base1 : base0) + 4 * c4;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p0 = 0; p0 < Pn; p0 += U) {
+                    float4 v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int p = p0 + u < Pn ? p0 + u : Pn - 1;
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(s0 + (int64_t)p * symlen));
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (p0 + u < Pn) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+                }
+                *reinterpret_cast<float4*>(&avg[bl * M + 2 * c4]) = acc;
+            }
+        } else {
+            for (int col = tid; col < PAR * M; col += NT) {
+                const int bl = col / M, m = col % M;
+                const float* s0 = ((b0 + bl) ? base1 : base0) + 2 * m;
+                float2 acc = make_float2(0.f, 0.f);
+                const bool al = (reinterpret_cast<uintptr_t>(s0) & 7) == 0 && (symlen % 2 == 0);
+#pragma unroll 4
+                for (int p = 0; p < Pn; ++p) {
+                    const float* sp = s0 + (int64_t)p * symlen;
+                    float2 v;
+                    if (al) v = ldg_stream2(sp);
+                    else { v.x = ldg_stream1(sp); v.y = ldg_stream1(sp + 1); }
+                    acc.x += v.x;
+                    acc.y += v.y;
+                }
+                avg[col] = acc;
+            }
+        }
+        __syncthreads();
+        // ---- 2. FFT of the sums (warps holding an active symbol group take part as whole warps)
+        constexpr int ACTIVE = (PAR * T < 32) ? 32 : PAR * T;
+        if (tid < ACTIVE) {
+            float2 x[R];
+            const int g = (tid / T) % PAR, t = tid % T;
+#pragma unroll
+            for (int i = 0; i < R; ++i) x[i] = avg[g * M + t + i * T];
+            fft_forward<P, (T == ACTIVE && ACTIVE != NT) ? NT : ACTIVE>(x, zb + g * MP, tw, t, g);
+        }
+        __syncthreads();
+        // ---- 3. untangle, divide by the known symbol, Hs / He to global, fit-window phases to smem
+        for (int item = tid; item < PAR * (M / 2); item += NT) {
+            const int bl = item / (M / 2), j = item % (M / 2);
+            const int blk = b0 + bl;
+            const int k = j == 0 ? M / 2 : j, km = M - k;
+            const float2* zs = zb + bl * MP;
+            float sn, cs;
+            sincospif(2.0f * (float)k / (float)N, &sn, &cs);
+            const float2 w2 = make_float2(-sn, -cs);
+            const float2 z1 = zs[zpad<P>(k)], z2 = zs[zpad<P>(km)];
+            const float2 s = make_float2(z1.x + z2.x, z1.y - z2.y);
+            const float2 d = make_float2(z1.x - z2.x, z1.y + z2.y);
+            const float2 tt = cmul(w2, d);
+            const float2 x1 = cadd(s, tt);
+            const float2 x2 = make_float2(s.x - tt.x, tt.y - s.y);
+            float2* Hout = blk ? He : Hs;
+            {
+                const float2 kn = known[k - 1];           // |known| = 1: 1/known = conj(known)
+                float2 h = cmul(x1, cconj(kn));
+                h.x *= invP; h.y *= invP;
+                Hout[k - 1] = h;
+                if (k - 1 >= flo && k - 1 < fhi) phi[blk * nfit + (k - 1 - flo)] = atan2((double)h.y, (double)h.x);
+            }
+            if (j != 0) {
+                const float2 kn = known[km - 1];
+                float2 h = cmul(x2, cconj(kn));
+                h.x *= invP; h.y *= invP;
+                Hout[km - 1] = h;
+                if (km - 1 >= flo && km - 1 < fhi) phi[blk * nfit + (km - 1 - flo)] = atan2((double)h.y, (double)h.x);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- 4. slope
+    const double sl = fit_slope<NT>(phi - flo, nfit, flo, fhi, warp_tot, red);
+    if (tid == 0) *s_slope = sl;
+    __syncthreads();
+    return *s_slope;
+}
+
+// ------------------------------------------------------------------------------------------
 // Data-symbol kernel.  One CTA owns a run of 16-symbol chunks of ONE packet.
 //   phase A: SF symbols at a time, T threads per symbol, FFT in registers -> Z in smem
 //   phase B: thread <-> bin pair (k, M-k): real-FFT untangling, equaliser, demap -> 2-bit codes
 //   flush  : 16 codes -> one 32-bit word of MSB-first packed bits, coalesced store
 // ------------------------------------------------------------------------------------------
-template <class P, int NT, int MINB, bool KNOWN_CH, bool WANT_EQ>
+template <class P, int NT, int MINB, bool KNOWN_CH, bool WANT_EQ, bool FUSE_EST = false>
 __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
+    static_assert(!(KNOWN_CH && FUSE_EST), "the known-channel receiver has no estimate to fuse");
     constexpr int T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP;
     constexpr int SF = NT / T;                        // symbols per FFT batch
     // symbols per packed-bit flush: a multiple of SF that divides kReseed, with FLUSH*Nd % 16 == 0, so
@@ -240,6 +369,9 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
         }
     }
     const double inv_lp = 1.0 / (double)(L + a.P);
+    __shared__ int est_warp_tot[NT / 32];
+    __shared__ double est_red[NT / 32];
+    __shared__ double est_slope;
     __syncthreads();
 
     // phase-A identity of this thread: symbol group ga, lane ta inside the group
@@ -286,7 +418,18 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
             pkt_base = a.samples + (a.pkt_offset ? a.pkt_offset[pkt] : pkt * a.pkt_stride);
             if constexpr (!KNOWN_CH) {
                 Hs = a.Hs + pkt * K;
-                slope = a.slope[pkt];
+                if constexpr (FUSE_EST) {
+                    // the packet's channel estimate, computed here (a packet split between two CTAs is
+                    // estimated by both: same inputs, same arithmetic, same values written)
+                    constexpr int PAR = demod_est_par<P, NT>();
+                    __syncthreads();                    // zbuf / stage are free: every earlier chunk is flushed
+                    slope = estimate_packet<P, NT, PAR>(pkt_base, symlen, a.cp, a.P, L, a.known, const_cast<float2*>(Hs),
+                                                        const_cast<float2*>(a.He) + pkt * K, a.fit_lo, a.fit_hi, zbuf,
+                                                        reinterpret_cast<double*>(stage), tw, est_warp_tot, est_red, &est_slope);
+                    if (tid == 0) const_cast<double*>(a.slope)[pkt] = slope;
+                } else {
+                    slope = a.slope[pkt];
+                }
                 // For the bits only the sign of data * G matters, so the per-symbol rotation
                 // G *= e^{-j delta} may be replaced by G *= (1 - j tan(delta)) = e^{-j delta} / cos(delta):
                 // the same angle, two FMAs.  Valid while cos(delta) > 0 and the growth over one re-seed
@@ -712,7 +855,7 @@ template <int LOGN> struct DemodCfg { using Plan = FftPlan<LOGN>; static constex
 #endif
 template <> struct DemodCfg<12> { using Plan = FftPlan<12>; static constexpr int NT = GF3_DEMOD12_THREADS, MINB = GF3_DEMOD12_MINB; };
 
-template <int LOGN, bool KNOWN_CH, bool WANT_EQ>
+template <int LOGN, bool KNOWN_CH, bool WANT_EQ, bool FUSE_EST = false>
 static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaStream_t st) {
     using P = typename DemodCfg<LOGN>::Plan;
     // CTA size: one symbol group needs P::T threads; small CTAs (several per SM) decorrelate the
@@ -733,8 +876,16 @@ static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaS
     a.chunks_per_packet = (a.L + flush - 1) / flush;
     const size_t smem = demod_cst_offset<P, NT>() + demod_cst_bytes<P, NT>() + (((size_t)flush * Nd + 15) & ~(size_t)15) + 16
                         + (((size_t)flush * Nd + 15) / 16 + 1) * sizeof(uint32_t);
-    auto kern = rx_demod_kernel<P, NT, MINB, KNOWN_CH, WANT_EQ>;
+    auto kern = rx_demod_kernel<P, NT, MINB, KNOWN_CH, WANT_EQ, FUSE_EST>;
     GF3_REQUIRE(smem <= 227 * 1024, "rx_demod: %zu bytes of shared memory needed (> 227 KB)", smem);
+    if constexpr (FUSE_EST) {
+        // sequential pilot blocks (N = 4096) make the in-kernel estimate slower than a separate launch
+        if (demod_est_par<P, NT>() < 2) return GF3_FUSE_UNFIT;
+        // the fused estimate keeps its fit-window phases (2 x window doubles) in the code staging area
+        const int K = P::M - 1;
+        const int flo = a.fit_lo < 0 ? 0 : (a.fit_lo > K ? K : a.fit_lo), fhi = a.fit_hi < flo ? flo : (a.fit_hi > K ? K : a.fit_hi);
+        if ((size_t)2 * (fhi - flo) * sizeof(double) > ((((size_t)flush * Nd + 15) & ~(size_t)15) + 16)) return GF3_FUSE_UNFIT;
+    }
     GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent CTAs: one full wave (resident CTAs per SM x SMs); each walks a contiguous, equally
     // sized range of flush chunks, so the per-CTA set-up (twiddles, XOR words, bin constants) is
@@ -779,7 +930,8 @@ static int launch_estimate(const gf3_plan* plan, EstArgs a, int64_t n_packets, c
 static int demod_common(const gf3_plan* plan, const float* samples, const int64_t* pkt_offset,
                         int64_t n_packets, const float* Hs, const float* He, const double* slope,
                         const uint8_t* xor2, uint8_t* bits, int64_t bits_stride, float* eq,
-                        bool known_ch, int P_override, int L_override, void* stream) {
+                        bool known_ch, int P_override, int L_override, void* stream,
+                        const float* fuse_known = nullptr) {
     GF3_REQUIRE(plan && samples, "rx_demod: null plan or samples");
     GF3_REQUIRE(n_packets >= 0, "rx_demod: negative packet count");
     if (n_packets == 0) return GF3_OK;
@@ -804,6 +956,12 @@ static int demod_common(const gf3_plan* plan, const float* samples, const int64_
         GF3_REQUIRE((reinterpret_cast<uintptr_t>(bits) & 3) == 0, "rx_demod: bits_packed must be 4-byte aligned");
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (fuse_known) {           // estimate + data symbols in one launch (gf3_rx_receive)
+        a.known = reinterpret_cast<const float2*>(fuse_known);
+        a.fit_lo = p.fit_lo; a.fit_hi = p.fit_hi;
+        if (eq) { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P::LOGN, false, true, true>(plan, a, n_packets, st))); }
+        else    { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P::LOGN, false, false, true>(plan, a, n_packets, st))); }
+    }
     if (known_ch) {
         if (eq) { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P::LOGN, true, true>(plan, a, n_packets, st))); }
         else    { GF3_DISPATCH_LOGN(plan->logN, return (launch_demod<P::LOGN, true, false>(plan, a, n_packets, st))); }
@@ -844,6 +1002,41 @@ extern "C" int gf3_rx_demod(const gf3_plan* plan, const float* samples, const in
                             void* stream) {
     return demod_common(plan, samples, pkt_offset, n_packets, Hs, He, slope, xor2, bits_packed,
                         bits_stride, eq, false, -1, -1, stream);
+}
+
+template <class P>
+static int receive_is_fused(const gf3_plan* plan) {
+    using C = DemodCfg<P::LOGN>;
+    constexpr int NT = (P::T > C::NT) ? P::T : C::NT, SF = NT / P::T;
+    if (demod_est_par<P, NT>() < 2) return 0;
+    const gf3_params& p = plan->p;
+    const int K = P::M - 1, Nd = p.hi - p.lo;
+    const int flo = p.fit_lo < 0 ? 0 : (p.fit_lo > K ? K : p.fit_lo), fhi = p.fit_hi < flo ? flo : (p.fit_hi > K ? K : p.fit_hi);
+    int flush = SF;
+    while ((flush * Nd) % 16 != 0 || flush < 8) flush += SF;     // as in launch_demod
+    return (size_t)2 * (fhi - flo) * sizeof(double) <= ((((size_t)flush * Nd + 15) & ~(size_t)15) + 16) ? 1 : 0;
+}
+
+extern "C" int gf3_rx_receive_is_fused(const gf3_plan* plan) {
+    if (!plan || plan->p.n_pilots < 1) return 0;
+    GF3_DISPATCH_LOGN(plan->logN, return receive_is_fused<P>(plan));
+    return 0;
+}
+
+extern "C" int gf3_rx_receive(const gf3_plan* plan, const float* samples, const int64_t* pkt_offset,
+                              int64_t n_packets, const float* known, float* Hs, float* He, double* slope,
+                              const uint8_t* xor2, uint8_t* bits_packed, int64_t bits_stride, float* eq,
+                              void* stream) {
+    GF3_REQUIRE(plan && known && Hs && He && slope, "rx_receive: null argument");
+    GF3_REQUIRE(plan->p.n_pilots >= 1, "rx_receive: n_pilots must be >= 1 (OFDM.py:424 short-circuits no_pilots == 0)");
+    int rc = demod_common(plan, samples, pkt_offset, n_packets, Hs, He, slope, xor2, bits_packed, bits_stride, eq,
+                          false, -1, -1, stream, known);
+    if (rc != GF3_FUSE_UNFIT) return rc;
+    // geometry the fused kernel cannot hold (very wide fit window on a short flush period): two launches
+    rc = gf3_rx_estimate(plan, samples, pkt_offset, n_packets, known, Hs, He, slope, stream);
+    if (rc) return rc;
+    return demod_common(plan, samples, pkt_offset, n_packets, Hs, He, slope, xor2, bits_packed, bits_stride, eq,
+                        false, -1, -1, stream);
 }
 
 extern "C" int gf3_rx_known_channel(const gf3_plan* plan, const float* samples, const int64_t* pkt_offset,

@@ -43,6 +43,8 @@ SIGNATURES = {
     "gf3_launch_count": (c_int64, []),
     "gf3_rx_estimate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gf3_rx_demod": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "gf3_rx_receive": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "gf3_rx_receive_is_fused": (c_int, [c_void_p]),
     "gf3_rx_known_channel": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "gf3_rx_spectrum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "gf3_sync_chirp": (c_int, [c_void_p, c_void_p, c_void_p]),

@@ -43,8 +43,7 @@ class HostReceiver:
                 else:
                     self.d_pcm[k][:n].copy_(sym_host[p0:p0 + n], non_blocking=True)
                     phy.pcm_to_f32(self.d_pcm[k][:n], out=d)
-                Hs, He, slope = phy.rx_estimate(d.reshape(-1), n)
-                phy.rx_demod(d.reshape(-1), n, Hs, He, slope, xor=xor, out=self.d_out[k][:n])
+                phy.rx_receive(d.reshape(-1), n, xor=xor, out=self.d_out[k][:n])        # estimate + data symbols, one launch
                 self.h_out[p0:p0 + n].copy_(self.d_out[k][:n], non_blocking=True)
         for s in self.streams:
             cur.wait_stream(s)

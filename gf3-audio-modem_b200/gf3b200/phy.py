@@ -83,6 +83,8 @@ class Phy:
         self.known_sequence = ks
         known = qpsk_points(ks[: 2 * self.K].reshape(self.K, 2)).astype(np.complex64)     # OFDM.py:429
         self.known = torch.from_numpy(known).to(self.device)
+        # does gf3_rx_receive run the channel estimate inside the data-symbol launch for this geometry?
+        self.fused_receive = bool(self.lib.gf3_rx_receive_is_fused(self._plan))
         kb = ks[: 2 * self.Nd].reshape(self.Nd, 2)
         self.xor2 = torch.from_numpy(((kb[:, 0] << 1) | kb[:, 1]).astype(np.uint8)).to(self.device)   # OFDM.py:542
 
@@ -275,8 +277,21 @@ class Phy:
         return out
 
     # ------------------------------------------------------------------ whole receive chain
+    def rx_receive(self, samples, n_packets, pkt_offset=None, xor=True, want_eq=False, out=None):
+        """Channel estimate + data symbols of n_packets packets in ONE launch (gf3_rx_receive):
+        -> (packed bits [n_packets, bits_stride] (, eq), Hs, He, slope)."""
+        self._f32(samples)
+        off = self._offsets(pkt_offset, n_packets)
+        Hs = torch.empty((n_packets, self.K), dtype=torch.complex64, device=self.device)
+        He = torch.empty_like(Hs)
+        slope = torch.empty((n_packets,), dtype=torch.float64, device=self.device)
+        bits = out if out is not None else torch.empty((n_packets, self.bits_stride), dtype=torch.uint8, device=self.device)
+        eq = torch.empty((n_packets, self.L, self.K), dtype=torch.complex64, device=self.device) if want_eq else None
+        check(self.lib.gf3_rx_receive(self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(self.known), _ptr(Hs), _ptr(He),
+                                      _ptr(slope), _ptr(self.xor2) if xor else None, _ptr(bits), self.bits_stride, _ptr(eq),
+                                      _stream()))
+        return ((bits, eq) if want_eq else bits), Hs, He, slope
+
     def receive_packets(self, samples, n_packets, pkt_offset=None, xor=True, want_eq=False):
-        """estimate + demod for n_packets packets whose starts are known."""
-        Hs, He, slope = self.rx_estimate(samples, n_packets, pkt_offset)
-        out = self.rx_demod(samples, n_packets, Hs, He, slope, pkt_offset, xor=xor, want_eq=want_eq)
-        return out, Hs, He, slope
+        """estimate + demod for n_packets packets whose starts are known (one fused launch)."""
+        return self.rx_receive(samples, n_packets, pkt_offset, xor=xor, want_eq=want_eq)

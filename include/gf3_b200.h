@@ -110,6 +110,20 @@ GF3_API int gf3_rx_demod(const gf3_plan* plan, const float* samples, const int64
                  const uint8_t* xor2, uint8_t* bits_packed, int64_t bits_stride, float* eq,
                  void* stream);
 
+/* The whole receive chain of a batch of packets in ONE launch: gf3_rx_estimate + gf3_rx_demod fused
+ * (every persistent CTA estimates the channel of a packet when it first touches it), so each received
+ * sample is read from HBM once and the estimate's memory-bound phase overlaps the data symbols'
+ * compute of the co-resident CTAs (OFDM.py:591-609 = receiver.receive after synchronisation).
+ * Hs, He, slope are OUTPUTS; the other arguments are those of gf3_rx_demod.                       */
+GF3_API int gf3_rx_receive(const gf3_plan* plan, const float* samples, const int64_t* pkt_offset,
+                   int64_t n_packets, const float* known, float* Hs, float* He, double* slope,
+                   const uint8_t* xor2, uint8_t* bits_packed, int64_t bits_stride, float* eq,
+                   void* stream);
+/* 1 if gf3_rx_receive runs as one launch for this plan; 0 if it falls back to the two launches
+ * gf3_rx_estimate + gf3_rx_demod (N = 4096, where the in-kernel estimate would be slower, or a fit
+ * window too wide for the kernel's scratch).  The results are the same either way.               */
+GF3_API int gf3_rx_receive_is_fused(const gf3_plan* plan);
+
 /* Known-channel receive (old API, Weekend Challenge.ipynb:162-226): Y/H on bins 1..K, demap.
  * Uses the plan's geometry with its n_pilots leading/trailing symbols skipped (create the plan
  * with n_pilots = 0, packet_len = symbols per block).  Hinv[K] = 1/H on bins 1..K.          */

@@ -96,6 +96,15 @@ def test_stage_receive_chain(name, known_sequence):
     packed_raw = phy.rx_demod(d, npk, torch.from_numpy(Hs).cuda(), torch.from_numpy(He).cuda(),
                               torch.from_numpy(slope).cuda(), off, xor=False)
     _check_bits(phy.unpack_bits(packed_raw), g["bits_raw"], g["eq"][:, dc], name + " raw")
+    # the whole chain in one launch (estimate fused into the data-symbol kernel): same bars
+    (packed_f, eq_f), Hs_f, He_f, slope_f = phy.rx_receive(d, npk, off, xor=True, want_eq=True)
+    assert np.max(np.abs(Hs_f.cpu().numpy() - g["Hs"])) / hscale < 2e-6
+    assert np.max(np.abs(He_f.cpu().numpy() - g["He"])) / hscale < 2e-6
+    np.testing.assert_allclose(slope_f.cpu().numpy(), g["slope"], rtol=0, atol=2e-7)
+    assert _rel_err(eq_f.cpu().numpy().reshape(-1, p.K)[:, dc], g["eq"][:, dc]).max() < EQ_RTOL
+    _check_bits(phy.unpack_bits(packed_f), g["bits"], g["eq"][:, dc], name + " fused")
+    packed_f2, _, _, _ = phy.rx_receive(d, npk, off, xor=True)
+    assert torch.equal(packed_f2, packed_f)
 
 
 @pytest.mark.parametrize("name", STAGE_NAMES)
