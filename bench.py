@@ -344,36 +344,38 @@ def run_gpu_arm(args, cfg, streams, desc):
     except Exception as ex:   # report the failure instead of a made-up number
         e2e = {"value": None, "unit": UNIT, "error": repr(ex)}
     # ---- the same path fed with 16-bit PCM host buffers (the native format of the recordings):
-    # half the PCIe bytes; reported separately because the samples are quantised to int16
-    e2e_pcm = None
+    # half / a quarter of the PCIe bytes; reported separately because the samples are quantised (the
+    # reference's own recordings are 8-bit PCM wav files, Final System Test.ipynb:85-86)
+    e2e_pcm = {}
     if e2e.get("value") and not args.no_e2e:
-        try:
-            del hr, h_sym
-            scale = 20000.0 / float(sym.abs().max())
-            sym_q = torch.round(sym * scale).to(torch.int16)
-            h_q = torch.empty(sym_q.shape, dtype=torch.int16).pin_memory()
-            h_q.copy_(sym_q)
-            qf = sym_q.to(torch.float32).reshape(-1)
-            ref_q = phy.rx_receive(qf, n_packets, xor=True)[0]
-            hq = HostReceiver(phy, n_packets, chunk=256, sample_dtype=torch.int16)
-            hq.run(h_q, xor=True)
-            barrier()
-            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            q0.record()
-            for _ in range(e_steps):
-                resq = hq.run(h_q, xor=True)
-            q1.record()
-            barrier()
-            q_ms = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=phy.device)
-            if world > 1:
-                dist.all_reduce(q_ms, op=dist.ReduceOp.MAX)
-            e2e_pcm = {"value": world * n_packets * phy.bits_per_packet * e_steps / (float(q_ms) * 1e-3) / 1e6, "unit": UNIT,
-                       "h2d_bytes_per_step": hq.h2d_bytes, "d2h_bytes_per_step": hq.d2h_bytes, "steps": e_steps,
-                       "note": "int16 PCM host buffers, converted on the device (gf3_pcm_to_f32)",
-                       "matches_device_result": bool(torch.equal(resq[:, :nbytes], ref_q[:, :nbytes].cpu()))}
-            del sym_q, qf, ref_q, hq, h_q
-        except Exception as ex:
-            e2e_pcm = {"value": None, "error": repr(ex)}
+        del hr, h_sym
+        for key, dt, full_scale, off in (("e2e_pcm16", torch.int16, 20000.0, 0.0), ("e2e_pcm8", torch.uint8, 120.0, 128.0)):
+            try:
+                scale = full_scale / float(sym.abs().max())
+                sym_q = (torch.round(sym * scale) + off).to(dt)
+                h_q = torch.empty(sym_q.shape, dtype=dt).pin_memory()
+                h_q.copy_(sym_q)
+                qf = sym_q.to(torch.float32).reshape(-1)
+                ref_q = phy.rx_receive(qf, n_packets, xor=True)[0]
+                hq = HostReceiver(phy, n_packets, chunk=256, sample_dtype=dt)
+                hq.run(h_q, xor=True)
+                barrier()
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q0.record()
+                for _ in range(e_steps):
+                    resq = hq.run(h_q, xor=True)
+                q1.record()
+                barrier()
+                q_ms = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=phy.device)
+                if world > 1:
+                    dist.all_reduce(q_ms, op=dist.ReduceOp.MAX)
+                e2e_pcm[key] = {"value": world * n_packets * phy.bits_per_packet * e_steps / (float(q_ms) * 1e-3) / 1e6, "unit": UNIT,
+                                "h2d_bytes_per_step": hq.h2d_bytes, "d2h_bytes_per_step": hq.d2h_bytes, "steps": e_steps,
+                                "note": "%s PCM host buffers, converted on the device (gf3_pcm_to_f32)" % str(dt).replace("torch.", ""),
+                                "matches_device_result": bool(torch.equal(resq[:, :nbytes], ref_q[:, :nbytes].cpu()))}
+                del sym_q, qf, ref_q, hq, h_q
+            except Exception as ex:
+                e2e_pcm[key] = {"value": None, "error": repr(ex)}
     sampler.stop()
 
     if rank == 0:
@@ -411,7 +413,7 @@ def run_gpu_arm(args, cfg, streams, desc):
                          "chain": {"achieved": chain_b * n_packets * world * args.steps / sec / 1e9 / world,
                                    "frac": chain_b * n_packets * args.steps / sec / 1e9 / peak,
                                    "algorithmic_bytes_per_packet": chain_b}},
-            "e2e": e2e, "e2e_pcm16": e2e_pcm, "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "e2e": e2e, "e2e_pcm16": e2e_pcm.get("e2e_pcm16"), "e2e_pcm8": e2e_pcm.get("e2e_pcm8"), "gpu_launches": int(launches), "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single_thread(cfg)

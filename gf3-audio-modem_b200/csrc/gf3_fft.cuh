@@ -45,32 +45,11 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 __device__ __forceinline__ float2 mul_nj(float2 a) { return make_float2(a.y, -a.x); }   // a * (-j)
 
-// ---------------------------------------------------------------- packed f32x2 arithmetic
-// Blackwell issues FFMA2 / FADD2 / FMUL2 (two fp32 lanes per instruction).  On B200 a scalar
-// 3-register FFMA runs at half rate while FFMA2 reaches the full 128 FMA/clk/SM, and FADD2 / FMUL2
-// take half the issue slots of their scalar forms (tools/microbench/f32x2.cu).  The data-symbol
-// kernel therefore carries TWO independent half-size FFTs of a symbol in the two lanes.
-// ptxas folds the negations below into operand modifiers and uses the scalar-broadcast operand form
-// for (s, s) pairs.
+// packed f32x2 multiply / fused multiply-add (FMUL2 / FFMA2): one issue slot for two fp32 lanes.  On B200
+// a scalar 3-register FFMA runs at about half rate while FFMA2 reaches the full 128 FMA/clk/SM
+// (tools/microbench/f32x2.cu).  ptxas uses the scalar-broadcast operand form for (s, s) pairs.
 __device__ __forceinline__ float2 pk_mul(float2 a, float2 b) { pk64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b))); return pk_unpack(d); }
 __device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) { pk64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b)), "l"(pk_pack(c))); return pk_unpack(d); }
-__device__ __forceinline__ float2 pk_neg(float2 a) { return make_float2(-a.x, -a.y); }
-__device__ __forceinline__ float2 pk_bc(float s) { return make_float2(s, s); }
-
-// two complex numbers, structure-of-arrays: lane x and lane y are independent
-struct cpk { float2 re, im; };
-__device__ __forceinline__ cpk cadd(cpk a, cpk b) { return cpk{pk_add(a.re, b.re), pk_add(a.im, b.im)}; }
-__device__ __forceinline__ cpk csub(cpk a, cpk b) { return cpk{pk_sub(a.re, b.re), pk_sub(a.im, b.im)}; }
-__device__ __forceinline__ cpk mul_nj(cpk a) { return cpk{a.im, pk_neg(a.re)}; }
-// both lanes times the same complex scalar w
-__device__ __forceinline__ cpk cmul_s(cpk a, float2 w) {
-    const float2 wr = pk_bc(w.x), wi = pk_bc(w.y);
-    return cpk{pk_fma(pk_neg(a.im), wi, pk_mul(a.re, wr)), pk_fma(a.re, wi, pk_mul(a.im, wr))};
-}
-// lane-wise complex product
-__device__ __forceinline__ cpk cmul(cpk a, cpk b) {
-    return cpk{pk_fma(pk_neg(a.im), b.im, pk_mul(a.re, b.re)), pk_fma(a.re, b.im, pk_mul(a.im, b.re))};
-}
 
 // Compile-time cos / sin of 2*pi*num/den (exact quadrant reduction on the integers, Taylor series
 // on [0, pi/4]); evaluated in double, rounded to float where used, so in-register twiddles become
@@ -205,34 +184,10 @@ __device__ __forceinline__ float2 mul_w(float2 a) {
     }
 }
 
-template <int NUM, int DEN>
-__device__ __forceinline__ cpk mul_w(cpk a) {
-    constexpr int n = ((NUM % DEN) + DEN) % DEN;
-    if constexpr (n == 0) return a;
-    else if constexpr (4 * n == DEN) return cpk{a.im, pk_neg(a.re)};                // -j
-    else if constexpr (2 * n == DEN) return cpk{pk_neg(a.re), pk_neg(a.im)};        // -1
-    else if constexpr (4 * n == 3 * DEN) return cpk{pk_neg(a.im), a.re};            // +j
-    else if constexpr ((8 * n) % DEN == 0) {
-        constexpr float h = 0.70710678118654752440f;
-        constexpr int o = (8 * n) / DEN;
-        constexpr float c = (o == 1 || o == 7) ? h : -h;
-        constexpr float sn = (o == 1 || o == 3) ? h : -h;
-        // (c re + s im, c im - s re) with |c| = |s|
-        const float2 p = (c * sn > 0.f) ? pk_add(a.re, a.im) : pk_sub(a.re, a.im);   // re + (s/c) im
-        const float2 q = (c * sn > 0.f) ? pk_sub(a.im, a.re) : pk_add(a.im, a.re);   // im - (s/c) re
-        return cpk{pk_mul(p, pk_bc(c)), pk_mul(q, pk_bc(c))};
-    } else {
-        constexpr float c = (float)cx_cos2pi(n, DEN);
-        constexpr float sn = (float)cx_sin2pi(n, DEN);
-        return cpk{pk_fma(a.im, pk_bc(sn), pk_mul(a.re, pk_bc(c))), pk_fma(a.re, pk_bc(-sn), pk_mul(a.im, pk_bc(c)))};
-    }
-}
-
 // ---------------------------------------------------------------- in-register DFT codelets
 // Forward DFT (e^{-2 pi i nk/R}), natural order in and out, on v[0..R).
 template <int R> struct Dft;
 
-// (V = float2: one complex number; V = cpk: two independent ones in the f32x2 lanes)
 template <> struct Dft<1> {
     template <class V> static __device__ __forceinline__ void run(V*) {}
 };
@@ -345,9 +300,6 @@ __host__ __device__ constexpr int zstride() {
     return S == 1 ? 1 : S + (S >> P::LOGPAD);
 }
 
-#ifndef GF3_FFT_SPLIT
-#define GF3_FFT_SPLIT 0
-#endif
 // One Stockham pass.  x[q*RAD + i]: thread-local data; zs: this symbol's padded smem buffer;
 // tw: twiddle table in smem; t: thread index within the symbol group.
 //
@@ -355,25 +307,16 @@ __host__ __device__ constexpr int zstride() {
 // instruction of the last pass writes runs of consecutive bins, which are conflict-free in any
 // layout, and the bin-pair walk of the data-symbol kernel (ascending k, descending M-k) then reads
 // conflict-free too (with padding, 16 descending bins straddle a pad slot and collide 2-way).
-//
-// Half-warp symbol groups (T == 16, Q == 2): both halves of a warp would fetch the SAME 16 twiddles
-// per load instruction (two shared-memory wavefronts for 128 useful bytes).  The upper half-warp
-// therefore takes its two sub-transforms in the opposite order (q ^ 1), so one load instruction
-// fetches 32 distinct twiddles.  Register names stay static; only addresses depend on the half.
 template <class P, int NTHREADS, int PASS, bool NATURAL = false>
 __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__ zs,
                                          const float2* __restrict__ tw, int t, int grp) {
     constexpr int RAD = P::rad(PASS), NS = P::ns(PASS), Q = P::R / RAD, STRIDE = P::M / RAD;
     static_assert(NS != 1 || RAD == (1 << P::LOGPAD), "first pass radix must equal the padding period");
     static_assert(!NATURAL || PASS == P::NPASS - 1, "natural-order output is for the last pass");
-    constexpr bool SPLIT = GF3_FFT_SPLIT && (P::T == 16 && Q == 2 && PASS > 0);
-    int hq = 0;                                         // 0/1: this thread's sub-transform order is flipped
-    if constexpr (SPLIT) hq = (threadIdx.x >> 4) & 1;
     if constexpr (PASS > 0) {
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
-            const int qq = SPLIT ? (q ^ hq) : q;
-            const float2* src = zs + zpad<P>(t + qq * P::T);
+            const float2* src = zs + zpad<P>(t + q * P::T);
             static_for<RAD>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
                 x[q * RAD + i] = src[i * zstride<P, STRIDE>()];
@@ -381,8 +324,7 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
         });
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
-            const int qq = SPLIT ? (q ^ hq) : q;
-            const float2* twp = tw + P::tw_off(PASS) + t + qq * ((RAD - 1) * P::T);
+            const float2* twp = tw + P::tw_off(PASS) + t + q * ((RAD - 1) * P::T);
             static_for<RAD - 1>([&](auto ic) {
                 constexpr int i = decltype(ic)::value + 1;
                 x[q * RAD + i] = cmul(x[q * RAD + i], twp[(i - 1) * P::T]);
@@ -396,8 +338,7 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
     });
     static_for<Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
-        const int qq = SPLIT ? (q ^ hq) : q;
-        const int j = t + qq * P::T;
+        const int j = t + q * P::T;
         const int base = (j / NS) * (NS * RAD) + (j % NS);
         if constexpr (NATURAL) {
             float2* dst = zs + base;

@@ -27,9 +27,6 @@ constexpr int kThreads = 256;
 #ifndef GF3_FLUSH_UNROLL
 #define GF3_FLUSH_UNROLL 2
 #endif
-#ifndef GF3_DEMOD_CST
-#define GF3_DEMOD_CST 0
-#endif
 #ifndef GF3_PHASEB_UNROLL
 #define GF3_PHASEB_UNROLL 4
 #endif
@@ -39,7 +36,6 @@ constexpr int kThreads = 256;
 #ifndef GF3_ABL
 #define GF3_ABL 0
 #endif
-constexpr float kPi = 3.14159265358979323846f;
 
 struct RxArgs {
     const float* samples;
@@ -123,29 +119,9 @@ __device__ __forceinline__ pk64 p_opaque(pk64 v, void* slot) {
 __device__ __forceinline__ void sts_u8_if(unsigned addr, unsigned val, unsigned cond) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u8 [%0], %1;\n\t}" ::"r"(addr), "r"(val), "r"(cond) : "memory");
 }
-// 16-byte shared-memory load the compiler must not hoist out of its phase or re-materialise
-__device__ __forceinline__ ulonglong2 lds_v2(const ulonglong2* p) {
-    ulonglong2 v;
-    asm volatile("ld.volatile.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y)
-                 : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
-    return v;
-}
-// Option (GF3_DEMOD_CST=1): plans with many bin pairs per thread (N = 4096: 4) keep the per-thread
-// phase-B constants in shared memory and re-read them every batch instead of holding them in registers
-// through the FFT phase.  Off by default: at N = 4096 the extra 32 KB costs the second CTA per SM.
 template <class P, int NT>
-__host__ __device__ constexpr bool demod_cst_in_smem() {
-    constexpr int TB = (P::M / 2 < NT) ? P::M / 2 : NT;
-    return GF3_DEMOD_CST && (P::M / 2) / TB >= 4;
-}
-template <class P, int NT>
-__host__ __device__ constexpr size_t demod_cst_offset() {      // [zbuf | tw | cst (16-byte aligned) | stage | xorw]
+__host__ __device__ constexpr size_t demod_stage_offset() {    // shared memory: [zbuf | tw | (16-byte aligned) stage | xorw]
     return (((size_t)((NT / P::T) * P::MP + P::TW_TOTAL) * sizeof(float2)) + 15) & ~(size_t)15;
-}
-template <class P, int NT>
-__host__ __device__ constexpr size_t demod_cst_bytes() {
-    constexpr int TB = (P::M / 2 < NT) ? P::M / 2 : NT;
-    return demod_cst_in_smem<P, NT>() ? (size_t)2 * ((P::M / 2) / TB) * NT * 16 : 0;
 }
 // pilot blocks the fused estimate processes at a time: both when their sums and spectra fit the
 // data-symbol kernel's spectrum buffer, else one after the other (N = 4096)
@@ -312,10 +288,7 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* zbuf = reinterpret_cast<float2*>(smem_raw);
     float2* tw = zbuf + SF * MP;
-    constexpr bool CST = demod_cst_in_smem<P, NT>();
-    // [2*PP][NT] 16-byte records (wA, wB)[pp], (Ure, Uim)[pp] when CST
-    ulonglong2* cst = reinterpret_cast<ulonglong2*>(smem_raw + demod_cst_offset<P, NT>());
-    uint8_t* stage = smem_raw + demod_cst_offset<P, NT>() + demod_cst_bytes<P, NT>();   // [FLUSH*Nd] 2-bit codes, one per byte
+    uint8_t* stage = smem_raw + demod_stage_offset<P, NT>();                 // [FLUSH*Nd] 2-bit codes, one per byte
 
     const int tid = threadIdx.x;
     const int Nd = a.hi - a.lo;
@@ -360,13 +333,9 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
         const int k = j == 0 ? M / 2 : j;
         float s, c;
         sincospif(2.0f * (float)k / (float)N, &s, &c);
-        wA[pp] = wB[pp] = Ure[pp] = Uim[pp] = Gre[pp] = Gim[pp] = 0ull;
-        if constexpr (CST) {
-            cst[(2 * pp) * NT + tid] = make_ulonglong2(pk_pack(make_float2(-s, -c)), pk_pack(make_float2(c, -s)));
-        } else {
-            wA[pp] = p_opaque(pk_pack(make_float2(-s, -c)), my_slot);   // -j * exp(-2 pi i k / N) = -s - j c
-            wB[pp] = p_opaque(pk_pack(make_float2(c, -s)), my_slot);
-        }
+        wA[pp] = p_opaque(pk_pack(make_float2(-s, -c)), my_slot);   // -j * exp(-2 pi i k / N) = -s - j c
+        wB[pp] = p_opaque(pk_pack(make_float2(c, -s)), my_slot);
+        Ure[pp] = Uim[pp] = Gre[pp] = Gim[pp] = 0ull;
     }
     const double inv_lp = 1.0 / (double)(L + a.P);
     __shared__ int est_warp_tot[NT / 32];
@@ -449,12 +418,8 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                         ur = pk_pack(make_float2(r1.x, r2.x));
                         ui = pk_pack(make_float2(r1.y, r2.y));
                     }
-                    if constexpr (CST) {
-                        cst[(2 * pp + 1) * NT + tid] = make_ulonglong2(ur, ui);
-                    } else {
-                        Ure[pp] = ur;
-                        Uim[pp] = ui;
-                    }
+                    Ure[pp] = ur;
+                    Uim[pp] = ui;
                 }
             }
         }
@@ -480,12 +445,7 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                 if (steps > 0) {
 #pragma unroll
                     for (int pp = 0; pp < PP; ++pp) {
-                        pk64 ur = Ure[pp], ui = Uim[pp];
-                        if constexpr (CST) {
-                            const ulonglong2 uc = lds_v2(cst + (2 * pp + 1) * NT + tid);
-                            ur = uc.x;
-                            ui = uc.y;
-                        }
+                        const pk64 ur = Ure[pp], ui = Uim[pp];
                         pk64 gre = Gre[pp], gim = Gim[pp];
 #pragma unroll 1
                         for (int i = 0; i < steps; ++i) {
@@ -568,16 +528,6 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                             zp2[pp] = zbuf + sb * MP + (NAT ? km : zpad<P>(km));
                             sp1[pp] = st0 + k;
                             sp2[pp] = st0 + km;
-                            if constexpr (CST) {
-                                const ulonglong2 wc = lds_v2(cst + (2 * pp) * NT + tid);
-                                wA[pp] = wc.x;
-                                wB[pp] = wc.y;
-                                if constexpr (!KNOWN_CH) {
-                                    const ulonglong2 uc = lds_v2(cst + (2 * pp + 1) * NT + tid);
-                                    Ure[pp] = uc.x;
-                                    Uim[pp] = uc.y;
-                                }
-                            }
                             e2[pp] = j != 0;
                             if (k >= a.lo && k < a.hi) dmask |= 1u << (2 * pp);
                             if (e2[pp] && km >= a.lo && km < a.hi) dmask |= 2u << (2 * pp);
@@ -874,7 +824,7 @@ static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaS
     a.tw = plan->d_tw;
     a.n_packets = n_packets;
     a.chunks_per_packet = (a.L + flush - 1) / flush;
-    const size_t smem = demod_cst_offset<P, NT>() + demod_cst_bytes<P, NT>() + (((size_t)flush * Nd + 15) & ~(size_t)15) + 16
+    const size_t smem = demod_stage_offset<P, NT>() + (((size_t)flush * Nd + 15) & ~(size_t)15) + 16
                         + (((size_t)flush * Nd + 15) / 16 + 1) * sizeof(uint32_t);
     auto kern = rx_demod_kernel<P, NT, MINB, KNOWN_CH, WANT_EQ, FUSE_EST>;
     GF3_REQUIRE(smem <= 227 * 1024, "rx_demod: %zu bytes of shared memory needed (> 227 KB)", smem);
