@@ -35,6 +35,8 @@ WORKLOADS = {
            "C3 (BASELINE.json configs[2]): 4096 streams x 1 packet, N=1024, CP=32, Nd=511, P=20, L=180, fit window [125:250), random 30-tap multipath + AWGN 20 dB"),
     "c4": (dict(N=4096, cp=704, lo=1, hi=2047, n_pilots=20, packet_len=180), 512,
            "C4 (BASELINE.json configs[3], mode B1): 512 streams x 1 packet, N=4096, CP=704, Nd=2046, P=20, L=180, random 30-tap multipath + AWGN 20 dB"),
+    "w2048": (dict(N=2048, cp=64, lo=1, hi=1024, n_pilots=20, packet_len=180, fit_lo=250, fit_hi=500), 2048,
+              "W2048 (parity-test geometry): 2048 streams x 1 packet, N=2048, CP=64, Nd=1023, P=20, L=180, random 30-tap multipath + AWGN 20 dB"),
     "a2": (dict(N=4096, cp=224, lo=100, hi=1500, n_pilots=20, packet_len=180), 512,
            "A2 (mode of the real recording): 512 streams x 1 packet, N=4096, CP=224, Nd=1400, P=20, L=180, random 30-tap multipath + AWGN 20 dB"),
 }

@@ -24,6 +24,9 @@ constexpr int kThreads = 256;
 #ifndef GF3_PREFETCH
 #define GF3_PREFETCH (-1)      // -1: per-plan default (see rx_demod_kernel)
 #endif
+#ifndef GF3_EST_U
+#define GF3_EST_U 20
+#endif
 #ifndef GF3_FLUSH_UNROLL
 #define GF3_FLUSH_UNROLL 2
 #endif
@@ -172,7 +175,7 @@ __device__ __noinline__ double estimate_packet(const float* pkt_base, int symlen
         const float* base1 = pkt_base + (int64_t)(Pn + Ln) * symlen + cp;
         const bool al16 = ((reinterpret_cast<uintptr_t>(base0) | reinterpret_cast<uintptr_t>(base1)) & 15) == 0 && (symlen % 4 == 0);
         if (al16) {
-            constexpr int U = 10;
+            constexpr int U = GF3_EST_U;
             for (int q = tid; q < PAR * (N / 4); q += NT) {
                 const int bl = q / (N / 4), c4 = q % (N / 4);
                 const float* s0 = ((b0 + bl) ? base1 : base0) + 4 * c4;
