@@ -469,9 +469,6 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
         }
 
         {
-            if ((nsym * Nd) & 15) {                   // last word of the chunk is partial: its missing codes are 0
-                if (tid < 16) stage[nsym * Nd + tid] = 0;
-            }
 #pragma unroll 1
             for (int b = 0; b < BATCHES; ++b) {
                 // ---------------- phase A: FFT of SF symbols
@@ -512,6 +509,7 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                 }
                 // ---------------- phase B: untangle, equalise, demap
                 // thread <-> PP bin pairs; walks the batch's symbols sb, sb+SB, ...
+                if (b == 0 && ((nsym * Nd) & 15) && tid < 16) stage[nsym * Nd + tid] = 0;   // a partial last word's missing codes are 0
                 {
                     const int ls0 = b * SF + sb;                               // first symbol (inside the chunk) of this thread
                     int n_it = (nsym - ls0 + SB - 1) / SB;                      // valid symbols for this thread in this batch
@@ -644,7 +642,8 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                     const int stride_words = (int)(a.bits_stride / 4) - (int)((int64_t)l0 * Nd / 16);
                     for (int w = nwords + tid; w < stride_words; w += NT) out[w] = 0u;
                 }
-                __syncthreads();
+                // no barrier here: the next chunk's loads and FFT do not touch the code staging area, and
+                // the barrier that ends its first FFT phase orders this flush's reads before new codes
             }
         }
     }
