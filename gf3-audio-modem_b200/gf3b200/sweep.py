@@ -51,7 +51,7 @@ def sweep(count_fn, n_streams, snrs_db, rank=0, world=1, dist=None, tensor_facto
 
 
 def make_gpu_count_fn(phy, pk_per_stream=1, seed=1234, use_sync=True):
-    """tx_modulate -> channel_sim -> xcorr/peak_pick -> rx_estimate -> rx_demod -> ber_count on the
+    """tx_modulate -> channel_sim -> xcorr/peak_pick -> rx_receive (estimate + data symbols) -> ber_count on the
     device, for an explicit list of stream ids."""
     import torch
     from . import synth
@@ -98,8 +98,7 @@ def make_gpu_count_fn(phy, pk_per_stream=1, seed=1234, use_sync=True):
             starts = torch.minimum(starts, torch.tensor(r.shape[1] - phy.pkt_samples, device=dev))
             fails = int((~ok).sum())
         off = (starts + (torch.arange(n, device=dev) * r.shape[1])[:, None]).reshape(-1).contiguous()
-        Hs, He, slope = phy.rx_estimate(r.reshape(-1), n * pk_per_stream, off)
-        out = phy.rx_demod(r.reshape(-1), n * pk_per_stream, Hs, He, slope, off, xor=False)
+        out = phy.rx_receive(r.reshape(-1), n * pk_per_stream, off, xor=False)[0]     # estimate + data symbols, one launch
         cntr = torch.zeros(2, dtype=torch.int64, device=dev)
         a = out[:, :nbytes].contiguous()
         b = bits.reshape(n * pk_per_stream, -1)[:, :nbytes].contiguous()
