@@ -47,6 +47,17 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
     for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
     const int g = tid / T, t = tid % T;
     const int64_t n_work = (a.n_streams * a.nblk + SF - 1) / SF;
+    // untangle items of this thread (item = tid + n*NT over SF*(M/2+1) pairs): block-in-CTA, bin and
+    // twiddle are the same for every work item, so they are computed once per CTA
+    constexpr int ITEMS = (SF * (M / 2 + 1) + NT - 1) / NT;
+    float2 uw[ITEMS];
+#pragma unroll
+    for (int n = 0; n < ITEMS; ++n) {
+        const int k = (tid + n * NT) % (M / 2 + 1);
+        float sn, cs;
+        sincospif(2.0f * (float)k / (float)N, &sn, &cs);
+        uw[n] = make_float2(-sn, -cs);
+    }
     // persistent: the twiddle table (~30 KB) is staged once per CTA, not once per pair of blocks
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
     const int64_t blk_global = work * SF + g;
@@ -88,16 +99,17 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
     fft_forward<P, NT>(x, zbuf + g * MP, tw, t, g);
     __syncthreads();
     // untangle: X[k] = (s + w2 d)/2, X[M-k] = conj(s - w2 d)/2
-    for (int item = tid; item < SF * (M / 2 + 1); item += NT) {
+#pragma unroll
+    for (int n = 0; n < ITEMS; ++n) {
+        const int item = tid + n * NT;
+        if (item >= SF * (M / 2 + 1)) break;
         const int gg = item / (M / 2 + 1), k = item % (M / 2 + 1), km = M - k;
         const int64_t bg = work * SF + gg;
         if (bg / a.nblk >= a.n_streams) continue;
         const float2* zs = zbuf + gg * MP;
         float2* out = a.spec + bg * M;
         const float2 z1 = zs[zpad<P>(k)], z2 = zs[zpad<P>(km == M ? 0 : km)];
-        float sn, cs;
-        sincospif(2.0f * (float)k / (float)N, &sn, &cs);
-        const float2 w2 = make_float2(-sn, -cs);
+        const float2 w2 = uw[n];
         const float2 s = make_float2(z1.x + z2.x, z1.y - z2.y);
         const float2 d = make_float2(z1.x - z2.x, z1.y + z2.y);
         const float2 tt = cmul(w2, d);
@@ -140,6 +152,13 @@ __global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
     __shared__ float wmax[NT / 32];
     const int tid = threadIdx.x;
     for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
+    float2 iw[PPT];                                    // e^{+j 2 pi k / N} of this thread's bin pairs, once per CTA
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        float sn, cs;
+        sincospif(2.0f * (float)(tid + q * NT) / (float)N, &sn, &cs);
+        iw[q] = make_float2(cs, sn);
+    }
     // persistent: the twiddle table is staged once per CTA; co-resident CTAs work on neighbouring
     // blocks, so the chirp-partition spectra and the shared input spectra stay hot in L2
     for (int64_t work = blockIdx.x; work < a.n_work; work += gridDim.x) {
@@ -183,11 +202,9 @@ __global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
         if (k >= PAIRS) continue;
         const int km = M - k;
         float2 Y1 = acc1[q], Y2 = (km == k) ? acc1[q] : acc2[q];      // k == 0: Y1 = (Y[0],0), Y2 = (Y[M],0)
-        float sn, cs;
-        sincospif(2.0f * (float)k / (float)N, &sn, &cs);
         const float2 E = make_float2(Y1.x + Y2.x, Y1.y - Y2.y);
         const float2 D = make_float2(Y1.x - Y2.x, Y1.y + Y2.y);
-        const float2 O = cmul(D, make_float2(cs, sn));
+        const float2 O = cmul(D, iw[q]);
         const float2 Zk = make_float2(E.x - O.y, E.y + O.x);
         const float2 Zm = make_float2(E.x + O.y, O.x - E.y);
         zbuf[zpad<P>(k == M ? 0 : k)] = cconj(Zk);
