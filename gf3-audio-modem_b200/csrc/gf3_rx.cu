@@ -1,13 +1,25 @@
-// gf3_rx.cu -- the receive chain of the GF3 modem as two fused sm_100a kernels.
+// gf3_rx.cu -- the receive chain of the GF3 modem as fused sm_100a kernels.
 //
 //   rx_estimate_kernel : known-symbol channel estimate          (OFDM.py:407-418,593,429-462)
 //   rx_demod_kernel    : CP strip + real FFT + one-tap equaliser + QPSK demap + XOR decode +
 //                        bit packing, every data sample read once (OFDM.py:407-418,593,466-478,
 //                        603,484-505,541-544); also the known-channel receiver of the
 //                        Weekend-Challenge notebook (Weekend Challenge.ipynb:162-226)
+//   rx_demod_kernel<.., FUSE_EST> : both in ONE launch (gf3_rx_receive): a persistent CTA estimates a
+//                        packet's channel when it first touches the packet (estimate_packet)
 //
-// HBM-bound streaming work: no tensor cores, grids sized in waves of the SM count, coalesced
-// 64/128-bit global access, FFT exchanges staged in shared memory.
+// Streaming work with no dense contraction: no tensor cores, persistent grids of one full wave,
+// coalesced 64/128-bit global access, FFT exchanges staged in shared memory, f32x2 (FADD2 / FMUL2 /
+// FFMA2) arithmetic in the butterflies and in the bin-pair phase.
+//
+// Compile-time knobs (experiments; the defaults are what profiles/ measured as fastest):
+//   GF3_PREFETCH       how the next FFT batch's samples are brought closer (see below)
+//   GF3_EST_U          pilot loads in flight per thread in the fused estimate
+//   GF3_PHASEB_UNROLL  symbols per unrolled step of the bin-pair phase
+//   GF3_FLUSH_UNROLL   packed words per unrolled step of the flush
+//   GF3_DEMOD_NATURAL  1: the last FFT pass leaves the spectrum unpadded (no mirrored-read conflicts)
+//   GF3_ABL            ablation mask for timing only (1: no bin-pair phase, 2: no FFT, 4: no global
+//                      loads, 8: no code stores); results are wrong with any bit set
 #include <stdlib.h>
 
 #include "gf3_common.cuh"
