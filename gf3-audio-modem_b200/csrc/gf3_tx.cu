@@ -11,7 +11,11 @@
 
 namespace gf3 {
 
-constexpr int kTxThreads = 256;
+#ifndef GF3_TX_THREADS
+#define GF3_TX_THREADS 128
+#endif
+constexpr int kTxThreads = GF3_TX_THREADS;       // one symbol group needs P::T <= 128 threads; small CTAs decorrelate the phases
+constexpr int kTxMinBlocks = 512 / GF3_TX_THREADS;
 
 struct TxArgs {
     const uint8_t* bits;        // [n_streams, pk_per_stream, bits_stride]   (null for the known symbol)
@@ -24,125 +28,160 @@ struct TxArgs {
     int cp, lo, hi, P, L, chirp_len;
     float gain;                 // tx_gain / N
     int batches_per_packet;     // ceil(L / SF)
+    int64_t n_work;             // n_streams * pk_per_stream * batches_per_packet (persistent grid walks them)
 };
 
-// QPSK point of the encoded bit pair of data carrier c in symbol l (OFDM.py:72-77):
-// (b0,b1) -> ((1-2 b1) + j (1-2 b0)) / sqrt(2)
-__device__ __forceinline__ float2 qpsk_from_bits(const uint8_t* __restrict__ sbits, int bitpos) {
-    const unsigned byte = sbits[bitpos >> 3];
-    const int sh = 6 - (bitpos & 7);                   // bitpos is even: b0 at 7-(g&7), b1 one below
-    const unsigned b0 = (byte >> (sh + 1)) & 1u, b1 = (byte >> sh) & 1u;
-    const float h = 0.70710678118654752440f;
-    return make_float2(b1 ? -h : h, b0 ? -h : h);
-}
-
-// One CTA = SF symbols of one packet.  Phase B' (thread <-> bin pair) builds conj(Z) in smem,
-// phase A' runs the FFT, the epilogue writes x[2m] = Re Y[m], x[2m+1] = -Im Y[m] (times gain)
-// plus the cyclic prefix.
+// Persistent CTAs; work item = one batch of SF consecutive symbols of one packet.  Phase B' (thread <->
+// bin pair (k, M-k), the same pairing as the receiver) builds conj(Z) in shared memory from the packed
+// bits, phase A' runs the FFT, the epilogue writes x[2m] = Re Y[m], x[2m+1] = -Im Y[m] (times gain)
+// plus the cyclic prefix.  Everything that depends only on the thread's bins (twiddle, bin class, bit
+// position inside a symbol) is computed once per CTA.
 template <class P, bool KNOWN_SYMBOL>
-__global__ void __launch_bounds__(kTxThreads, 2) tx_symbols_kernel(const TxArgs a) {
+__global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(const TxArgs a) {
     constexpr int NT = kTxThreads, T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP, K = M - 1;
     constexpr int SF = NT / T;
+    constexpr int TB = (M / 2 < NT) ? M / 2 : NT;     // threads per symbol in phase B'
+    constexpr int SB = NT / TB;                       // symbols handled concurrently in phase B'
+    constexpr int PP = (M / 2) / TB;                  // bin pairs per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* zbuf = reinterpret_cast<float2*>(smem_raw);
     float2* tw = zbuf + SF * MP;
-    uint8_t* sbits = reinterpret_cast<uint8_t*>(tw + P::TW_TOTAL);     // [SF][bytes_per_sym + 2]
+    uint8_t* sbits = reinterpret_cast<uint8_t*>(tw + P::TW_TOTAL);     // [SF][sym_bytes]
 
     const int tid = threadIdx.x;
     const int Nd = a.hi - a.lo;
     const int symlen = N + a.cp;
-    int64_t pktg = 0;           // global packet index (stream * pk_per_stream + packet)
-    int l_first = 0, nsym = 1;
-    if constexpr (!KNOWN_SYMBOL) {
-        pktg = blockIdx.x / a.batches_per_packet;
-        l_first = (blockIdx.x % a.batches_per_packet) * SF;
-        nsym = min(SF, a.L - l_first);
-    }
-    const int64_t stream = pktg / a.pk_per_stream, pk = pktg % a.pk_per_stream;
-
+    const int sym_bytes = ((2 * Nd + 7) / 8 + 1 + 3) & ~3;
     for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
 
-    // stage the packed bits of the nsym symbols (bit offset l*2Nd is not byte aligned in general)
-    const int sym_bytes = (2 * Nd + 7) / 8 + 1;
-    if constexpr (!KNOWN_SYMBOL) {
-        const uint8_t* pb = a.bits + pktg * a.bits_stride;
-        for (int i = tid; i < nsym * sym_bytes; i += NT) {
-            const int s = i / sym_bytes, o = i % sym_bytes;
-            const int64_t byte0 = ((int64_t)(l_first + s) * 2 * Nd) >> 3;
-            const int64_t idx = byte0 + o;
-            sbits[s * sym_bytes + o] = idx < a.bits_stride ? pb[idx] : 0;
-        }
-    }
-    __syncthreads();
-
-    // ---- phase B': Hermitian spectrum -> conj(Z[k]) for the packed inverse real FFT
-    //   E = X[k] + conj X[M-k],  O = (X[k] - conj X[M-k]) e^{+2 pi i k/N},  Z = E + jO
-    for (int item = tid; item < SF * (M / 2 + 1); item += NT) {
-        const int s = item / (M / 2 + 1), k = item % (M / 2 + 1), km = M - k;
-        float2 X1 = make_float2(0.f, 0.f), X2 = make_float2(0.f, 0.f);
-        if (s < nsym) {
-            auto bin = [&](int kk) -> float2 {
-                if (kk < 1 || kk > K) return make_float2(0.f, 0.f);              // DC and Nyquist stay 0 (OFDM.py:209)
-                if constexpr (KNOWN_SYMBOL) return a.known[kk - 1];
-                else {
-                    if (kk >= a.lo && kk < a.hi) {
-                        const int g = (int)((((int64_t)(l_first + s) * 2 * Nd) & 7) + 2 * (kk - a.lo));
-                        return qpsk_from_bits(sbits + s * sym_bytes, g);
-                    }
-                    // np.delete(carriers, data_carriers-1) keeps ascending order (OFDM.py:49,213)
-                    const int u = kk < a.lo ? kk - 1 : kk - 1 - Nd;
-                    return a.filler[stream * (K - Nd) + u];
-                }
-            };
-            X1 = bin(k);
-            X2 = bin(km);
-        }
-        float sn, cs;
-        sincospif(2.0f * (float)k / (float)N, &sn, &cs);                          // e^{+j theta}
-        const float2 E = make_float2(X1.x + X2.x, X1.y - X2.y);
-        const float2 D = make_float2(X1.x - X2.x, X1.y + X2.y);
-        const float2 O = cmul(D, make_float2(cs, sn));
-        // Z[k] = E + jO ;  Z[M-k] = conj(E) + j conj(O)... derived from the same pair:
-        const float2 Zk = make_float2(E.x - O.y, E.y + O.x);
-        const float2 Zm = make_float2(E.x + O.y, O.x - E.y);                       // conj(E - jO) = conj(E) + j conj(O)
-        float2* zs = zbuf + s * MP;
-        if (k < M) zs[zpad<P>(k)] = cconj(Zk);
-        if (k != 0 && km != k) zs[zpad<P>(km)] = cconj(Zm);
-        else if (k == 0) { /* Z[M] aliases Z[0]; nothing to store */ }
-    }
-    __syncthreads();
-
-    // ---- phase A': forward FFT of conj(Z)
-    {
-        const int g = tid / T, t = tid % T;
-        float2 x[R];
-        float2* zs = zbuf + g * MP;
+    // ---- per-thread constants of phase B': pairs k = jb + pp*TB (k = M/2 takes the slot of k = 0)
+    const int jb = tid % TB, sb = tid / TB;
+    float2 rot[PP];             // e^{+2 pi i k / N}
+    int src1[PP], src2[PP];     // bin k / M-k: >= 0 bit offset of the carrier's pair inside a symbol; -1 - u filler index; INT_MIN zero
+    constexpr int kZero = (int)0x80000000;
+    auto classify = [&](int kk) -> int {
+        if (kk < 1 || kk > K) return kZero;                               // DC and Nyquist stay 0 (OFDM.py:209)
+        if (KNOWN_SYMBOL) return -1 - (kk - 1);                           // "filler" = the known symbol itself
+        if (kk >= a.lo && kk < a.hi) return 2 * (kk - a.lo);
+        return -1 - (kk < a.lo ? kk - 1 : kk - 1 - Nd);                    // np.delete keeps ascending order (OFDM.py:49,213)
+    };
 #pragma unroll
-        for (int i = 0; i < R; ++i) x[i] = zs[zpad<P>(t + i * T)];
-        group_sync<P, NT>(g);
-        fft_forward<P, NT>(x, zs, tw, t, g);
+    for (int pp = 0; pp < PP; ++pp) {
+        const int j = jb + pp * TB;
+        const int k = j == 0 ? M / 2 : j, km = M - k;
+        float sn, cs;
+        sincospif(2.0f * (float)k / (float)N, &sn, &cs);
+        rot[pp] = make_float2(cs, sn);
+        src1[pp] = classify(k);
+        src2[pp] = classify(km);
     }
-    __syncthreads();
+    const float h = 0.70710678118654752440f;
+    const int g = tid / T, t = tid % T;
 
-    // ---- epilogue: time samples with cyclic prefix (OFDM.py:221-226), gain (OFDM.py:256)
-    for (int item = tid; item < nsym * M; item += NT) {
-        const int s = item / M, m = item % M;
-        const float2 y = zbuf[s * MP + zpad<P>(m)];
-        const float2 v = make_float2(y.x * a.gain, -y.y * a.gain);
-        float* o;
-        if constexpr (KNOWN_SYMBOL) o = a.out;
-        else o = a.out + stream * a.out_stride + pk * ((int64_t)a.chirp_len + (int64_t)(2 * a.P + a.L) * symlen)
-                 + a.chirp_len + (int64_t)(a.P + l_first + s) * symlen;
-        const int n0 = 2 * m - (N - a.cp);                       // position of this pair inside the cyclic prefix
-        if (((reinterpret_cast<uintptr_t>(o) | (uintptr_t)(a.cp * 4)) & 7) == 0) {       // 8-byte aligned symbol and even CP
-            *reinterpret_cast<float2*>(o + a.cp + 2 * m) = v;
-            if (n0 >= 0) *reinterpret_cast<float2*>(o + n0) = v;
-        } else {
-            o[a.cp + 2 * m] = v.x;
-            o[a.cp + 2 * m + 1] = v.y;
-            if (n0 >= 0) o[n0] = v.x;
-            if (n0 + 1 >= 0) o[n0 + 1] = v.y;
+    const int64_t n_work = KNOWN_SYMBOL ? 1 : a.n_work;
+#pragma unroll 1
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
+        int64_t pktg = 0;           // global packet index (stream * pk_per_stream + packet)
+        int l_first = 0, nsym = 1;
+        if constexpr (!KNOWN_SYMBOL) {
+            pktg = work / a.batches_per_packet;
+            l_first = (int)(work % a.batches_per_packet) * SF;
+            nsym = min(SF, a.L - l_first);
         }
+        const int64_t stream = pktg / a.pk_per_stream, pk = pktg % a.pk_per_stream;
+        const float2* fill = KNOWN_SYMBOL ? a.known : a.filler + stream * (K - Nd);
+
+        // stage the packed bits of the nsym symbols (bit offset l*2Nd is not byte aligned in general)
+        if constexpr (!KNOWN_SYMBOL) {
+            const uint8_t* pb = a.bits + pktg * a.bits_stride;
+            for (int i = tid; i < nsym * sym_bytes; i += NT) {
+                const int s = i / sym_bytes, o = i % sym_bytes;
+                const int64_t idx = (((int64_t)(l_first + s) * 2 * Nd) >> 3) + o;
+                sbits[i] = idx < a.bits_stride ? pb[idx] : 0;
+                (void)s;
+            }
+        }
+        __syncthreads();            // also: the previous work item's epilogue is done with zbuf
+
+        // ---- phase B': Hermitian spectrum -> conj(Z[k]) for the packed inverse real FFT
+        //   E = X[k] + conj X[M-k],  O = (X[k] - conj X[M-k]) e^{+2 pi i k/N},  Z = E + jO
+        for (int s = sb; s < SF; s += SB) {
+            float2* zs = zbuf + s * MP;
+            const int bit0 = (int)(((int64_t)(l_first + s) * 2 * Nd) & 7);
+            const uint8_t* sym = sbits + s * sym_bytes;
+            const bool live = s < nsym;
+            auto bin = [&](int src) -> float2 {
+                // data bin: QPSK of the encoded bit pair (OFDM.py:72-77), (b0,b1) -> ((1-2 b1) + j (1-2 b0)) / sqrt(2):
+                // the two bits (MSB first) are moved onto the sign bits of +1/sqrt(2)
+                const int bp = bit0 + (src > 0 ? src : 0);                 // even bit position inside the staged symbol
+                const unsigned w = (unsigned)sym[bp >> 3] << (24 + (bp & 7));   // bit 31 = b0, bit 30 = b1
+                float2 v = make_float2(__uint_as_float(0x3f3504f3u | ((w << 1) & 0x80000000u)),
+                                       __uint_as_float(0x3f3504f3u | (w & 0x80000000u)));
+                if (src < 0) v = (src == kZero) ? make_float2(0.f, 0.f) : fill[-1 - src];    // unused bin / filler (or known) symbol
+                if (!live) v = make_float2(0.f, 0.f);
+                return v;
+            };
+#pragma unroll
+            for (int pp = 0; pp < PP; ++pp) {
+                const int j = jb + pp * TB;
+                const int k = j == 0 ? M / 2 : j, km = M - k;
+                const float2 X1 = bin(src1[pp]), X2 = bin(src2[pp]);
+                const float2 E = make_float2(X1.x + X2.x, X1.y - X2.y);
+                const float2 D = make_float2(X1.x - X2.x, X1.y + X2.y);
+                const float2 O = cmul(D, rot[pp]);
+                // Z[k] = E + jO ;  Z[M-k] = conj(E) + j conj(O); conj(Z) is stored (ifft = conj fft conj)
+                zs[zpad<P>(k)] = make_float2(E.x - O.y, -(E.y + O.x));
+                if (j != 0) zs[zpad<P>(km)] = make_float2(E.x + O.y, E.y - O.x);
+                else zs[0] = make_float2(0.f, 0.f);                       // Z[0] packs DC and Nyquist: both 0
+            }
+        }
+        __syncthreads();
+
+        // ---- phase A': forward FFT of conj(Z)
+        {
+            float2 x[R];
+            float2* zs = zbuf + g * MP;
+#pragma unroll
+            for (int i = 0; i < R; ++i) x[i] = zs[zpad<P>(t + i * T)];
+            group_sync<P, NT>(g);
+            fft_forward<P, NT>(x, zs, tw, t, g);
+        }
+        __syncthreads();
+
+        // ---- epilogue: time samples with cyclic prefix (OFDM.py:221-226), gain (OFDM.py:256)
+        float* o0;
+        if constexpr (KNOWN_SYMBOL) o0 = a.out;
+        else o0 = a.out + stream * a.out_stride + pk * ((int64_t)a.chirp_len + (int64_t)(2 * a.P + a.L) * symlen)
+                  + a.chirp_len + (int64_t)(a.P + l_first) * symlen;
+        const bool al8 = ((reinterpret_cast<uintptr_t>(o0) | (uintptr_t)(a.cp * 4) | (uintptr_t)(symlen * 4)) & 7) == 0;
+        const int cp_first = (N - a.cp + 1) / 2;           // pairs m >= cp_first lie entirely inside the cyclic prefix's source
+        for (int s = g; s < nsym; s += SF) {               // every symbol group writes its own symbol
+            float* o = o0 + (int64_t)s * symlen;
+            const float2* zs = zbuf + s * MP;
+            if (al8) {                                     // 8-byte aligned symbol, even CP: two coalesced float2 streams
+                float2* body = reinterpret_cast<float2*>(o + a.cp);
+                float2* pre = reinterpret_cast<float2*>(o) - cp_first;      // pre[m] = o[2m - (N - cp)]
+#pragma unroll 8
+                for (int i = 0; i < R; ++i) {
+                    const int m = t + i * T;
+                    const float2 y = zs[zpad<P>(m)];
+                    const float2 v = make_float2(y.x * a.gain, -y.y * a.gain);
+                    body[m] = v;
+                    if (m >= cp_first) pre[m] = v;
+                }
+            } else {
+                for (int m = t; m < M; m += T) {
+                    const float2 y = zs[zpad<P>(m)];
+                    const float v0 = y.x * a.gain, v1 = -y.y * a.gain;
+                    const int n0 = 2 * m - (N - a.cp);                   // position of this pair inside the cyclic prefix
+                    o[a.cp + 2 * m] = v0;
+                    o[a.cp + 2 * m + 1] = v1;
+                    if (n0 >= 0) o[n0] = v0;
+                    if (n0 + 1 >= 0) o[n0 + 1] = v1;
+                }
+            }
+        }
+        // (the next work item's first barrier orders these zbuf reads before its phase B' writes)
     }
 }
 
@@ -152,29 +191,37 @@ struct FrameArgs {
     const float* known_time;    // [N + cp], gain applied
     float* out;
     int64_t out_stride, pk_per_stream, n_streams;
-    int symlen, P, L, chirp_len, gx;
+    int symlen, P, L, chirp_len;
 };
 
-// row = blockIdx.x / gx = stream * (pk_per_stream + 1) + packet; the extra "packet" is the trailing chirp
-// (OFDM.py:259).  Each row copies [chirp | P x known | (L data symbols skipped) | P x known].
+// One CTA copies one segment of one row: row = stream * (pk_per_stream + 1) + packet (the extra "packet"
+// is the trailing chirp, OFDM.py:259); segment 0 = the chirp, segments 1 .. 2P = the known symbols
+// before and after the L data symbols (which tx_symbols_kernel writes).  No per-sample index math.
 __global__ void __launch_bounds__(256) tx_frame_kernel(const FrameArgs a) {
-    const int rows_per_stream = (int)a.pk_per_stream + 1;
-    const int64_t row = blockIdx.x / a.gx;
-    const int bx = blockIdx.x % a.gx;
+    const unsigned row = blockIdx.x;                                     // grid = (rows, 2P + 1)
+    const int seg = blockIdx.y;
+    const unsigned rows_per_stream = (unsigned)a.pk_per_stream + 1u;
     const int64_t stream = row / rows_per_stream;
     const int pk = (int)(row % rows_per_stream);
+    if (pk == (int)a.pk_per_stream && seg != 0) return;                 // the trailing row is a chirp only
     const int64_t pkt_len = (int64_t)a.chirp_len + (int64_t)(2 * a.P + a.L) * a.symlen;
     float* o = a.out + stream * a.out_stride + (int64_t)pk * pkt_len;
-    const int seg = (pk == (int)a.pk_per_stream) ? a.chirp_len : a.chirp_len + 2 * a.P * a.symlen;
-    for (int i = bx * blockDim.x + threadIdx.x; i < seg; i += a.gx * blockDim.x) {
-        if (i < a.chirp_len) {
-            o[i] = a.chirp[i];
-        } else {
-            const int r = i - a.chirp_len;
-            const int sidx = r / a.symlen, n = r - sidx * a.symlen;     // sidx in [0, 2P)
-            const int slot = sidx < a.P ? sidx : sidx + a.L;
-            o[a.chirp_len + (int64_t)slot * a.symlen + n] = a.known_time[n];
-        }
+    const float* src;
+    int n;
+    if (seg == 0) { src = a.chirp; n = a.chirp_len; }
+    else {
+        const int sidx = seg - 1;                                       // 0 .. 2P-1
+        const int slot = sidx < a.P ? sidx : sidx + a.L;
+        o += a.chirp_len + (int64_t)slot * a.symlen;
+        src = a.known_time;
+        n = a.symlen;
+    }
+    if (((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) reinterpret_cast<float4*>(o)[i] = reinterpret_cast<const float4*>(src)[i];
+        for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) o[i] = src[i];
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = src[i];
     }
 }
 
@@ -203,7 +250,7 @@ static int launch_tx(const gf3_plan* plan, TxArgs a, const float* known, int64_t
     constexpr int SF = kTxThreads / P::T;
     const gf3_params& p = plan->p;
     const int Nd = p.hi - p.lo;
-    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)SF * ((2 * Nd + 7) / 8 + 1) + 16;
+    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)SF * ((((2 * Nd + 7) / 8 + 1) + 3) & ~3) + 16;
     // 1. the known symbol's time waveform (one symbol, gain applied) into scratch
     {
         TxArgs k = a;
@@ -216,10 +263,13 @@ static int launch_tx(const gf3_plan* plan, TxArgs a, const float* known, int64_t
     // 2. data symbols
     {
         a.batches_per_packet = (a.L + SF - 1) / SF;
-        const int64_t grid = n_streams * a.pk_per_stream * a.batches_per_packet;
-        GF3_REQUIRE(grid <= 0x7fffffff, "tx_modulate: grid too large");
+        a.n_work = n_streams * a.pk_per_stream * a.batches_per_packet;
         auto kern = tx_symbols_kernel<P, false>;
         GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        GF3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTxThreads, smem));
+        int64_t grid = (int64_t)plan->sm_count * (per_sm < 1 ? 1 : per_sm);         // persistent: one full wave
+        if (grid > a.n_work) grid = a.n_work;
         if (grid > 0) {
             kern<<<(unsigned)grid, kTxThreads, smem, st>>>(a);
             GF3_LAUNCH_CHECK();
@@ -231,13 +281,10 @@ static int launch_tx(const gf3_plan* plan, TxArgs a, const float* known, int64_t
         f.chirp = plan->d_chirp; f.known_time = known_time; f.out = a.out; f.out_stride = a.out_stride;
         f.pk_per_stream = a.pk_per_stream; f.n_streams = n_streams; f.symlen = p.N + p.cp; f.P = a.P; f.L = a.L;
         f.chirp_len = p.chirp_len;
-        const int seg = p.chirp_len + 2 * a.P * f.symlen;
-        int gx = (seg + 256 * 4 - 1) / (256 * 4);
-        if (gx < 1) gx = 1;
-        f.gx = gx;
         const int64_t rows = n_streams * (a.pk_per_stream + 1);
-        GF3_REQUIRE(rows * gx <= 0x7fffffff, "tx_modulate: too many packets in one call");
-        tx_frame_kernel<<<(unsigned)(rows * gx), 256, 0, st>>>(f);
+        const int64_t nseg = 2 * a.P + 1;
+        GF3_REQUIRE(rows <= 0x7fffffff && nseg <= 65535, "tx_modulate: too many packets in one call");
+        tx_frame_kernel<<<dim3((unsigned)rows, (unsigned)nseg), 256, 0, st>>>(f);
         GF3_LAUNCH_CHECK();
     }
     return GF3_OK;
@@ -251,7 +298,7 @@ static int launch_frame_known(const gf3_plan* plan, const float* known, const fl
     constexpr int SF = kTxThreads / P::T;
     const gf3_params& p = plan->p;
     const int Nd = p.hi - p.lo;
-    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)SF * ((2 * Nd + 7) / 8 + 1) + 16;
+    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)SF * ((((2 * Nd + 7) / 8 + 1) + 3) & ~3) + 16;
     TxArgs k;
     memset(&k, 0, sizeof(k));
     k.known = reinterpret_cast<const float2*>(known); k.tw = plan->d_tw; k.out = known_time;
@@ -266,13 +313,10 @@ static int launch_frame_known(const gf3_plan* plan, const float* known, const fl
     f.pk_per_stream = n_packets; f.n_streams = 1; f.symlen = p.N + p.cp; f.P = p.n_pilots; f.L = p.packet_len;
     f.chirp_len = sync_len;
     f.out_stride = 0;
-    const int seg = sync_len + 2 * f.P * f.symlen;
-    int gx = (seg + 256 * 4 - 1) / (256 * 4);
-    if (gx < 1) gx = 1;
-    f.gx = gx;
     const int64_t rows = n_packets + 1;
-    GF3_REQUIRE(rows * gx <= 0x7fffffff, "tx_frame: too many packets in one call");
-    tx_frame_kernel<<<(unsigned)(rows * gx), 256, 0, st>>>(f);
+    const int64_t nseg = 2 * f.P + 1;
+    GF3_REQUIRE(rows <= 0x7fffffff && nseg <= 65535, "tx_frame: too many packets in one call");
+    tx_frame_kernel<<<dim3((unsigned)rows, (unsigned)nseg), 256, 0, st>>>(f);
     GF3_LAUNCH_CHECK();
     return GF3_OK;
 }
