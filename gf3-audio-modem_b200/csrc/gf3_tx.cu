@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
     // ---- per-thread constants of phase B': pairs k = jb + pp*TB (k = M/2 takes the slot of k = 0)
     const int jb = tid % TB, sb = tid / TB;
     float2 rot[PP];             // e^{+2 pi i k / N}
+    int zo1[PP], zo2[PP];       // padded smem offsets of Z[k], Z[M-k]
     int src1[PP], src2[PP];     // bin k / M-k: >= 0 bit offset of the carrier's pair inside a symbol; -1 - u filler index; INT_MIN zero
     constexpr int kZero = (int)0x80000000;
     auto classify = [&](int kk) -> int {
@@ -74,6 +75,8 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
         rot[pp] = make_float2(cs, sn);
         src1[pp] = classify(k);
         src2[pp] = classify(km);
+        zo1[pp] = zpad<P>(k);
+        zo2[pp] = j != 0 ? zpad<P>(km) : 0;            // the k = M/2 slot also clears Z[0] (DC and Nyquist: both 0)
     }
     const float h = 0.70710678118654752440f;
     const int g = tid / T, t = tid % T;
@@ -105,11 +108,10 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
 
         // ---- phase B': Hermitian spectrum -> conj(Z[k]) for the packed inverse real FFT
         //   E = X[k] + conj X[M-k],  O = (X[k] - conj X[M-k]) e^{+2 pi i k/N},  Z = E + jO
-        for (int s = sb; s < SF; s += SB) {
-            float2* zs = zbuf + s * MP;
+        for (int s = sb; s < nsym; s += SB) {              // (symbols past the packet's end: their buffers hold stale
+            float2* zs = zbuf + s * MP;                    //  values, the FFT runs on them and nothing is written out)
             const int bit0 = (int)(((int64_t)(l_first + s) * 2 * Nd) & 7);
             const uint8_t* sym = sbits + s * sym_bytes;
-            const bool live = s < nsym;
             auto bin = [&](int src) -> float2 {
                 // data bin: QPSK of the encoded bit pair (OFDM.py:72-77), (b0,b1) -> ((1-2 b1) + j (1-2 b0)) / sqrt(2):
                 // the two bits (MSB first) are moved onto the sign bits of +1/sqrt(2)
@@ -118,21 +120,18 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
                 float2 v = make_float2(__uint_as_float(0x3f3504f3u | ((w << 1) & 0x80000000u)),
                                        __uint_as_float(0x3f3504f3u | (w & 0x80000000u)));
                 if (src < 0) v = (src == kZero) ? make_float2(0.f, 0.f) : fill[-1 - src];    // unused bin / filler (or known) symbol
-                if (!live) v = make_float2(0.f, 0.f);
                 return v;
             };
 #pragma unroll
             for (int pp = 0; pp < PP; ++pp) {
-                const int j = jb + pp * TB;
-                const int k = j == 0 ? M / 2 : j, km = M - k;
                 const float2 X1 = bin(src1[pp]), X2 = bin(src2[pp]);
                 const float2 E = make_float2(X1.x + X2.x, X1.y - X2.y);
                 const float2 D = make_float2(X1.x - X2.x, X1.y + X2.y);
                 const float2 O = cmul(D, rot[pp]);
                 // Z[k] = E + jO ;  Z[M-k] = conj(E) + j conj(O); conj(Z) is stored (ifft = conj fft conj)
-                zs[zpad<P>(k)] = make_float2(E.x - O.y, -(E.y + O.x));
-                if (j != 0) zs[zpad<P>(km)] = make_float2(E.x + O.y, E.y - O.x);
-                else zs[0] = make_float2(0.f, 0.f);                       // Z[0] packs DC and Nyquist: both 0
+                const bool self = (jb + pp * TB) == 0;                     // k = M/2 pairs with itself
+                zs[zo1[pp]] = make_float2(E.x - O.y, -(E.y + O.x));
+                zs[zo2[pp]] = self ? make_float2(0.f, 0.f) : make_float2(E.x + O.y, E.y - O.x);
             }
         }
         __syncthreads();
