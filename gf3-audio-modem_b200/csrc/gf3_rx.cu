@@ -79,12 +79,6 @@ __device__ __forceinline__ float2 ldg_stream2(const float* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
 }
-__device__ __forceinline__ float ldg_stream1(const float* p) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-
 // Load one symbol's N samples (CP already skipped by the caller) into the first-pass layout
 // x[i] = z[t + i*T],  z[m] = (s[2m], s[2m+1]).
 template <class P>
@@ -92,11 +86,12 @@ __device__ __forceinline__ void load_symbol(float2 (&x)[P::R], const float* __re
     if ((reinterpret_cast<uintptr_t>(s) & 7) == 0) {
 #pragma unroll
         for (int i = 0; i < P::R; ++i) x[i] = ldg_stream2(s + 2 * (t + i * P::T));
-    } else {   // odd sample offset (arbitrary sync index): two coalesced scalar loads
+    } else {   // odd sample offset (arbitrary sync index): two scalar loads per point.  Each touches every
+               // other float of the same sectors, so these loads DO allocate in L1: the second one hits
 #pragma unroll
         for (int i = 0; i < P::R; ++i) {
-            x[i].x = ldg_stream1(s + 2 * (t + i * P::T));
-            x[i].y = ldg_stream1(s + 2 * (t + i * P::T) + 1);
+            x[i].x = __ldg(s + 2 * (t + i * P::T));
+            x[i].y = __ldg(s + 2 * (t + i * P::T) + 1);
         }
     }
 }
@@ -217,7 +212,7 @@ __device__ __noinline__ double estimate_packet(const float* pkt_base, int symlen
                     const float* sp = s0 + (int64_t)p * symlen;
                     float2 v;
                     if (al) v = ldg_stream2(sp);
-                    else { v.x = ldg_stream1(sp); v.y = ldg_stream1(sp + 1); }
+                    else { v.x = __ldg(sp); v.y = __ldg(sp + 1); }      // L1-allocating: the two loads share sectors
                     acc.x += v.x;
                     acc.y += v.y;
                 }
@@ -736,7 +731,7 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
                     const float* s = s0 + (int64_t)p * symlen;
                     float2 v;
                     if (al) v = ldg_stream2(s);
-                    else { v.x = ldg_stream1(s); v.y = ldg_stream1(s + 1); }
+                    else { v.x = __ldg(s); v.y = __ldg(s + 1); }        // L1-allocating: the two loads share sectors
                     acc.x += v.x;
                     acc.y += v.y;
                 }
