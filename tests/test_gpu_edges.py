@@ -103,6 +103,28 @@ def test_receive_chain_edges_vs_oracle(case, known_sequence):
     if phy.bits_per_packet % 8:
         mask = (1 << (8 - phy.bits_per_packet % 8)) - 1
         assert bool(torch.all((gb.view[:, nb - 1] & mask) == 0))
+    # ---- the same chain as ONE launch (gf3_rx_receive), into fresh guarded buffers
+    fHs = Guarded(torch, npk * K * 8, torch.complex64, (npk, K))
+    fHe = Guarded(torch, npk * K * 8, torch.complex64, (npk, K))
+    fsl = Guarded(torch, npk * 8, torch.float64, (npk,))
+    fb = Guarded(torch, npk * phy.bits_stride, torch.uint8, (npk, phy.bits_stride))
+    feq = Guarded(torch, npk * L * K * 8, torch.complex64, (npk, L, K))
+    check(phy.lib.gf3_rx_receive(phy._plan, vp(d), vp(off), npk, vp(phy.known), vp(fHs.view), vp(fHe.view), vp(fsl.view),
+                                 vp(phy.xor2), vp(fb.view), phy.bits_stride, vp(feq.view), st))
+    torch.cuda.synchronize()
+    for g, name in ((fHs, "fused Hs"), (fHe, "fused He"), (fsl, "fused slope"), (fb, "fused bits"), (feq, "fused eq")):
+        g.check(name)
+    assert np.max(np.abs(fHs.view.cpu().numpy() - ref["Hs"])) / hs < 3e-6
+    assert np.max(np.abs(fHe.view.cpu().numpy() - ref["He"])) / hs < 3e-6
+    np.testing.assert_allclose(fsl.view.cpu().numpy(), ref["slope"], rtol=0, atol=5e-7)
+    relf = np.abs(feq.view.cpu().numpy().reshape(-1, K)[:, dc] - ref["eq"][:, dc]) / np.maximum(np.abs(ref["eq"][:, dc]), 1e-30)
+    assert relf.max() < 2e-4, relf.max()
+    gotf = phy.unpack_bits(fb.view)
+    for i in np.flatnonzero(gotf != ref["bits"]):
+        c = pts[i // 2]
+        comp = abs(c.imag) if i % 2 == 0 else abs(c.real)
+        assert comp / abs(c) < 1e-4, "fused: bit %d differs (margin %.3e)" % (i, comp / abs(c))
+    assert bool(torch.all(fb.view[:, nb:] == 0))
 
 
 def test_empty_batches_and_bad_arguments(known_sequence):
@@ -118,6 +140,16 @@ def test_empty_batches_and_bad_arguments(known_sequence):
     assert phy.lib.gf3_rx_demod(phy._plan, vp(d), None, 0, vp(d), vp(d), vp(d), None, vp(d), 16, None, None) == 0
     assert phy.lib.gf3_xcorr(phy._plan, vp(d), 8, 0, 8, vp(d), 2000, vp(d), vp(d), None) == 0
     assert phy.lib.gf3_tx_modulate(phy._plan, vp(d), phy.bits_stride, vp(d), vp(phy.known), 0, 1, vp(d), 10 ** 6, None) == 0
+    assert phy.lib.gf3_rx_receive(phy._plan, vp(d), None, 0, vp(phy.known), vp(d), vp(d), vp(d), None, vp(d), 16, None, None) == 0
+    assert phy.lib.gf3_eq_estimate(phy._plan, vp(d), vp(d), 0, vp(phy.known), vp(d), vp(d), vp(d), None) == 0
+    assert phy.lib.gf3_eq_apply(phy._plan, vp(d), 0, vp(d), vp(d), vp(d), vp(d), None, None) == 0
+    assert phy.lib.gf3_demap(vp(d), 0, vp(d), None, None) == 0
+    assert gf3b200.launch_count() == n0
+    assert phy.lib.gf3_rx_receive(phy._plan, vp(d), None, 1, None, vp(d), vp(d), vp(d), None, vp(d), 16, None, None) == _lib.GF3_ERR_INVALID
+    assert phy.lib.gf3_rx_receive(phy._plan, vp(d), None, 1, vp(phy.known), vp(d), vp(d), vp(d), None, vp(d), 6, None, None) == _lib.GF3_ERR_INVALID
+    assert phy.lib.gf3_eq_apply(phy._plan, None, 1, vp(d), vp(d), vp(d), vp(d), None, None) == _lib.GF3_ERR_INVALID
+    assert phy.lib.gf3_demap(None, 4, vp(d), None, None) == _lib.GF3_ERR_INVALID
+    assert phy.lib.gf3_tx_frame(phy._plan, vp(d), 1, None, 8, vp(phy.known), vp(d), None) == _lib.GF3_ERR_INVALID
     assert gf3b200.launch_count() == n0
     # bad arguments: error codes + message, no exception across the ABI, no launch
     assert phy.lib.gf3_rx_demod(phy._plan, vp(d), None, 1, vp(d), vp(d), vp(d), None, vp(d), 6, None, None) == _lib.GF3_ERR_INVALID
