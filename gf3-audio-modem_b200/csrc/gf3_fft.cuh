@@ -248,12 +248,21 @@ template <> struct Dft<64> {
 // ---------------------------------------------------------------- FFT plans
 // N real samples -> M = N/2 complex points; T threads per symbol, R points per thread,
 // Stockham passes with radices RAD(0)=R, RAD(1), [RAD(2)].
+#ifndef GF3_FFT_PAIRED
+#define GF3_FFT_PAIRED 1
+#endif
 template <int LOGN_, int R_, int NPASS_, int R0_, int R1_, int R2_>
 struct FftPlanT {
     static constexpr int LOGN = LOGN_, N = 1 << LOGN_, M = N / 2, R = R_, T = M / R_;
     static constexpr int NPASS = NPASS_;
     static constexpr int LOGPAD = (R_ == 64 ? 6 : R_ == 32 ? 5 : R_ == 16 ? 4 : 3);
-    static constexpr int MP = M + (M >> LOGPAD);   // padded complex points per symbol
+    // PAIRED (N = 1024: two passes, two sub-transforms per thread in the second): the second pass takes the
+    // ADJACENT columns j = 2t, 2t+1 of the T x R0 intermediate matrix, so every shared-memory access of
+    // the exchange is 128 bits wide (row stride R0 + 2 keeps 16-byte alignment and quarter-warp
+    // conflict freedom): half the LDS / STS instructions of the FFT.
+    static constexpr bool PAIRED = GF3_FFT_PAIRED && (LOGN_ == 10);
+    static constexpr int ROWP = R0_ + 2;             // PAIRED: padded row of the intermediate matrix
+    static constexpr int MP = PAIRED ? T * ROWP : M + (M >> LOGPAD);   // complex points reserved per symbol
     __host__ __device__ static constexpr int rad(int p) { return p == 0 ? R0_ : p == 1 ? R1_ : R2_; }
     __host__ __device__ static constexpr int ns(int p) { return p == 0 ? 1 : p == 1 ? R0_ : R0_ * R1_; }
     // twiddle table: pass p >= 1 holds Q*(rad-1)*T entries at offset tw_off(p)
@@ -314,6 +323,16 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
     static_assert(NS != 1 || RAD == (1 << P::LOGPAD), "first pass radix must equal the padding period");
     static_assert(!NATURAL || PASS == P::NPASS - 1, "natural-order output is for the last pass");
     if constexpr (PASS > 0) {
+        if constexpr (P::PAIRED) {
+            static_assert(Q == 2 && P::NPASS == 2, "paired layout: two passes, two sub-transforms in the second");
+            const float4* src = reinterpret_cast<const float4*>(zs + 2 * t);
+            static_for<RAD>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                const float4 v = src[i * (P::ROWP / 2)];                 // row i, columns 2t and 2t+1
+                x[i] = make_float2(v.x, v.y);
+                x[RAD + i] = make_float2(v.z, v.w);
+            });
+        } else {
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             const float2* src = zs + zpad<P>(t + q * P::T);
@@ -322,6 +341,7 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
                 x[q * RAD + i] = src[i * zstride<P, STRIDE>()];
             });
         });
+        }
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             const float2* twp = tw + P::tw_off(PASS) + t + q * ((RAD - 1) * P::T);
@@ -336,9 +356,24 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
         constexpr int q = decltype(qc)::value;
         Dft<RAD>::run(&x[q * RAD]);
     });
+    if constexpr (P::PAIRED && PASS == 0) {
+        // row t of the T x R0 matrix, two columns per 128-bit store
+        float4* dst = reinterpret_cast<float4*>(zs + t * P::ROWP);
+        static_for<RAD / 2>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            dst[m] = make_float4(x[2 * m].x, x[2 * m].y, x[2 * m + 1].x, x[2 * m + 1].y);
+        });
+    } else if constexpr (P::PAIRED && NATURAL) {
+        // bins k = 2t + NS*i and k + 1 (the two sub-transforms of this thread) are neighbours
+        float4* dst = reinterpret_cast<float4*>(zs + 2 * t);
+        static_for<RAD>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            dst[i * (NS / 2)] = make_float4(x[i].x, x[i].y, x[RAD + i].x, x[RAD + i].y);
+        });
+    } else
     static_for<Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
-        const int j = t + q * P::T;
+        const int j = P::PAIRED ? 2 * t + q : t + q * P::T;
         const int base = (j / NS) * (NS * RAD) + (j % NS);
         if constexpr (NATURAL) {
             float2* dst = zs + base;
@@ -381,7 +416,7 @@ inline void fill_twiddles(float2* out) {
         for (int q = 0; q < Q; ++q)
             for (int i = 1; i < RAD; ++i)
                 for (int t = 0; t < P::T; ++t) {
-                    const int j = t + q * P::T;
+                    const int j = P::PAIRED ? 2 * t + q : t + q * P::T;
                     const double ang = -2.0 * 3.14159265358979323846 * (double)((j % NS) * i) / (double)(NS * RAD);
                     o[(q * (RAD - 1) + (i - 1)) * P::T + t] = make_float2((float)cos(ang), (float)sin(ang));
                 }
