@@ -342,6 +342,16 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
             });
         });
         }
+        if constexpr (P::PAIRED) {
+            // the twiddles of the two adjacent columns sit side by side: one 128-bit load for both
+            const float4* twp = reinterpret_cast<const float4*>(tw + P::tw_off(PASS) + 2 * t);
+            static_for<RAD - 1>([&](auto ic) {
+                constexpr int i = decltype(ic)::value + 1;
+                const float4 w = twp[(i - 1) * P::T];
+                x[i] = cmul(x[i], make_float2(w.x, w.y));
+                x[RAD + i] = cmul(x[RAD + i], make_float2(w.z, w.w));
+            });
+        } else {
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             const float2* twp = tw + P::tw_off(PASS) + t + q * ((RAD - 1) * P::T);
@@ -350,6 +360,7 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
                 x[q * RAD + i] = cmul(x[q * RAD + i], twp[(i - 1) * P::T]);
             });
         });
+        }
         group_sync<P, NTHREADS>(grp);   // every thread of the symbol has read before anyone overwrites
     }
     static_for<Q>([&](auto qc) {
@@ -418,7 +429,8 @@ inline void fill_twiddles(float2* out) {
                 for (int t = 0; t < P::T; ++t) {
                     const int j = P::PAIRED ? 2 * t + q : t + q * P::T;
                     const double ang = -2.0 * 3.14159265358979323846 * (double)((j % NS) * i) / (double)(NS * RAD);
-                    o[(q * (RAD - 1) + (i - 1)) * P::T + t] = make_float2((float)cos(ang), (float)sin(ang));
+                    const int idx = P::PAIRED ? (i - 1) * 2 * P::T + 2 * t + q : (q * (RAD - 1) + (i - 1)) * P::T + t;
+                    o[idx] = make_float2((float)cos(ang), (float)sin(ang));
                 }
     }
 }
