@@ -522,7 +522,8 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                     int n_it = (nsym - ls0 + SB - 1) / SB;                      // valid symbols for this thread in this batch
                     n_it = n_it < 0 ? 0 : (n_it > SF / SB ? SF / SB : n_it);
                     auto phase_b = [&](auto fastc, auto bitsc) {
-                        constexpr bool FAST = decltype(fastc)::value, BITS = decltype(bitsc)::value;
+                        [[maybe_unused]] constexpr bool FAST = decltype(fastc)::value;
+                        constexpr bool BITS = decltype(bitsc)::value;
                         const float2 *zp1[PP], *zp2[PP];
                         unsigned sp1[PP], sp2[PP];                              // shared-memory byte addresses of the code slots
                         bool e2[PP];                                            // bin M-k exists (k != M/2)
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                             if (e2[pp] && km >= a.lo && km < a.hi) dmask |= 2u << (2 * pp);
                         }
                         asm volatile("" : "+r"(dmask));             // keep the mask in a register: no re-derivation per store
-                        float2* eqp = nullptr;
+                        [[maybe_unused]] float2* eqp = nullptr;
                         if constexpr (WANT_EQ) eqp = a.eq + ((int64_t)pkt * L + l0 + ls0) * K - 1;
                         const int st_step = SB * Nd;
                         int soff = 0;

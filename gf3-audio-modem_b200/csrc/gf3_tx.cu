@@ -78,7 +78,6 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
         zo1[pp] = zpad<P>(k);
         zo2[pp] = j != 0 ? zpad<P>(km) : 0;            // the k = M/2 slot also clears Z[0] (DC and Nyquist: both 0)
     }
-    const float h = 0.70710678118654752440f;
     const int g = tid / T, t = tid % T;
 
     const int64_t n_work = KNOWN_SYMBOL ? 1 : a.n_work;
