@@ -41,37 +41,63 @@ struct ChanArgs {
     int n_taps;
 };
 
-// grid.y = stream; each thread produces 4 consecutive samples.
+// grid.y = stream; a CTA walks tiles of 1024 consecutive outputs; each thread produces 4 of them.
+// The tile's input window (tile + n_taps - 1 samples of history, zero outside [0, T)) is staged in
+// shared memory; a thread slides an 8-sample register window over it four taps at a time, so every
+// multiply-add takes its operands from registers (128-bit conflict-free shared-memory reads only).
+// Summation order (k ascending, one fused multiply-add per tap) and the Philox counter per group of
+// four samples are those of the straightforward loop, so results do not depend on the tiling.
 __global__ void __launch_bounds__(256) channel_sim_kernel(const ChanArgs a) {
-    __shared__ float h[kMaxTaps];
+    constexpr int NT = 256, TILE = NT * 4, HIST = kMaxTaps;              // HIST: multiple of 4, >= n_taps - 1
+    __shared__ __align__(16) float h[kMaxTaps];
+    __shared__ __align__(16) float xs[HIST + TILE];
+    const int tid = threadIdx.x;
     const int64_t stream = blockIdx.y;
-    if (threadIdx.x < a.n_taps) h[threadIdx.x] = a.taps[stream * a.n_taps + threadIdx.x];
-    __syncthreads();
+    if (tid < kMaxTaps) h[tid] = tid < a.n_taps ? a.taps[stream * a.n_taps + tid] : 0.f;
     const float* x = a.x + stream * a.x_stride;
     float* y = a.y + stream * a.y_stride;
     const float sg = a.sigma ? a.sigma[stream] : 0.f;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < a.T; q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t n0 = q * 4;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        // window x[n0 - n_taps + 1 .. n0 + 3]
-        for (int k = 0; k < a.n_taps; ++k) {
-            const float hk = h[k];
+    const int nblk = (a.n_taps + 3) >> 2;                                // tap blocks of four
+    const bool y_al16 = ((reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    for (int64_t tile0 = (int64_t)blockIdx.x * TILE; tile0 < a.T; tile0 += (int64_t)gridDim.x * TILE) {
+        __syncthreads();                                                  // previous tile fully consumed (and h written)
+        for (int i = tid; i < HIST + TILE; i += NT) {
+            const int64_t n = tile0 - HIST + i;
+            xs[i] = (n >= 0 && n < a.T) ? x[n] : 0.f;
+        }
+        __syncthreads();
+        const int64_t n0 = tile0 + 4 * tid;
+        if (n0 < a.T) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            // taps k = 4 kb + kk use samples n0 + e - k = (n0 - 4 kb) + (e - kk): the window w[0..7] = xs at
+            // (4 tid + HIST - 4 kb) - 4 .. + 3 covers e - kk in [-3, 3]
+            const float4* xw = reinterpret_cast<const float4*>(xs) + tid + HIST / 4;
+            const float4* hw = reinterpret_cast<const float4*>(h);
+            for (int kb = 0; kb < nblk; ++kb) {
+                const float4 lo = xw[-kb - 1], hi = xw[-kb], hk = hw[kb];
+                const float w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                const float hv[4] = {hk.x, hk.y, hk.z, hk.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int64_t i = n0 + e - k;
-                if (i >= 0 && i < a.T) acc[e] = fmaf(hk, x[i], acc[e]);
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[e] = fmaf(hv[kk], w[4 + e - kk], acc[e]);
+            }
+            if (sg != 0.f) {
+                const int64_t q = n0 >> 2;
+                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)),
+                                                make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                const float2 g0 = box_muller(rnd.x, rnd.y), g1 = box_muller(rnd.z, rnd.w);
+                acc[0] = fmaf(sg, g0.x, acc[0]); acc[1] = fmaf(sg, g0.y, acc[1]);
+                acc[2] = fmaf(sg, g1.x, acc[2]); acc[3] = fmaf(sg, g1.y, acc[3]);
+            }
+            if (y_al16 && (a.y_stride & 3) == 0 && n0 + 3 < a.T) {
+                *reinterpret_cast<float4*>(y + n0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (n0 + e < a.T) y[n0 + e] = acc[e];
             }
         }
-        if (sg != 0.f) {
-            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)),
-                                            make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-            const float2 g0 = box_muller(rnd.x, rnd.y), g1 = box_muller(rnd.z, rnd.w);
-            acc[0] = fmaf(sg, g0.x, acc[0]); acc[1] = fmaf(sg, g0.y, acc[1]);
-            acc[2] = fmaf(sg, g1.x, acc[2]); acc[3] = fmaf(sg, g1.y, acc[3]);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (n0 + e < a.T) y[n0 + e] = acc[e];
     }
 }
 
@@ -142,8 +168,9 @@ extern "C" int gf3_channel_sim(const float* x, int64_t x_stride, int64_t n_strea
     ChanArgs a;
     a.x = x; a.taps = taps; a.sigma = sigma; a.y = y; a.x_stride = x_stride; a.y_stride = y_stride; a.T = T;
     a.seed = seed; a.n_taps = n_taps;
-    int64_t gx = (T / 4 + 255) / 256;
-    if (gx > 4096) gx = 4096;
+    int64_t gx = (T + 1023) / 1024;                  // tiles of 1024 outputs per stream
+    const int64_t cap = (148LL * 8 * 4 + n_streams - 1) / n_streams;      // a few waves in total
+    if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     channel_sim_kernel<<<dim3((unsigned)gx, (unsigned)n_streams), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     GF3_LAUNCH_CHECK();
