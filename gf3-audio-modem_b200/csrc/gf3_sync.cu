@@ -249,13 +249,82 @@ __global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
 struct PeakArgs {
     const float* P;
     const float* pmax;
+    uint32_t* mask;              // [n_streams, nw] candidate bits (work buffer)
     int64_t* peaks;
     int32_t* count;
     int64_t p_stride, plen;      // plen = T + Lc - 1
+    int64_t n_streams, nw;       // nw = 32-bit words per stream = ceil((plen - 2) / 32)
     int32_t max_peaks, Lc;
     float thresh;
 };
 
+// Phase 1, fully parallel: one candidate bit per position of `zeros` (OFDM.py:360-361).  A CTA takes
+// chunks of 64 mask words (2048 positions) of one stream; each warp evaluates 32 consecutive positions
+// per step with coalesced loads and stores one word of the bit mask.
+__global__ void __launch_bounds__(256) peak_mark_kernel(const PeakArgs a) {
+    constexpr int WPC = 64;                                        // mask words per chunk
+    const int64_t nz = a.plen - 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t cps = (a.nw + WPC - 1) / WPC;                    // chunks per stream
+    const int64_t n_chunks = a.n_streams * cps;
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const int64_t stream = c / cps, w0 = (c - stream * cps) * WPC + warp * (WPC / 8);
+        const float* Prow = a.P + stream * a.p_stride;
+        uint32_t* mrow = a.mask + stream * a.nw;
+        const float inv = 1.0f / a.pmax[stream];
+#pragma unroll
+        for (int j = 0; j < WPC / 8; ++j) {
+            const int64_t w = w0 + j;
+            if (w >= a.nw) break;
+            const int64_t i = w * 32 + lane;
+            bool cand = false;
+            if (i < nz) {
+                const float prev = Prow[i] * inv, cur = Prow[i + 1] * inv, nxt = Prow[i + 2] * inv;
+                const float d0 = cur - prev, d1 = nxt - cur;
+                cand = d0 * d1 <= 0.f && cur > a.thresh;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, cand);
+            if (lane == 0) mrow[w] = m;
+        }
+    }
+}
+
+// Phase 2, one CTA per stream: ascending walk over the candidate bits with the hold-off of one chirp
+// length (OFDM.py:364-366) and the end-of-signal wipe-out (OFDM.py:366-370).  The walk reads 8192
+// positions per step and jumps over every hold-off window.
+__global__ void __launch_bounds__(256) peak_scan_kernel(const PeakArgs a) {
+    constexpr int NT = 256;
+    __shared__ long long s_first;
+    const int tid = threadIdx.x;
+    const int64_t stream = blockIdx.x;
+    const uint32_t* mrow = a.mask + stream * a.nw;
+    const int64_t nz = a.plen - 2;
+    int32_t found = 0;
+    bool wiped = false;
+    int64_t pos = 0;
+    while (pos < nz) {
+        if (tid == 0) s_first = 0x7fffffffffffffffLL;
+        __syncthreads();
+        const int64_t w0 = pos >> 5, w = w0 + tid;
+        if (w < a.nw) {
+            uint32_t m = mrow[w];
+            if (w == w0) m &= 0xffffffffu << (pos & 31);          // positions before pos are behind us
+            if (m) atomicMin(&s_first, (long long)(w * 32 + __ffs(m) - 1));
+        }
+        __syncthreads();
+        const long long first = s_first;
+        __syncthreads();
+        if (first == 0x7fffffffffffffffLL) { pos = (w0 + NT) * 32; continue; }
+        if (first + a.Lc >= nz) { wiped = true; break; }
+        if (tid == 0 && found < a.max_peaks) a.peaks[stream * a.max_peaks + found] = first;
+        ++found;
+        pos = first + a.Lc + 1;
+    }
+    if (tid == 0) a.count[stream] = wiped ? 0 : found;
+}
+
+// Single-kernel variant, one CTA per stream walking 2048-position tiles: with hundreds of streams in a
+// batch the streams themselves supply the parallelism, and one pass over P is cheaper than mark + scan.
 __global__ void __launch_bounds__(256) peak_pick_kernel(const PeakArgs a) {
     constexpr int NT = 256, PER = 8, TILE = NT * PER;
     __shared__ long long s_first;
@@ -393,17 +462,39 @@ extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride,
     return GF3_OK;
 }
 
+extern "C" size_t gf3_peak_pick_work_bytes(const gf3_plan* plan, int64_t n_streams, int64_t T) {
+    if (!plan || n_streams <= 0 || T <= 0) return 0;
+    const int64_t nz = T + plan->p.chirp_len - 3;
+    return (size_t)n_streams * (size_t)((nz + 31) / 32) * sizeof(uint32_t);
+}
+
 extern "C" int gf3_peak_pick(const gf3_plan* plan, const float* P, int64_t p_stride, int64_t n_streams,
                              int64_t T, const float* pmax, int64_t* peaks, int32_t max_peaks, int32_t* count,
-                             void* stream) {
+                             void* work, void* stream) {
     GF3_REQUIRE(plan && P && pmax && peaks && count, "peak_pick: null argument");
     GF3_REQUIRE(max_peaks >= 1 && n_streams >= 0 && n_streams <= 0x7fffffff, "peak_pick: bad sizes");
     if (n_streams == 0) return GF3_OK;
+    GF3_REQUIRE(work != nullptr, "peak_pick: null work buffer (gf3_peak_pick_work_bytes)");
     PeakArgs a;
     a.P = P; a.pmax = pmax; a.peaks = peaks; a.count = count; a.p_stride = p_stride;
     a.plen = T + plan->p.chirp_len - 1; a.max_peaks = max_peaks; a.Lc = plan->p.chirp_len; a.thresh = plan->p.thresh;
     GF3_REQUIRE(a.plen >= 3, "peak_pick: signal too short");
-    peak_pick_kernel<<<(unsigned)n_streams, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    a.mask = reinterpret_cast<uint32_t*>(work);
+    a.n_streams = n_streams;
+    a.nw = (a.plen - 2 + 31) / 32;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int64_t blocks = a.n_streams * ((a.nw + 63) / 64);               // chunks of 64 mask words
+    const int64_t cap = (int64_t)plan->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (n_streams >= 2 * (int64_t)plan->sm_count) {                  // enough streams to fill the GPU: one pass, one CTA each
+        peak_pick_kernel<<<(unsigned)n_streams, 256, 0, st>>>(a);
+        GF3_LAUNCH_CHECK();
+        return GF3_OK;
+    }
+    peak_mark_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    GF3_LAUNCH_CHECK();
+    peak_scan_kernel<<<(unsigned)n_streams, 256, 0, st>>>(a);
     GF3_LAUNCH_CHECK();
     return GF3_OK;
 }

@@ -50,7 +50,8 @@ SIGNATURES = {
     "gf3_sync_chirp": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gf3_xcorr_work_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
     "gf3_xcorr": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "gf3_peak_pick": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "gf3_peak_pick_work_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
+    "gf3_peak_pick": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "gf3_tx_modulate": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "gf3_eq_estimate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gf3_eq_apply": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

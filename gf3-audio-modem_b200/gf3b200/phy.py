@@ -182,8 +182,9 @@ class Phy:
         B = P.shape[0]
         peaks = torch.full((B, max_peaks), -1, dtype=torch.int64, device=self.device)
         count = torch.empty((B,), dtype=torch.int32, device=self.device)
+        work = torch.empty((max(1, int(self.lib.gf3_peak_pick_work_bytes(self._plan, B, T))),), dtype=torch.uint8, device=self.device)
         check(self.lib.gf3_peak_pick(self._plan, _ptr(P), P.stride(0), B, T, _ptr(pmax), _ptr(peaks), max_peaks,
-                                     _ptr(count), _stream()))
+                                     _ptr(count), _ptr(work), _stream()))
         return peaks, count
 
     # ------------------------------------------------------------------ transmit chain

@@ -153,10 +153,12 @@ GF3_API int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride, in
  * candidate mask (D[i]*D[i+1] <= 0) & (P[i+1] > thresh), ascending hold-off of chirp_len,
  * including the end-of-signal wipe-out quirk (OFDM.py:366-370).
  *   peaks [n_streams, max_peaks] int64: indices into the reference's `zeros` array
- *   count [n_streams] int32: detections found (may exceed max_peaks; only max_peaks stored) */
+ *   count [n_streams] int32: detections found (may exceed max_peaks; only max_peaks stored)
+ *   work: device scratch of gf3_peak_pick_work_bytes() bytes (one candidate bit per position) */
+GF3_API size_t gf3_peak_pick_work_bytes(const gf3_plan* plan, int64_t n_streams, int64_t T);
 GF3_API int gf3_peak_pick(const gf3_plan* plan, const float* P, int64_t p_stride, int64_t n_streams,
                   int64_t T, const float* pmax, int64_t* peaks, int32_t max_peaks, int32_t* count,
-                  void* stream);
+                  void* work, void* stream);
 
 /* ---- transmit chain ---------------------------------------------- */
 /* map + build_OFDM_symbol + ifft + add_cp + send_to_stream fused (OFDM.py:191-226, 244-259,

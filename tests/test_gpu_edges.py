@@ -191,9 +191,10 @@ def test_tx_sync_outputs_guarded(known_sequence):
     check(phy.lib.gf3_xcorr(phy._plan, vp(r), T, B, T, vp(gP.view), plen, vp(gm.view), vp(work), None))
     gk = Guarded(torch, B * 2 * 8, torch.int64, (B, 2))          # fewer slots than detections (3 per stream)
     gc = Guarded(torch, B * 4, torch.int32, (B,))
-    check(phy.lib.gf3_peak_pick(phy._plan, vp(gP.view), plen, B, T, vp(gm.view), vp(gk.view), 2, vp(gc.view), None))
+    gw = Guarded(torch, int(phy.lib.gf3_peak_pick_work_bytes(phy._plan, B, T)), torch.uint8, (-1,))
+    check(phy.lib.gf3_peak_pick(phy._plan, vp(gP.view), plen, B, T, vp(gm.view), vp(gk.view), 2, vp(gc.view), vp(gw.view), None))
     torch.cuda.synchronize()
-    for gg, name in ((gP, "P"), (gm, "pmax"), (gk, "peaks"), (gc, "count")):
+    for gg, name in ((gP, "P"), (gm, "pmax"), (gk, "peaks"), (gc, "count"), (gw, "peak_pick work")):
         gg.check(name)
     # the final chirp ends exactly at the end of r: the reference's wipe-out quirk gives 0 detections
     assert gc.view.cpu().tolist() == [0, 0, 0]
