@@ -1,4 +1,8 @@
-import sys; sys.path.insert(0,"gf3-audio-modem_b200")
+#!/usr/bin/env python
+"""Matched-filter (gf3_xcorr) throughput for the two chirp lengths that matter: 21 600 samples (N = 4096
+modes, 11 partitions of 2048) and 5 280 samples (the C3 geometry, 3 partitions).
+usage (from the repo root): python tools/bench_xcorr.py"""
+import os, sys; sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gf3-audio-modem_b200"))
 import torch, gf3b200
 for cfg,B,T in ((dict(N=4096,cp=224,lo=100,hi=1500),64,993600+21600),(dict(N=1024,cp=32,lo=1,hi=512),1024,242984)):
     phy=gf3b200.Phy(**cfg)

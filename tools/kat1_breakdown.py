@@ -1,7 +1,11 @@
+#!/usr/bin/env python
+"""Per-stage times of one receive of the real recording (gr5ch1_signal.wav, mode A2) through the Phy
+calls the drop-in makes; run under `ncu --metrics gpu__time_duration.sum` for the kernel times.
+usage (from the repo root): python tools/kat1_breakdown.py"""
 import os, sys, time
-sys.path.insert(0, "gf3-audio-modem_b200")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gf3-audio-modem_b200"))
 import numpy as np, torch, gf3b200
-g = np.load("tests/golden/kat1_gr5ch1.npz")
+g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "kat1_gr5ch1.npz"))
 r8 = g["wav_u8"]
 phy = gf3b200.Phy(N=4096, cp=224, lo=100, hi=1500)
 def ev(): return torch.cuda.Event(enable_timing=True)
