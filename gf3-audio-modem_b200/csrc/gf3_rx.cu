@@ -43,7 +43,7 @@ constexpr int kThreads = 256;
 #define GF3_FLUSH_UNROLL 2
 #endif
 #ifndef GF3_PHASEB_UNROLL
-#define GF3_PHASEB_UNROLL 4
+#define GF3_PHASEB_UNROLL 8
 #endif
 #ifndef GF3_DEMOD_NATURAL
 #define GF3_DEMOD_NATURAL 1
