@@ -204,3 +204,39 @@ def test_tx_sync_outputs_guarded(known_sequence):
     peaks, cnt = phy.peak_pick(P2, m2, T + 4, 2)
     assert cnt.cpu().tolist() == [pk + 1] * B                    # count reports all, only max_peaks stored
     assert peaks[:, 0].cpu().tolist() == [phy.chirp_len - 2] * B
+
+
+def test_receive_chain_replays_from_a_cuda_graph(known_sequence):
+    """The whole receive chain is one asynchronous launch on the caller's stream with no host
+    synchronisation inside the library: it can be captured once and replayed from a CUDA graph."""
+    torch = _torch()
+    import gf3b200
+    from gf3b200 import synth
+    phy = gf3b200.Phy(N=1024, cp=32, lo=1, hi=512, n_pilots=4, packet_len=24, known_sequence=known_sequence,
+                      fit_lo=125, fit_hi=250)
+    b = synth.make_batch(phy, 96, 1, snr_db=15.0, seed=21)
+    sym = synth.packets_from_streams(phy, b).contiguous()
+    n = sym.shape[0]
+    flat = sym.reshape(-1)
+    eager, Hs0, He0, sl0 = phy.rx_receive(flat, n, xor=True)
+    torch.cuda.synchronize()
+    out = torch.zeros_like(eager)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        phy.rx_receive(flat, n, xor=True, out=out)                      # warm-up on the capture stream
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            _, Hs, He, sl = phy.rx_receive(flat, n, xor=True, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    out.zero_()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager) and torch.equal(Hs, Hs0) and torch.equal(sl, sl0)
+    # new samples in the same buffer: the replay sees them
+    flat.mul_(-1.0)
+    neg, _, _, _ = phy.rx_receive(flat, n, xor=True)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, neg)
