@@ -104,9 +104,12 @@ class _RngShim:
         return self.g.choice(a, size=size, replace=replace)
 
 
-def _cpu_worker(args):
-    p, rx = args
+_CPU_JOB = None      # (params, packets) inherited by the forked workers: nothing is pickled per step
+
+
+def _cpu_worker(_):
     from oracle import gf3_oracle as orc
+    p, rx = _CPU_JOB
     return len(orc.receive_symbols(p, rx)["bits"])
 
 
@@ -142,10 +145,12 @@ def run_reference_arm(args, cfg, desc):
         return
     cores = os.cpu_count() or 1
     per_core = 16
+    global _CPU_JOB
     p, rx, _ = _cpu_packets(cfg, per_core)
+    _CPU_JOB = (p, rx)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        work = [(p, rx)] * cores
+        work = list(range(cores))
         for _ in range(args.warmup):
             pool.map(_cpu_worker, work)
         t0 = time.perf_counter()
