@@ -18,6 +18,7 @@
 //   GF3_PHASEB_UNROLL  symbols per unrolled step of the bin-pair phase
 //   GF3_FLUSH_UNROLL   packed words per unrolled step of the flush
 //   GF3_DEMOD_NATURAL  1: the last FFT pass leaves the spectrum unpadded (no mirrored-read conflicts)
+//   GF3_FUSE_SEQUENTIAL 1: fuse the estimate at N = 4096 too (measured slower: 0.80 vs 0.71 ms on C4)
 //   GF3_ABL            ablation mask for timing only (1: no bin-pair phase, 2: no FFT, 4: no global
 //                      loads, 8: no code stores); results are wrong with any bit set
 #include <stdlib.h>
@@ -38,6 +39,9 @@ constexpr int kThreads = 256;
 #endif
 #ifndef GF3_EST_U
 #define GF3_EST_U 20
+#endif
+#ifndef GF3_FUSE_SEQUENTIAL
+#define GF3_FUSE_SEQUENTIAL 0      // 1: fuse the estimate at N = 4096 too (pilot blocks one after the other)
 #endif
 #ifndef GF3_FLUSH_UNROLL
 #define GF3_FLUSH_UNROLL 2
@@ -840,7 +844,7 @@ static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaS
     GF3_REQUIRE(smem <= 227 * 1024, "rx_demod: %zu bytes of shared memory needed (> 227 KB)", smem);
     if constexpr (FUSE_EST) {
         // sequential pilot blocks (N = 4096) make the in-kernel estimate slower than a separate launch
-        if (demod_est_par<P, NT>() < 2) return GF3_FUSE_UNFIT;
+        if (demod_est_par<P, NT>() < 2 && !GF3_FUSE_SEQUENTIAL) return GF3_FUSE_UNFIT;
         // the fused estimate keeps its fit-window phases (2 x window doubles) in the code staging area
         const int K = P::M - 1;
         const int flo = a.fit_lo < 0 ? 0 : (a.fit_lo > K ? K : a.fit_lo), fhi = a.fit_hi < flo ? flo : (a.fit_hi > K ? K : a.fit_hi);
@@ -968,7 +972,7 @@ template <class P>
 static int receive_is_fused(const gf3_plan* plan) {
     using C = DemodCfg<P::LOGN>;
     constexpr int NT = (P::T > C::NT) ? P::T : C::NT, SF = NT / P::T;
-    if (demod_est_par<P, NT>() < 2) return 0;
+    if (demod_est_par<P, NT>() < 2 && !GF3_FUSE_SEQUENTIAL) return 0;
     const gf3_params& p = plan->p;
     const int K = P::M - 1, Nd = p.hi - p.lo;
     const int flo = p.fit_lo < 0 ? 0 : (p.fit_lo > K ? K : p.fit_lo), fhi = p.fit_hi < flo ? flo : (p.fit_hi > K ? K : p.fit_hi);
