@@ -453,3 +453,31 @@ def test_pcm_ingest(known_sequence, capsys):
     torch.cuda.synchronize()
     assert torch.equal(o16, o32)
     assert np.array_equal(phy2.unpack_bits(o16), gl["bits"])
+
+
+def test_fused_receive_is_deterministic_and_equals_two_launches(known_sequence):
+    """A large batch through the one-launch chain twice, and through gf3_rx_estimate + gf3_rx_demod:
+    byte-identical packed bits (persistent CTAs split packets between them, estimate some packets
+    twice and skip barriers around the flush -- any race would show up as a difference)."""
+    torch = _torch()
+    import gf3b200
+    from gf3b200 import synth
+    phy = gf3b200.Phy(N=1024, cp=32, lo=1, hi=512, n_pilots=20, packet_len=180, known_sequence=known_sequence,
+                      fit_lo=125, fit_hi=250)
+    b = synth.make_batch(phy, 1200, 1, snr_db=14.0, seed=77)
+    sym = synth.packets_from_streams(phy, b).contiguous()
+    n = sym.shape[0]
+    flat = sym.reshape(-1)
+    one, Hs1, He1, sl1 = phy.rx_receive(flat, n, xor=True)
+    again, _, _, sl2 = phy.rx_receive(flat, n, xor=True)
+    Hs, He, slope = phy.rx_estimate(flat, n)
+    two = phy.rx_demod(flat, n, Hs, He, slope, xor=True)
+    torch.cuda.synchronize()
+    assert torch.equal(one, again) and torch.equal(sl1, sl2)
+    assert float((Hs1 - Hs).abs().max() / Hs.abs().max()) < 1e-6           # the fused estimate sums the pilots in another order
+    diff = (one != two).any(dim=1)
+    # decisions may differ only where the two estimates' rounding moves a point across a boundary
+    assert int(diff.sum()) <= max(1, n // 100), int(diff.sum())
+    cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    phy.ber_count(one.contiguous(), two.contiguous(), n * phy.bits_stride * 8, cnt)
+    assert int(cnt[0]) <= n // 50, int(cnt[0])
