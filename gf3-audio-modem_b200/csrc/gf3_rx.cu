@@ -46,6 +46,9 @@ constexpr int kThreads = 256;
 #ifndef GF3_FLUSH_UNROLL
 #define GF3_FLUSH_UNROLL 2
 #endif
+#ifndef GF3_DMASK_ONCE
+#define GF3_DMASK_ONCE (-1)    // data-carrier mask of a thread's bins: 1 once per CTA, 0 per batch, -1 per-plan default
+#endif
 #ifndef GF3_PHASEB_UNROLL
 #define GF3_PHASEB_UNROLL 8
 #endif
@@ -351,6 +354,25 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
         wB[pp] = p_opaque(pk_pack(make_float2(c, -s)), my_slot);
         Ure[pp] = Uim[pp] = Gre[pp] = Gim[pp] = 0ull;
     }
+    // which of this thread's bins carry data: bit 2pp = bin k, bit 2pp+1 = bin M-k (absent for k = M/2).
+    // Derived once per CTA and pinned in a register: recomputing it costs ~10 instructions per pair.
+    // (A plan that is out of registers -- N = 2048 on 128-thread CTAs: 4 pairs x 5 packed constants next
+    // to 32 complex samples -- rebuilds the mask per batch instead: cheaper than one more spill.)
+    constexpr bool MASK_ONCE = GF3_DMASK_ONCE >= 0 ? GF3_DMASK_ONCE != 0 : !(R * PP >= 128 && MINB * NT >= 512);
+    auto data_mask = [&]() {
+        unsigned m = 0;
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) {
+            const int j = jb + pp * TB;
+            const int k = j == 0 ? M / 2 : j, km = M - k;
+            if (k >= a.lo && k < a.hi) m |= 1u << (2 * pp);
+            if (j != 0 && km >= a.lo && km < a.hi) m |= 2u << (2 * pp);
+        }
+        asm volatile("" : "+r"(m));                     // pinned: never re-derived per store
+        return m;
+    };
+    [[maybe_unused]] unsigned dmask_cta = 0;
+    if constexpr (MASK_ONCE) dmask_cta = data_mask();
     const double inv_lp = 1.0 / (double)(L + a.P);
     __shared__ int est_warp_tot[NT / 32];
     __shared__ double est_red[NT / 32];
@@ -531,7 +553,6 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                         const float2 *zp1[PP], *zp2[PP];
                         unsigned sp1[PP], sp2[PP];                              // shared-memory byte addresses of the code slots
                         bool e2[PP];                                            // bin M-k exists (k != M/2)
-                        unsigned dmask = 0;                                     // bit 2pp: bin k carries data, bit 2pp+1: bin M-k does
                         const unsigned st0 = (unsigned)__cvta_generic_to_shared(stage) + ls0 * Nd - a.lo;
 #pragma unroll
                         for (int pp = 0; pp < PP; ++pp) {
@@ -542,10 +563,10 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                             sp1[pp] = st0 + k;
                             sp2[pp] = st0 + km;
                             e2[pp] = j != 0;
-                            if (k >= a.lo && k < a.hi) dmask |= 1u << (2 * pp);
-                            if (e2[pp] && km >= a.lo && km < a.hi) dmask |= 2u << (2 * pp);
                         }
-                        asm volatile("" : "+r"(dmask));             // keep the mask in a register: no re-derivation per store
+                        unsigned dmask;
+                        if constexpr (MASK_ONCE) dmask = dmask_cta;
+                        else dmask = data_mask();
                         [[maybe_unused]] float2* eqp = nullptr;
                         if constexpr (WANT_EQ) eqp = a.eq + ((int64_t)pkt * L + l0 + ls0) * K - 1;
                         const int st_step = SB * Nd;
@@ -818,6 +839,14 @@ template <int LOGN> struct DemodCfg { using Plan = FftPlan<LOGN>; static constex
 #define GF3_DEMOD12_MINB 2
 #endif
 template <> struct DemodCfg<12> { using Plan = FftPlan<12>; static constexpr int NT = GF3_DEMOD12_THREADS, MINB = GF3_DEMOD12_MINB; };
+// N = 2048: a warp per symbol (32 x 32).  128-thread CTAs would give every thread 4 bin pairs next to
+// its 32 complex samples and spill; 256 threads (8 symbols per batch, 2 pairs per thread) fit:
+// chain 1.118 vs 1.154 ms on 2048 streams.
+#ifndef GF3_DEMOD11_THREADS
+#define GF3_DEMOD11_THREADS 256
+#define GF3_DEMOD11_MINB 2
+#endif
+template <> struct DemodCfg<11> { using Plan = FftPlan<11>; static constexpr int NT = GF3_DEMOD11_THREADS, MINB = GF3_DEMOD11_MINB; };
 
 template <int LOGN, bool KNOWN_CH, bool WANT_EQ, bool FUSE_EST = false>
 static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaStream_t st) {
