@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
     const int tid = threadIdx.x;
     for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
     const int g = tid / T, t = tid % T;
-    const int64_t n_work = (a.n_streams * a.nblk + SF - 1) / SF;
+    const int64_t total_blocks = a.n_streams * a.nblk;
+    const int64_t n_work = (total_blocks + SF - 1) / SF;
     // untangle items of this thread (item = tid + n*NT over SF*(M/2+1) pairs): block-in-CTA, bin and
     // twiddle are the same for every work item, so they are computed once per CTA
     constexpr int ITEMS = (SF * (M / 2 + 1) + NT - 1) / NT;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
         }
     }
     __syncthreads();
-    fft_forward<P, NT>(x, zbuf + g * MP, tw, t, g);
+    fft_forward<P, NT, true>(x, zbuf + g * MP, tw, t, g);     // natural order: the mirrored reads below stay conflict-free
     __syncthreads();
     // untangle: X[k] = (s + w2 d)/2, X[M-k] = conj(s - w2 d)/2
 #pragma unroll
@@ -105,10 +106,10 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
         if (item >= SF * (M / 2 + 1)) break;
         const int gg = item / (M / 2 + 1), k = item % (M / 2 + 1), km = M - k;
         const int64_t bg = work * SF + gg;
-        if (bg / a.nblk >= a.n_streams) continue;
+        if (bg >= total_blocks) continue;
         const float2* zs = zbuf + gg * MP;
         float2* out = a.spec + bg * M;
-        const float2 z1 = zs[zpad<P>(k)], z2 = zs[zpad<P>(km == M ? 0 : km)];
+        const float2 z1 = zs[k], z2 = zs[km == M ? 0 : km];
         const float2 w2 = uw[n];
         const float2 s = make_float2(z1.x + z2.x, z1.y - z2.y);
         const float2 d = make_float2(z1.x - z2.x, z1.y + z2.y);
@@ -207,22 +208,22 @@ __global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
         const float2 O = cmul(D, iw[q]);
         const float2 Zk = make_float2(E.x - O.y, E.y + O.x);
         const float2 Zm = make_float2(E.x + O.y, O.x - E.y);
-        zbuf[zpad<P>(k == M ? 0 : k)] = cconj(Zk);
-        if (k != 0 && km != k) zbuf[zpad<P>(km)] = cconj(Zm);
+        zbuf[k == M ? 0 : k] = cconj(Zk);               // plain indexing: this hand-over and the output below
+        if (k != 0 && km != k) zbuf[km] = cconj(Zm);    // are both conflict-free without padding
     }
     __syncthreads();
     float2 x[R];
 #pragma unroll
-    for (int i = 0; i < R; ++i) x[i] = zbuf[zpad<P>(tid + i * T)];
+    for (int i = 0; i < R; ++i) x[i] = zbuf[tid + i * T];
     __syncthreads();
-    fft_forward<P, NT>(x, zbuf, tw, tid, 0);
+    fft_forward<P, NT, true>(x, zbuf, tw, tid, 0);
     __syncthreads();
     // last B samples of the block: z[m], m in [M/2, M);  x[2m] = Re Y/N, x[2m+1] = -Im Y/N
     const float scale = 1.0f / (float)N;
     float* Prow = a.P + stream * a.p_stride;
     float lmax = __int_as_float(0xff800000);
     for (int m = M / 2 + tid; m < M; m += NT) {
-        const float2 y = zbuf[zpad<P>(m)];
+        const float2 y = zbuf[m];
         const int64_t n = (int64_t)b * kB + (2 * m - kB);
         const float v0 = y.x * scale, v1 = -y.y * scale;
         if (n < a.out_len) { Prow[n] = v0; lmax = fmaxf(lmax, v0); }
