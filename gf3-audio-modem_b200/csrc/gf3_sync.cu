@@ -37,9 +37,13 @@ struct FwdArgs {
 };
 
 // block b of a stream = samples [b*B - B, b*B + B), zero outside [0, T)
+// Each 128-thread group transforms one block and untangles it itself: thread t owns the bin pairs
+// (k, M-k), k = t + 128 q, so bin, twiddle and addresses need no per-item index arithmetic.  The
+// next work item's samples are requested right after the FFT, so they fly during the untangle.
 __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArgs a) {
     using P = SP;
     constexpr int NT = kSyncThreads, T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP, SF = NT / T;
+    constexpr int Q = (M / 2) / T;                     // bin pairs per thread (k = M/2 is one more for t = 0)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* zbuf = reinterpret_cast<float2*>(smem_raw);
     float2* tw = zbuf + SF * MP;
@@ -48,80 +52,85 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
     const int g = tid / T, t = tid % T;
     const int64_t total_blocks = a.n_streams * a.nblk;
     const int64_t n_work = (total_blocks + SF - 1) / SF;
-    // untangle items of this thread (item = tid + n*NT over SF*(M/2+1) pairs): block-in-CTA, bin and
-    // twiddle are the same for every work item, so they are computed once per CTA
-    constexpr int ITEMS = (SF * (M / 2 + 1) + NT - 1) / NT;
-    float2 uw[ITEMS];
+    float2 uw[Q];                                      // -j e^{-2 pi i k / N} of this thread's pairs, once per CTA
 #pragma unroll
-    for (int n = 0; n < ITEMS; ++n) {
-        const int k = (tid + n * NT) % (M / 2 + 1);
+    for (int q = 0; q < Q; ++q) {
         float sn, cs;
-        sincospif(2.0f * (float)k / (float)N, &sn, &cs);
-        uw[n] = make_float2(-sn, -cs);
+        sincospif(2.0f * (float)(t + q * T) / (float)N, &sn, &cs);
+        uw[q] = make_float2(-sn, -cs);
     }
-    // persistent: the twiddle table (~30 KB) is staged once per CTA, not once per pair of blocks
-    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
-    const int64_t blk_global = work * SF + g;
-    const int64_t stream = blk_global / a.nblk;
-    const int b = (int)(blk_global % a.nblk);
-    const bool live = stream < a.n_streams;
-    if (live && b == 0 && t == 0 && a.pmax) a.pmax[stream] = __int_as_float(0xff800000);
     float2 x[R];
-    {
-        const float* row = a.r + (live ? stream : 0) * a.r_stride;
+    auto load_block = [&](int64_t work) {
+        const int64_t blk_global = work * SF + g;
+        const bool live = blk_global < total_blocks;
+        const int64_t stream = live ? blk_global / a.nblk : 0;
+        const int b = (int)(blk_global - stream * a.nblk);
+        if (live && b == 0 && t == 0 && a.pmax) a.pmax[stream] = __int_as_float(0xff800000);
+        const float* row = a.r + stream * a.r_stride;
         const int64_t s0 = (int64_t)b * kB - kB + a.in_off;
         const bool fast = live && !a.reverse && s0 >= 0 && s0 + 2 * kB <= a.T && a.valid_len >= 2 * kB &&
                           ((reinterpret_cast<uintptr_t>(row + s0) & 7) == 0);
         if (fast) {      // interior block, 8-byte aligned: vector loads without bounds checks
 #pragma unroll
-            for (int i = 0; i < R; ++i) x[i] = *reinterpret_cast<const float2*>(row + s0 + 2 * (t + i * T));
+            for (int i = 0; i < R; ++i) x[i] = __ldg(reinterpret_cast<const float2*>(row + s0) + (t + i * T));
         } else {
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-            const int loc = 2 * (t + i * T);
-            const int64_t n = s0 + loc;
-            float v0 = 0.f, v1 = 0.f;
-            if (live) {
-                const bool ok0 = n >= 0 && n < a.T && loc < a.valid_len;
-                const bool ok1 = n + 1 >= 0 && n + 1 < a.T && loc + 1 < a.valid_len;
-                if (!a.reverse) {
-                    if (ok0) v0 = row[n];
-                    if (ok1) v1 = row[n + 1];
-                } else {
-                    if (ok0) v0 = row[a.T - 1 - n];
-                    if (ok1) v1 = row[a.T - 2 - n];
+            for (int i = 0; i < R; ++i) {
+                const int loc = 2 * (t + i * T);
+                const int64_t n = s0 + loc;
+                float v0 = 0.f, v1 = 0.f;
+                if (live) {
+                    const bool ok0 = n >= 0 && n < a.T && loc < a.valid_len;
+                    const bool ok1 = n + 1 >= 0 && n + 1 < a.T && loc + 1 < a.valid_len;
+                    if (!a.reverse) {
+                        if (ok0) v0 = row[n];
+                        if (ok1) v1 = row[n + 1];
+                    } else {
+                        if (ok0) v0 = row[a.T - 1 - n];
+                        if (ok1) v1 = row[a.T - 2 - n];
+                    }
                 }
+                x[i] = make_float2(v0, v1);
             }
-            x[i] = make_float2(v0, v1);
         }
-        }
-    }
-    __syncthreads();
-    fft_forward<P, NT, true>(x, zbuf + g * MP, tw, t, g);     // natural order: the mirrored reads below stay conflict-free
-    __syncthreads();
-    // untangle: X[k] = (s + w2 d)/2, X[M-k] = conj(s - w2 d)/2
-#pragma unroll
-    for (int n = 0; n < ITEMS; ++n) {
-        const int item = tid + n * NT;
-        if (item >= SF * (M / 2 + 1)) break;
-        const int gg = item / (M / 2 + 1), k = item % (M / 2 + 1), km = M - k;
-        const int64_t bg = work * SF + gg;
+    };
+    // persistent: the twiddle table (~30 KB) is staged once per CTA, not once per pair of blocks
+    if ((int64_t)blockIdx.x < n_work) load_block(blockIdx.x);
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
+        __syncthreads();                               // twiddles staged / previous untangle done with zbuf
+        float2* zs = zbuf + g * MP;
+        fft_forward<P, NT, true>(x, zs, tw, t, g);     // natural order: the mirrored reads below stay conflict-free
+        __syncthreads();
+        if (work + gridDim.x < n_work) load_block(work + gridDim.x);
+        const int64_t bg = work * SF + g;
         if (bg >= total_blocks) continue;
-        const float2* zs = zbuf + gg * MP;
         float2* out = a.spec + bg * M;
-        const float2 z1 = zs[k], z2 = zs[km == M ? 0 : km];
-        const float2 w2 = uw[n];
-        const float2 s = make_float2(z1.x + z2.x, z1.y - z2.y);
-        const float2 d = make_float2(z1.x - z2.x, z1.y + z2.y);
-        const float2 tt = cmul(w2, d);
-        const float2 x1 = make_float2(0.5f * (s.x + tt.x), 0.5f * (s.y + tt.y));
-        const float2 x2 = make_float2(0.5f * (s.x - tt.x), 0.5f * (tt.y - s.y));
-        if (k == 0) out[0] = make_float2(x1.x, x2.x);          // (X[0], X[M])
-        else {
-            out[k] = x1;
-            if (km != k) out[km] = x2;
+        // untangle: X[k] = (s + w2 d)/2, X[M-k] = conj(s - w2 d)/2
+        auto pair = [&](int k, float2 w2, float2& x1, float2& x2) {
+            const float2 z1 = zs[k], z2 = zs[(M - k) & (M - 1)];
+            const float2 s = make_float2(z1.x + z2.x, z1.y - z2.y);
+            const float2 d = make_float2(z1.x - z2.x, z1.y + z2.y);
+            const float2 tt = cmul(w2, d);
+            x1 = make_float2(0.5f * (s.x + tt.x), 0.5f * (s.y + tt.y));
+            x2 = make_float2(0.5f * (s.x - tt.x), 0.5f * (tt.y - s.y));
+        };
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int k = t + q * T;
+            float2 x1, x2;
+            pair(k, uw[q], x1, x2);
+            if (q == 0 && t == 0) {
+                out[0] = make_float2(x1.x, x2.x);      // (X[0], X[M]), both real
+            } else {
+                out[k] = x1;
+                out[M - k] = x2;
+            }
         }
-    }
+        if (t == 0) {                                   // k = M/2 pairs with itself; w2 = -j e^{-j pi/2} = -1
+            float2 x1, x2;
+            pair(M / 2, make_float2(-1.f, 0.f), x1, x2);
+            out[M / 2] = x1;
+        }
     }
 }
 
@@ -141,103 +150,112 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
     else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-// One CTA (128 threads = one symbol group) per output block.
+// One CTA (128 threads = one symbol group) per output block.  Thread t owns the bin pairs (k, M-k),
+// k = t + 128 q (k = M/2, which pairs with itself, takes the slot of k = 0); thread 0 also carries
+// the packed (DC, Nyquist) element, whose products are real.
 __global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
     using P = SP;
     constexpr int NT = 128, T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP;
     static_assert(T == NT, "one symbol group per CTA");
-    constexpr int PAIRS = M / 2 + 1, PPT = (PAIRS + NT - 1) / NT;
+    constexpr int Q = (M / 2) / NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* zbuf = reinterpret_cast<float2*>(smem_raw);
     float2* tw = zbuf + MP;
     __shared__ float wmax[NT / 32];
     const int tid = threadIdx.x;
     for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
-    float2 iw[PPT];                                    // e^{+j 2 pi k / N} of this thread's bin pairs, once per CTA
+    const int k0 = tid == 0 ? M / 2 : tid;             // bin of slot 0; slot q is k0 + q * NT
+    float2 iw[Q];                                      // e^{+j 2 pi k / N} of this thread's bin pairs, once per CTA
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) {
+    for (int q = 0; q < Q; ++q) {
         float sn, cs;
-        sincospif(2.0f * (float)(tid + q * NT) / (float)N, &sn, &cs);
+        sincospif(2.0f * (float)(q == 0 ? k0 : tid + q * NT) / (float)N, &sn, &cs);
         iw[q] = make_float2(cs, sn);
     }
     // persistent: the twiddle table is staged once per CTA; co-resident CTAs work on neighbouring
     // blocks, so the chirp-partition spectra and the shared input spectra stay hot in L2
     for (int64_t work = blockIdx.x; work < a.n_work; work += gridDim.x) {
-    const int64_t stream = work / a.nblk_out;
-    const int b = (int)(work % a.nblk_out);
-    __syncthreads();
+        const int64_t stream = work / a.nblk_out;
+        const int b = (int)(work - stream * a.nblk_out);
+        __syncthreads();
 
-    float2 acc1[PPT], acc2[PPT];
+        float2 acc1[Q], acc2[Q];
+        float dc = 0.f, ny = 0.f;
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) acc1[q] = acc2[q] = make_float2(0.f, 0.f);
-    for (int p = 0; p < a.parts; ++p) {
-        const int bi = b - p;
-        if (bi < 0 || bi >= a.nblk_in) continue;
-        const float2* X = a.spec + (stream * a.nblk_in + bi) * M;
-        const float2* H = a.H + (int64_t)p * M;
+        for (int q = 0; q < Q; ++q) acc1[q] = acc2[q] = make_float2(0.f, 0.f);
+        const int p_lo = b - (a.nblk_in - 1) > 0 ? b - (a.nblk_in - 1) : 0;
+        const int p_hi = b < a.parts - 1 ? b : a.parts - 1;
+        const float2* X = a.spec + (stream * a.nblk_in + (b - p_lo)) * M;
+        const float2* H = a.H + (int64_t)p_lo * M;
+        for (int p = p_lo; p <= p_hi; ++p, X -= M, H += M) {
 #pragma unroll
-        for (int q = 0; q < PPT; ++q) {
-            const int k = tid + q * NT;
-            if (k >= PAIRS) continue;
-            const int km = M - k;
-            if (k == 0) {          // packed (DC, Nyquist): component-wise real products
-                const float2 xv = X[0], hv = H[0];
-                acc1[q].x += xv.x * hv.x;
-                acc2[q].x += xv.y * hv.y;
-            } else {
-                const float2 x1 = X[k], h1 = H[k];
+            for (int q = 0; q < Q; ++q) {
+                const int k = q == 0 ? k0 : tid + q * NT, km = M - k;
+                const float2 x1 = X[k], h1 = __ldg(H + k), x2 = X[km], h2 = __ldg(H + km);
                 acc1[q].x = fmaf(x1.x, h1.x, fmaf(-x1.y, h1.y, acc1[q].x));
                 acc1[q].y = fmaf(x1.x, h1.y, fmaf(x1.y, h1.x, acc1[q].y));
-                if (km != k) {
-                    const float2 x2 = X[km], h2 = H[km];
-                    acc2[q].x = fmaf(x2.x, h2.x, fmaf(-x2.y, h2.y, acc2[q].x));
-                    acc2[q].y = fmaf(x2.x, h2.y, fmaf(x2.y, h2.x, acc2[q].y));
-                }
+                acc2[q].x = fmaf(x2.x, h2.x, fmaf(-x2.y, h2.y, acc2[q].x));
+                acc2[q].y = fmaf(x2.x, h2.y, fmaf(x2.y, h2.x, acc2[q].y));
+            }
+            if (tid == 0) {        // packed (DC, Nyquist): component-wise real products
+                const float2 xv = X[0], hv = __ldg(H);
+                dc = fmaf(xv.x, hv.x, dc);
+                ny = fmaf(xv.y, hv.y, ny);
             }
         }
-    }
-    // inverse untangle: Z[k] = E + jO, E = Y[k] + conj Y[M-k], O = (Y[k] - conj Y[M-k]) e^{+j theta}
+        // inverse untangle: Z[k] = E + jO, E = Y[k] + conj Y[M-k], O = (Y[k] - conj Y[M-k]) e^{+j theta};
+        // the forward engine then runs on conj Z.  Plain indexing: this hand-over and the output below
+        // are both conflict-free without padding
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-        const int k = tid + q * NT;
-        if (k >= PAIRS) continue;
-        const int km = M - k;
-        float2 Y1 = acc1[q], Y2 = (km == k) ? acc1[q] : acc2[q];      // k == 0: Y1 = (Y[0],0), Y2 = (Y[M],0)
-        const float2 E = make_float2(Y1.x + Y2.x, Y1.y - Y2.y);
-        const float2 D = make_float2(Y1.x - Y2.x, Y1.y + Y2.y);
-        const float2 O = cmul(D, iw[q]);
-        const float2 Zk = make_float2(E.x - O.y, E.y + O.x);
-        const float2 Zm = make_float2(E.x + O.y, O.x - E.y);
-        zbuf[k == M ? 0 : k] = cconj(Zk);               // plain indexing: this hand-over and the output below
-        if (k != 0 && km != k) zbuf[km] = cconj(Zm);    // are both conflict-free without padding
-    }
-    __syncthreads();
-    float2 x[R];
+        for (int q = 0; q < Q; ++q) {
+            const int k = q == 0 ? k0 : tid + q * NT, km = M - k;
+            const float2 Y1 = acc1[q], Y2 = acc2[q];
+            const float2 E = make_float2(Y1.x + Y2.x, Y1.y - Y2.y);
+            const float2 D = make_float2(Y1.x - Y2.x, Y1.y + Y2.y);
+            const float2 O = cmul(D, iw[q]);
+            zbuf[k] = make_float2(E.x - O.y, -(E.y + O.x));
+            zbuf[km] = make_float2(E.x + O.y, E.y - O.x);      // k = M/2: the same value to the same slot
+        }
+        if (tid == 0) zbuf[0] = make_float2(dc + ny, ny - dc);
+        __syncthreads();
+        float2 x[R];
 #pragma unroll
-    for (int i = 0; i < R; ++i) x[i] = zbuf[tid + i * T];
-    __syncthreads();
-    fft_forward<P, NT, true>(x, zbuf, tw, tid, 0);
-    __syncthreads();
-    // last B samples of the block: z[m], m in [M/2, M);  x[2m] = Re Y/N, x[2m+1] = -Im Y/N
-    const float scale = 1.0f / (float)N;
-    float* Prow = a.P + stream * a.p_stride;
-    float lmax = __int_as_float(0xff800000);
-    for (int m = M / 2 + tid; m < M; m += NT) {
-        const float2 y = zbuf[m];
-        const int64_t n = (int64_t)b * kB + (2 * m - kB);
-        const float v0 = y.x * scale, v1 = -y.y * scale;
-        if (n < a.out_len) { Prow[n] = v0; lmax = fmaxf(lmax, v0); }
-        if (n + 1 < a.out_len) { Prow[n + 1] = v1; lmax = fmaxf(lmax, v1); }
-    }
+        for (int i = 0; i < R; ++i) x[i] = zbuf[tid + i * T];
+        __syncthreads();
+        fft_forward<P, NT, true>(x, zbuf, tw, tid, 0);
+        __syncthreads();
+        // last B samples of the block: z[m], m in [M/2, M);  x[2m] = Re Y/N, x[2m+1] = -Im Y/N
+        const float scale = 1.0f / (float)N;
+        float* Prow = a.P + stream * a.p_stride;
+        float lmax = __int_as_float(0xff800000);
+        const int64_t n0 = (int64_t)b * kB - kB;
+        if (n0 + 2 * M <= a.out_len && ((reinterpret_cast<uintptr_t>(Prow + n0) & 7) == 0)) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-    if ((tid & 31) == 0) wmax[tid >> 5] = lmax;
-    __syncthreads();
-    if (tid == 0) {
-        float m = wmax[0];
-        for (int w = 1; w < NT / 32; ++w) m = fmaxf(m, wmax[w]);
-        if (m > __int_as_float(0xff800000)) atomic_max_float(a.pmax + stream, m);
-    }
+            for (int i = 0; i < M / 2 / NT; ++i) {
+                const int m = M / 2 + tid + i * NT;
+                const float2 y = zbuf[m];
+                const float2 v = make_float2(y.x * scale, -y.y * scale);
+                *reinterpret_cast<float2*>(Prow + n0 + 2 * m) = v;
+                lmax = fmaxf(lmax, fmaxf(v.x, v.y));
+            }
+        } else {
+            for (int m = M / 2 + tid; m < M; m += NT) {
+                const float2 y = zbuf[m];
+                const int64_t n = n0 + 2 * m;
+                const float v0 = y.x * scale, v1 = -y.y * scale;
+                if (n < a.out_len) { Prow[n] = v0; lmax = fmaxf(lmax, v0); }
+                if (n + 1 < a.out_len) { Prow[n + 1] = v1; lmax = fmaxf(lmax, v1); }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if ((tid & 31) == 0) wmax[tid >> 5] = lmax;
+        __syncthreads();
+        if (tid == 0) {
+            float m = wmax[0];
+            for (int w = 1; w < NT / 32; ++w) m = fmaxf(m, wmax[w]);
+            if (m > __int_as_float(0xff800000)) atomic_max_float(a.pmax + stream, m);
+        }
     }
 }
 
