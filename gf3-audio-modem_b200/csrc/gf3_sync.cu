@@ -342,41 +342,60 @@ __global__ void __launch_bounds__(256) peak_scan_kernel(const PeakArgs a) {
     if (tid == 0) a.count[stream] = wiped ? 0 : found;
 }
 
-// Single-kernel variant, one CTA per stream walking 2048-position tiles: with hundreds of streams in a
+// Single-kernel variant, one CTA per stream walking 4096-position tiles: with hundreds of streams in a
 // batch the streams themselves supply the parallelism, and one pass over P is cheaper than mark + scan.
+// A round costs one DRAM latency, so it is made wide: every thread takes 16 positions from four
+// 128-bit loads (tiles start on a 16-byte boundary at or below the walk position; positions behind it
+// are masked), evaluates them without branches, and the CTA agrees on the first candidate with one
+// barrier per round (three result slots in rotation: the slot of round r+2 is cleared in round r).
 __global__ void __launch_bounds__(256) peak_pick_kernel(const PeakArgs a) {
-    constexpr int NT = 256, PER = 8, TILE = NT * PER;
-    __shared__ long long s_first;
+    constexpr int NT = 256, PER = 16, TILE = NT * PER;
+    constexpr long long kNone = 0x7fffffffffffffffLL;
+    __shared__ long long s_first[3];
     const int tid = threadIdx.x;
     const int64_t stream = blockIdx.x;
     const float* Prow = a.P + stream * a.p_stride;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(Prow) & 15) == 0;
     const float inv = 1.0f / a.pmax[stream];
     const int64_t nz = a.plen - 2;
     int32_t found = 0;
     bool wiped = false;
     int64_t pos = 0;
-    while (pos < nz) {
-        if (tid == 0) s_first = 0x7fffffffffffffffLL;
-        __syncthreads();
-        const int64_t base = pos + (int64_t)tid * PER;
-        long long mine = 0x7fffffffffffffffLL;
+    if (tid < 3) s_first[tid] = kNone;
+    __syncthreads();
+    for (int round = 0; pos < nz; ++round) {
+        const int slot = round % 3;
+        const int64_t tb = pos & ~(int64_t)3;
+        const int64_t base = tb + (int64_t)tid * PER;
         if (base < nz) {
-            float prev = Prow[base] * inv, cur = Prow[base + 1] * inv;
+            float v[PER + 2];
+            if (vec_ok && base + PER + 2 <= a.plen) {
+#pragma unroll
+                for (int e = 0; e < PER / 4; ++e) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(Prow + base) + e);
+                    v[4 * e] = q.x; v[4 * e + 1] = q.y; v[4 * e + 2] = q.z; v[4 * e + 3] = q.w;
+                }
+                const float2 q2 = __ldg(reinterpret_cast<const float2*>(Prow + base + PER));
+                v[PER] = q2.x; v[PER + 1] = q2.y;
+            } else {
+#pragma unroll
+                for (int e = 0; e < PER + 2; ++e) v[e] = base + e < a.plen ? Prow[base + e] : 0.f;
+            }
+            unsigned m = 0;
 #pragma unroll
             for (int e = 0; e < PER; ++e) {
-                const int64_t i = base + e;
-                if (i >= nz) break;
-                const float nxt = Prow[i + 2] * inv;
+                const float prev = v[e] * inv, cur = v[e + 1] * inv, nxt = v[e + 2] * inv;
                 const float d0 = cur - prev, d1 = nxt - cur;
-                if (d0 * d1 <= 0.f && cur > a.thresh) { mine = i; break; }
-                prev = cur; cur = nxt;
+                if (d0 * d1 <= 0.f && cur > a.thresh) m |= 1u << e;
             }
+            if (base < pos) m &= 0xffffffffu << (int)(pos - base);       // positions behind the walk
+            if (base + PER > nz) m &= 0xffffffffu >> (32 - (int)(nz - base)); // positions past the end
+            if (m) atomicMin(&s_first[slot], (long long)(base + __ffs(m) - 1));
         }
-        if (mine != 0x7fffffffffffffffLL) atomicMin(&s_first, mine);
         __syncthreads();
-        const long long first = s_first;
-        __syncthreads();
-        if (first == 0x7fffffffffffffffLL) { pos += TILE; continue; }
+        const long long first = s_first[slot];
+        if (tid == 0) s_first[(round + 2) % 3] = kNone;
+        if (first == kNone) { pos = tb + TILE; continue; }
         if (first + a.Lc >= nz) { wiped = true; break; }
         if (tid == 0 && found < a.max_peaks) a.peaks[stream * a.max_peaks + found] = first;
         ++found;

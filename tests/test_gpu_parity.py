@@ -281,6 +281,41 @@ def test_sync_quirk_wipeout(known_sequence):
         assert np.array_equal(peaks[0, : int(count[0])].cpu().numpy(), g["peaks_trail%d" % trail]), trail
 
 
+def test_peak_pick_paths_agree(known_sequence):
+    """The one-kernel path (batches of at least two waves of streams) and the mark + scan path
+    (validated against the goldens above) walk the same detections: many streams at different
+    delays, noise levels above the threshold, truncated tails (wipe-out quirk), rows at 16-byte
+    aligned and unaligned addresses."""
+    torch = _torch()
+    g = load_golden("sync_quirk.npz")
+    p = oracle_params(g["cfg"], known_sequence, encoding="None")
+    p.fit_lo, p.fit_hi = 10, 100
+    phy = _phy(p)
+    sig = torch.from_numpy(g["sig"].astype(np.float32)).cuda()
+    B = 2 * torch.cuda.get_device_properties(0).multi_processor_count + 37
+    T = sig.numel() + 240
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    r = 0.02 * torch.randn((B, T), device="cuda", generator=gen)
+    for s in range(B):
+        d = {20: 240, 21: 239}.get(s, (s * 7) % 200)                # 20, 21: no room after the last chirp (wipe-out)
+        n = sig.numel() if s % 5 or s in (20, 21) else sig.numel() - (s % 11)   # some streams lose their tail
+        r[s, d:d + n] += sig[:n] * (1.0 + 0.01 * (s % 13))
+    if B > 10:
+        r[10] = 0.3 * torch.randn(T, device="cuda", generator=gen)  # noise only: many candidates above 0.4 max
+    P, pmax = phy.xcorr(r)
+    one, one_n = phy.peak_pick(P, pmax, T, 8)
+    parts = [phy.peak_pick(P[i:i + 64], pmax[i:i + 64], T, 8) for i in range(0, B, 64)]
+    two = torch.cat([q[0] for q in parts]); two_n = torch.cat([q[1] for q in parts])
+    assert torch.equal(one_n, two_n) and torch.equal(one, two)
+    assert int((one_n > 0).sum()) > B // 2 and int(one_n.max()) >= 3 and int(one_n[20]) == 0
+    for shift in (1, 2, 3):                                         # rows that are not 16-byte aligned
+        buf = torch.zeros((B, P.stride(0) + 4), dtype=torch.float32, device="cuda")
+        Pu = buf[:, shift:shift + P.shape[1]]
+        Pu.copy_(P)
+        o, n = phy.peak_pick(Pu, pmax, T, 8)
+        assert torch.equal(n, one_n) and torch.equal(o, one), shift
+
+
 # ----------------------------------------------------------------------------- properties at scale
 @pytest.mark.parametrize("cfg", [
     dict(N=1024, cp=32, lo=1, hi=512, n_pilots=20, packet_len=180, streams=256),      # BASELINE config C3 shape
