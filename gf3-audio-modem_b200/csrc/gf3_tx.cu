@@ -46,12 +46,11 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* zbuf = reinterpret_cast<float2*>(smem_raw);
     float2* tw = zbuf + SF * MP;
-    uint8_t* sbits = reinterpret_cast<uint8_t*>(tw + P::TW_TOTAL);     // [SF][sym_bytes]
+    uint8_t* sbits = reinterpret_cast<uint8_t*>(tw + P::TW_TOTAL);     // [NB * NT] packed bits of the work item's symbols
 
     const int tid = threadIdx.x;
     const int Nd = a.hi - a.lo;
     const int symlen = N + a.cp;
-    const int sym_bytes = ((2 * Nd + 7) / 8 + 1 + 3) & ~3;
     for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
 
     // ---- per-thread constants of phase B': pairs k = jb + pp*TB (k = M/2 takes the slot of k = 0)
@@ -81,6 +80,27 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
     const int g = tid / T, t = tid % T;
 
     const int64_t n_work = KNOWN_SYMBOL ? 1 : a.n_work;
+    // The packed bits of a work item's symbols are one contiguous byte range of the packet (symbol l
+    // starts at bit 2 Nd l).  They are fetched one item ahead into registers (NB bytes per thread), so
+    // their latency is covered by the previous item's spectrum / FFT / store phases.
+    constexpr int NB = R / 4 + 1;                     // >= ceil((SF * 2 Nd / 8 + 2) / NT), Nd < M
+    uint8_t nb[NB];
+    auto fetch_bits = [&](int64_t w) {
+        const int64_t pg = w / a.batches_per_packet;
+        const int lf = (int)(w % a.batches_per_packet) * SF;
+        const int ns = min(SF, a.L - lf);
+        const int64_t first = ((int64_t)lf * 2 * Nd) >> 3;
+        const int nbytes = (int)((((int64_t)(lf + ns) * 2 * Nd + 7) >> 3) - first);
+        const uint8_t* pb = a.bits + pg * a.bits_stride + first;
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int i = tid + n * NT;
+            nb[n] = (i < nbytes && first + i < a.bits_stride) ? __ldg(pb + i) : (uint8_t)0;
+        }
+    };
+    if constexpr (!KNOWN_SYMBOL) {
+        if ((int64_t)blockIdx.x < n_work) fetch_bits(blockIdx.x);
+    }
 #pragma unroll 1
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
         int64_t pktg = 0;           // global packet index (stream * pk_per_stream + packet)
@@ -94,23 +114,21 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
         const float2* fill = KNOWN_SYMBOL ? a.known : a.filler + stream * (K - Nd);
 
         // stage the packed bits of the nsym symbols (bit offset l*2Nd is not byte aligned in general)
-        if constexpr (!KNOWN_SYMBOL) {
-            const uint8_t* pb = a.bits + pktg * a.bits_stride;
-            for (int i = tid; i < nsym * sym_bytes; i += NT) {
-                const int s = i / sym_bytes, o = i % sym_bytes;
-                const int64_t idx = (((int64_t)(l_first + s) * 2 * Nd) >> 3) + o;
-                sbits[i] = idx < a.bits_stride ? pb[idx] : 0;
-                (void)s;
-            }
+        if constexpr (!KNOWN_SYMBOL) {      // (the previous item's phase B' reads of sbits are two barriers back)
+#pragma unroll
+            for (int n = 0; n < NB; ++n) sbits[tid + n * NT] = nb[n];
         }
         __syncthreads();            // also: the previous work item's epilogue is done with zbuf
+        if constexpr (!KNOWN_SYMBOL) {
+            if (work + gridDim.x < n_work) fetch_bits(work + gridDim.x);
+        }
 
         // ---- phase B': Hermitian spectrum -> conj(Z[k]) for the packed inverse real FFT
         //   E = X[k] + conj X[M-k],  O = (X[k] - conj X[M-k]) e^{+2 pi i k/N},  Z = E + jO
         for (int s = sb; s < nsym; s += SB) {              // (symbols past the packet's end: their buffers hold stale
             float2* zs = zbuf + s * MP;                    //  values, the FFT runs on them and nothing is written out)
-            const int bit0 = (int)(((int64_t)(l_first + s) * 2 * Nd) & 7);
-            const uint8_t* sym = sbits + s * sym_bytes;
+            const int bit0 = s * 2 * Nd + (int)(((int64_t)l_first * 2 * Nd) & 7);   // first bit of symbol s in the staged range
+            const uint8_t* sym = sbits;
             auto bin = [&](int src) -> float2 {
                 // data bin: QPSK of the encoded bit pair (OFDM.py:72-77), (b0,b1) -> ((1-2 b1) + j (1-2 b0)) / sqrt(2):
                 // the two bits (MSB first) are moved onto the sign bits of +1/sqrt(2)
@@ -247,8 +265,7 @@ template <class P>
 static int launch_tx(const gf3_plan* plan, TxArgs a, const float* known, int64_t n_streams, float* known_time, cudaStream_t st) {
     constexpr int SF = kTxThreads / P::T;
     const gf3_params& p = plan->p;
-    const int Nd = p.hi - p.lo;
-    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)SF * ((((2 * Nd + 7) / 8 + 1) + 3) & ~3) + 16;
+    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)(P::R / 4 + 1) * kTxThreads + 16;   // staged bits: NB bytes per thread
     // 1. the known symbol's time waveform (one symbol, gain applied) into scratch
     {
         TxArgs k = a;
@@ -295,8 +312,7 @@ static int launch_frame_known(const gf3_plan* plan, const float* known, const fl
                               int64_t n_packets, float* out, float* known_time, cudaStream_t st) {
     constexpr int SF = kTxThreads / P::T;
     const gf3_params& p = plan->p;
-    const int Nd = p.hi - p.lo;
-    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)SF * ((((2 * Nd + 7) / 8 + 1) + 3) & ~3) + 16;
+    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)(P::R / 4 + 1) * kTxThreads + 16;   // staged bits: NB bytes per thread
     TxArgs k;
     memset(&k, 0, sizeof(k));
     k.known = reinterpret_cast<const float2*>(known); k.tw = plan->d_tw; k.out = known_time;
