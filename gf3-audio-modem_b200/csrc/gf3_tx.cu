@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
     // ---- per-thread constants of phase B': pairs k = jb + pp*TB (k = M/2 takes the slot of k = 0)
     const int jb = tid % TB, sb = tid / TB;
     float2 rot[PP];             // e^{+2 pi i k / N}
-    int zo1[PP], zo2[PP];       // padded smem offsets of Z[k], Z[M-k]
+    int zo1[PP], zo2[PP];       // smem offsets of Z[k], Z[M-k]
     int src1[PP], src2[PP];     // bin k / M-k: >= 0 bit offset of the carrier's pair inside a symbol; -1 - u filler index; INT_MIN zero
     constexpr int kZero = (int)0x80000000;
     auto classify = [&](int kk) -> int {
@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
         rot[pp] = make_float2(cs, sn);
         src1[pp] = classify(k);
         src2[pp] = classify(km);
-        zo1[pp] = zpad<P>(k);
-        zo2[pp] = j != 0 ? zpad<P>(km) : 0;            // the k = M/2 slot also clears Z[0] (DC and Nyquist: both 0)
+        zo1[pp] = k;                                   // plain indexing: the hand-over to the FFT's register layout and the
+        zo2[pp] = j != 0 ? km : 0;                     // natural-order output below are conflict-free without padding;            // the k = M/2 slot also clears Z[0] (DC and Nyquist: both 0)
     }
     const int g = tid / T, t = tid % T;
 
@@ -158,9 +158,9 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
             float2 x[R];
             float2* zs = zbuf + g * MP;
 #pragma unroll
-            for (int i = 0; i < R; ++i) x[i] = zs[zpad<P>(t + i * T)];
+            for (int i = 0; i < R; ++i) x[i] = zs[t + i * T];
             group_sync<P, NT>(g);
-            fft_forward<P, NT>(x, zs, tw, t, g);
+            fft_forward<P, NT, true>(x, zs, tw, t, g);
         }
         __syncthreads();
 
@@ -180,14 +180,14 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
 #pragma unroll 8
                 for (int i = 0; i < R; ++i) {
                     const int m = t + i * T;
-                    const float2 y = zs[zpad<P>(m)];
+                    const float2 y = zs[m];
                     const float2 v = make_float2(y.x * a.gain, -y.y * a.gain);
                     body[m] = v;
                     if (m >= cp_first) pre[m] = v;
                 }
             } else {
                 for (int m = t; m < M; m += T) {
-                    const float2 y = zs[zpad<P>(m)];
+                    const float2 y = zs[m];
                     const float v0 = y.x * a.gain, v1 = -y.y * a.gain;
                     const int n0 = 2 * m - (N - a.cp);                   // position of this pair inside the cyclic prefix
                     o[a.cp + 2 * m] = v0;
