@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
         if (kk >= a.lo && kk < a.hi) return 2 * (kk - a.lo);
         return -1 - (kk < a.lo ? kk - 1 : kk - 1 - Nd);                    // np.delete keeps ascending order (OFDM.py:49,213)
     };
+    bool all_data = !KNOWN_SYMBOL;                    // every bin of this thread is a data carrier: no selects, no filler loads
 #pragma unroll
     for (int pp = 0; pp < PP; ++pp) {
         const int j = jb + pp * TB;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
         rot[pp] = make_float2(cs, sn);
         src1[pp] = classify(k);
         src2[pp] = classify(km);
+        all_data = all_data && src1[pp] >= 0 && src2[pp] >= 0;
         zo1[pp] = k;                                   // plain indexing: the hand-over to the FFT's register layout and the
         zo2[pp] = j != 0 ? km : 0;                     // natural-order output below are conflict-free without padding;            // the k = M/2 slot also clears Z[0] (DC and Nyquist: both 0)
     }
@@ -139,9 +141,12 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
                 if (src < 0) v = (src == kZero) ? make_float2(0.f, 0.f) : fill[-1 - src];    // unused bin / filler (or known) symbol
                 return v;
             };
-#pragma unroll
-            for (int pp = 0; pp < PP; ++pp) {
-                const float2 X1 = bin(src1[pp]), X2 = bin(src2[pp]);
+            auto data_bin = [&](int bp) -> float2 {         // bp: even bit position inside the staged range
+                const unsigned w = (unsigned)sym[bp >> 3] << (24 + (bp & 7));   // bit 31 = b0, bit 30 = b1
+                return make_float2(__uint_as_float(0x3f3504f3u | ((w << 1) & 0x80000000u)),
+                                   __uint_as_float(0x3f3504f3u | (w & 0x80000000u)));
+            };
+            auto put_pair = [&](int pp, float2 X1, float2 X2) {
                 const float2 E = make_float2(X1.x + X2.x, X1.y - X2.y);
                 const float2 D = make_float2(X1.x - X2.x, X1.y + X2.y);
                 const float2 O = cmul(D, rot[pp]);
@@ -149,6 +154,13 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
                 const bool self = (jb + pp * TB) == 0;                     // k = M/2 pairs with itself
                 zs[zo1[pp]] = make_float2(E.x - O.y, -(E.y + O.x));
                 zs[zo2[pp]] = self ? make_float2(0.f, 0.f) : make_float2(E.x + O.y, E.y - O.x);
+            };
+            if (all_data) {
+#pragma unroll
+                for (int pp = 0; pp < PP; ++pp) put_pair(pp, data_bin(bit0 + src1[pp]), data_bin(bit0 + src2[pp]));
+            } else {
+#pragma unroll
+                for (int pp = 0; pp < PP; ++pp) put_pair(pp, bin(src1[pp]), bin(src2[pp]));
             }
         }
         __syncthreads();
