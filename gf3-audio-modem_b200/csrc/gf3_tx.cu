@@ -92,13 +92,12 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
         const int lf = (int)(w % a.batches_per_packet) * SF;
         const int ns = min(SF, a.L - lf);
         const int64_t first = ((int64_t)lf * 2 * Nd) >> 3;
-        const int nbytes = (int)((((int64_t)(lf + ns) * 2 * Nd + 7) >> 3) - first);
-        const uint8_t* pb = a.bits + pg * a.bits_stride + first;
+        int lim = (int)((((int64_t)(lf + ns) * 2 * Nd + 7) >> 3) - first);         // bytes of this item ...
+        const int64_t room = a.bits_stride - first;                                // ... that exist in the row
+        lim = room < lim ? (int)(room < 0 ? 0 : room) : lim;
+        const uint8_t* pb = a.bits + pg * a.bits_stride + first + tid;
 #pragma unroll
-        for (int n = 0; n < NB; ++n) {
-            const int i = tid + n * NT;
-            nb[n] = (i < nbytes && first + i < a.bits_stride) ? __ldg(pb + i) : (uint8_t)0;
-        }
+        for (int n = 0; n < NB; ++n) nb[n] = (tid + n * NT < lim) ? __ldg(pb + n * NT) : (uint8_t)0;
     };
     if constexpr (!KNOWN_SYMBOL) {
         if ((int64_t)blockIdx.x < n_work) fetch_bits(blockIdx.x);
