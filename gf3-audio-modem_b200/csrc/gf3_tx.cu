@@ -225,14 +225,15 @@ struct FrameArgs {
 // is the trailing chirp, OFDM.py:259); segment 0 = the chirp, segments 1 .. 2P = the known symbols
 // before and after the L data symbols (which tx_symbols_kernel writes).  No per-sample index math.
 __global__ void __launch_bounds__(256) tx_frame_kernel(const FrameArgs a) {
-    const unsigned row = blockIdx.x;                                     // grid = (rows, 2P + 1)
-    const int seg = blockIdx.y;
+    const unsigned row = blockIdx.x;                                     // grid = (rows, a few CTAs sharing the 2P + 1 segments)
     const unsigned rows_per_stream = (unsigned)a.pk_per_stream + 1u;
     const int64_t stream = row / rows_per_stream;
     const int pk = (int)(row % rows_per_stream);
-    if (pk == (int)a.pk_per_stream && seg != 0) return;                 // the trailing row is a chirp only
     const int64_t pkt_len = (int64_t)a.chirp_len + (int64_t)(2 * a.P + a.L) * a.symlen;
-    float* o = a.out + stream * a.out_stride + (int64_t)pk * pkt_len;
+    float* const row_out = a.out + stream * a.out_stride + (int64_t)pk * pkt_len;
+    const int nseg = pk == (int)a.pk_per_stream ? 1 : 2 * a.P + 1;      // the trailing row is a chirp only
+    for (int seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
+    float* o = row_out;
     const float* src;
     int n;
     if (seg == 0) { src = a.chirp; n = a.chirp_len; }
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(256) tx_frame_kernel(const FrameArgs a) {
         for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) o[i] = src[i];
     } else {
         for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = src[i];
+    }
     }
 }
 
@@ -270,6 +272,14 @@ int make_chirp(gf3_plan* plan) {
     GF3_LAUNCH_CHECK();
     GF3_CHECK_CUDA(cudaDeviceSynchronize());
     return GF3_OK;
+}
+
+// CTAs per frame row: enough CTAs to fill the GPU a few times over, each looping over its share of
+// the row's 2P + 1 segments (one CTA per 4 KB segment was mostly launch overhead)
+static unsigned frame_grid_y(const gf3_plan* plan, int64_t rows, int64_t nseg) {
+    int64_t gy = ((int64_t)plan->sm_count * 16 + rows - 1) / rows;
+    gy = gy < 1 ? 1 : (gy > nseg ? nseg : gy);
+    return (unsigned)(gy > 65535 ? 65535 : gy);
 }
 
 template <class P>
@@ -309,8 +319,8 @@ static int launch_tx(const gf3_plan* plan, TxArgs a, const float* known, int64_t
         f.chirp_len = p.chirp_len;
         const int64_t rows = n_streams * (a.pk_per_stream + 1);
         const int64_t nseg = 2 * a.P + 1;
-        GF3_REQUIRE(rows <= 0x7fffffff && nseg <= 65535, "tx_modulate: too many packets in one call");
-        tx_frame_kernel<<<dim3((unsigned)rows, (unsigned)nseg), 256, 0, st>>>(f);
+        GF3_REQUIRE(rows <= 0x7fffffff, "tx_modulate: too many packets in one call");
+        tx_frame_kernel<<<dim3((unsigned)rows, frame_grid_y(plan, rows, nseg)), 256, 0, st>>>(f);
         GF3_LAUNCH_CHECK();
     }
     return GF3_OK;
@@ -340,8 +350,8 @@ static int launch_frame_known(const gf3_plan* plan, const float* known, const fl
     f.out_stride = 0;
     const int64_t rows = n_packets + 1;
     const int64_t nseg = 2 * f.P + 1;
-    GF3_REQUIRE(rows <= 0x7fffffff && nseg <= 65535, "tx_frame: too many packets in one call");
-    tx_frame_kernel<<<dim3((unsigned)rows, (unsigned)nseg), 256, 0, st>>>(f);
+    GF3_REQUIRE(rows <= 0x7fffffff, "tx_frame: too many packets in one call");
+    tx_frame_kernel<<<dim3((unsigned)rows, frame_grid_y(plan, rows, nseg)), 256, 0, st>>>(f);
     GF3_LAUNCH_CHECK();
     return GF3_OK;
 }
