@@ -19,6 +19,9 @@
 //   GF3_FLUSH_UNROLL   packed words per unrolled step of the flush
 //   GF3_DEMOD_NATURAL  1: the last FFT pass leaves the spectrum unpadded (no mirrored-read conflicts)
 //   GF3_FUSE_SEQUENTIAL 1: fuse the estimate at N = 4096 too (measured slower: 0.80 vs 0.71 ms on C4)
+//   GF3_DMASK_ONCE     data-carrier mask of a thread's bins: once per CTA (1) or per batch (0); -1 = per plan
+//   GF3_DEMOD_THREADS / GF3_DEMOD11_THREADS / GF3_DEMOD12_THREADS (+ _MINB)  CTA size and CTAs per SM
+//                      for N <= 1024 (128 x 4), N = 2048 (256 x 2), N = 4096 (256 x 2)
 //   GF3_ABL            ablation mask for timing only (1: no bin-pair phase, 2: no FFT, 4: no global
 //                      loads, 8: no code stores); results are wrong with any bit set
 #include <stdlib.h>
