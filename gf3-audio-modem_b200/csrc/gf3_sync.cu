@@ -13,6 +13,14 @@
 #include "gf3_common.cuh"
 #include "gf3_fft.cuh"
 
+// persistent grids of the two matched-filter kernels, in CTAs per SM
+#ifndef GF3_XC_FWD_CTAS
+#define GF3_XC_FWD_CTAS 12
+#endif
+#ifndef GF3_XC_ACC_CTAS
+#define GF3_XC_ACC_CTAS 16
+#endif
+
 namespace gf3 {
 
 using SP = FftPlan<12>;                   // 4096 real samples per block
@@ -416,7 +424,7 @@ static int run_fwd(const float* r, int64_t r_stride, int64_t n_streams, int64_t 
     int64_t gx = (n_streams * nblk + SF - 1) / SF;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    if (gx > (int64_t)sms * 3 * 4) gx = (int64_t)sms * 3 * 4;       // 3 CTAs / SM resident, ~4 work items each at least
+    if (gx > (int64_t)sms * GF3_XC_FWD_CTAS) gx = (int64_t)sms * GF3_XC_FWD_CTAS;   // 2 CTAs / SM resident, several rounds of them
     xcorr_fwd_kernel<<<(unsigned)gx, kSyncThreads, smem, st>>>(f);
     GF3_LAUNCH_CHECK();
     return GF3_OK;
@@ -493,7 +501,7 @@ extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride,
         a.p_stride = p_stride; a.out_len = g.out_len; a.nblk_in = g.nblk_in; a.nblk_out = g.nblk_out; a.parts = plan->sync_parts;
         a.n_work = ns * g.nblk_out;
         int64_t grid = a.n_work;
-        if (grid > (int64_t)plan->sm_count * 4 * 4) grid = (int64_t)plan->sm_count * 4 * 4;
+        if (grid > (int64_t)plan->sm_count * GF3_XC_ACC_CTAS) grid = (int64_t)plan->sm_count * GF3_XC_ACC_CTAS;   // 4 CTAs / SM resident
         xcorr_acc_kernel<<<(unsigned)grid, 128, smem, st>>>(a);
         GF3_LAUNCH_CHECK();
     }
