@@ -20,6 +20,9 @@
 #ifndef GF3_XC_ACC_CTAS
 #define GF3_XC_ACC_CTAS 16
 #endif
+#ifndef GF3_PEAK_PER
+#define GF3_PEAK_PER 24        // positions per thread and round of the one-kernel peak picker (multiple of 4, <= 28)
+#endif
 
 namespace gf3 {
 
@@ -350,14 +353,14 @@ __global__ void __launch_bounds__(256) peak_scan_kernel(const PeakArgs a) {
     if (tid == 0) a.count[stream] = wiped ? 0 : found;
 }
 
-// Single-kernel variant, one CTA per stream walking 4096-position tiles: with hundreds of streams in a
+// Single-kernel variant, one CTA per stream walking 6144-position tiles: with hundreds of streams in a
 // batch the streams themselves supply the parallelism, and one pass over P is cheaper than mark + scan.
-// A round costs one DRAM latency, so it is made wide: every thread takes 16 positions from four
+// A round costs one DRAM latency, so it is made wide: every thread takes 24 positions from six
 // 128-bit loads (tiles start on a 16-byte boundary at or below the walk position; positions behind it
 // are masked), evaluates them without branches, and the CTA agrees on the first candidate with one
 // barrier per round (three result slots in rotation: the slot of round r+2 is cleared in round r).
 __global__ void __launch_bounds__(256) peak_pick_kernel(const PeakArgs a) {
-    constexpr int NT = 256, PER = 16, TILE = NT * PER;
+    constexpr int NT = 256, PER = GF3_PEAK_PER, TILE = NT * PER;
     constexpr long long kNone = 0x7fffffffffffffffLL;
     __shared__ long long s_first[3];
     const int tid = threadIdx.x;
