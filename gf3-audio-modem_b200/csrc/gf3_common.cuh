@@ -63,5 +63,4 @@ struct gf3_plan {
     float2* d_sync_tw;   // twiddles of the sync FFT plan
     float2* d_chirp_spec;  // [sync_parts][NB/2+1] spectrum of the time-reversed chirp partitions
     float* d_chirp;      // [chirp_len] sync chirp
-    float* d_known_time; // [N+cp] scratch: time waveform of the known symbol (tx_modulate; one stream at a time)
 };

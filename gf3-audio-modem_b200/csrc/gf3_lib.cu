@@ -108,15 +108,20 @@ extern "C" int gf3_plan_create(const gf3_params* p, gf3_plan** out) {
     memset(plan, 0, sizeof(*plan));
     plan->p = *p;
     plan->logN = ilog2(p->N);
-    GF3_CHECK_CUDA(cudaGetDevice(&plan->device));
-    GF3_CHECK_CUDA(cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device));
-    rc = upload_twiddles(plan->logN, &plan->d_tw);
-    if (rc) { delete plan; return rc; }
-    const int K = p->N / 2 - 1;
-    std::vector<float2> ones(K, make_float2(1.f, 0.f));
-    GF3_CHECK_CUDA(cudaMalloc(&plan->d_ones, K * sizeof(float2)));
-    GF3_CHECK_CUDA(cudaMemcpy(plan->d_ones, ones.data(), K * sizeof(float2), cudaMemcpyHostToDevice));
-    rc = sync_plan_init(plan);
+    // every failure below goes through gf3_plan_destroy: the handle is zero-initialised, so whatever was
+    // allocated so far is released and nothing else is touched
+    auto fill = [&]() -> int {
+        GF3_CHECK_CUDA(cudaGetDevice(&plan->device));
+        GF3_CHECK_CUDA(cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device));
+        int r = upload_twiddles(plan->logN, &plan->d_tw);
+        if (r) return r;
+        const int K = p->N / 2 - 1;
+        std::vector<float2> ones(K, make_float2(1.f, 0.f));
+        GF3_CHECK_CUDA(cudaMalloc(&plan->d_ones, K * sizeof(float2)));
+        GF3_CHECK_CUDA(cudaMemcpy(plan->d_ones, ones.data(), K * sizeof(float2), cudaMemcpyHostToDevice));
+        return sync_plan_init(plan);
+    };
+    rc = fill();
     if (rc) { gf3_plan_destroy(plan); return rc; }
     *out = plan;
     return GF3_OK;

@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
     pk64 Ure[PP], Uim[PP];                              // per-symbol rotation: e^{-j delta} (exact) or Ure = tan(delta) (fast)
     pk64* const my_slot = reinterpret_cast<pk64*>(zbuf) + tid;   // scratch for p_opaque (zbuf is not in use yet)
     const pk64 pm = p_opaque(pk_pack(make_float2(1.f, -1.f)), my_slot);
+    const pk64 tie_eps = p_opaque(pk_pack(make_float2(__uint_as_float(0x0D800000u), __uint_as_float(0x0D800000u))), my_slot);   // 2^-100
 #pragma unroll
     for (int pp = 0; pp < PP; ++pp) {
         const int j = jb + pp * TB;
@@ -588,8 +589,10 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                                 // 2 X[k] = s + tt, 2 X[M-k] = conj(s - tt): real and imaginary parts of the pair
                                 const pk64 xre = p_fma(p_bc(p_lo(tt)), pm, p_bc(p_lo(sa)));
                                 const pk64 xim = p_fma(p_bc(p_hi(sd)), pm, p_bc(p_hi(tt)));
-                                const pk64 yre_ = p_fma(p_neg(xim), Gim[pp], p_mul(xre, Gre[pp]));
-                                const pk64 yim_ = p_fma(xre, Gim[pp], p_mul(xim, Gre[pp]));
+                                // (the inner products are a * b + (+0): a sum with +0 is never -0, so neither is y -- the
+                                // sign bit of a component is then exactly "component < 0", as the reference's argmin needs)
+                                const pk64 yre_ = p_fma(p_neg(xim), Gim[pp], p_fma(xre, Gre[pp], 0ull));
+                                const pk64 yim_ = p_fma(xre, Gim[pp], p_fma(xim, Gre[pp], 0ull));
                                 if constexpr (!KNOWN_CH) {
                                     const pk64 gr = Gre[pp];
                                     if constexpr (FAST) {                          // G *= 1 - j tan(delta)
@@ -602,9 +605,13 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                                 }
                                 const float2 yre = pk_unpack(yre_), yim = pk_unpack(yim_);
                                 if constexpr (BITS) {
-                                    // code = 2 * (imag < 0) + (real < 0)  (OFDM.py:484-500 reduced to sign tests)
-                                    sts_u8_if(sp1[pp] + soff, __funnelshift_l(__float_as_uint(yre.x), __float_as_uint(yim.x) >> 31, 1), dmask & (1u << (2 * pp)));
-                                    sts_u8_if(sp2[pp] + soff, __funnelshift_l(__float_as_uint(yre.y), __float_as_uint(yim.y) >> 31, 1), dmask & (2u << (2 * pp)));
+                                    // OFDM.py:484-500: argmin over [(0,0),(1,0),(1,1),(0,1)] keeps the FIRST minimum, i.e.
+                                    //   b1 = real < 0,  b0 = imag < 0 or (imag == 0 and real < 0)   (first-minimum rule, pinned on exact ties by the tests).
+                                    // tie = imag + real * 2^-100 has the sign of imag unless imag is exactly zero, where it takes
+                                    // the sign of real (an underflow to -0 keeps the sign bit); y itself is never -0 (above).
+                                    const float2 tie = pk_unpack(p_fma(yre_, tie_eps, yim_));
+                                    sts_u8_if(sp1[pp] + soff, __funnelshift_l(__float_as_uint(yre.x), __float_as_uint(tie.x) >> 31, 1), dmask & (1u << (2 * pp)));
+                                    sts_u8_if(sp2[pp] + soff, __funnelshift_l(__float_as_uint(yre.y), __float_as_uint(tie.y) >> 31, 1), dmask & (2u << (2 * pp)));
                                 }
                                 if constexpr (WANT_EQ) {
                                     const int k = (int)(sp1[pp] - st0), km = M - k;

@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256) peak_pick_kernel(const PeakArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static int run_fwd(const float* r, int64_t r_stride, int64_t n_streams, int64_t T, int nblk, int reverse,
+static int run_fwd(const gf3_plan* plan, const float* r, int64_t r_stride, int64_t n_streams, int64_t T, int nblk, int reverse,
                    int in_off, int valid_len, float2* spec, const float2* tw, float* pmax, cudaStream_t st) {
     constexpr int SF = kSyncThreads / SP::T;
     FwdArgs f;
@@ -425,8 +425,7 @@ static int run_fwd(const float* r, int64_t r_stride, int64_t n_streams, int64_t 
     const size_t smem = (size_t)(SF * SP::MP + SP::TW_TOTAL) * sizeof(float2);
     GF3_CHECK_CUDA(cudaFuncSetAttribute(xcorr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t gx = (n_streams * nblk + SF - 1) / SF;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = plan->sm_count;
     if (gx > (int64_t)sms * GF3_XC_FWD_CTAS) gx = (int64_t)sms * GF3_XC_FWD_CTAS;   // 2 CTAs / SM resident, several rounds of them
     xcorr_fwd_kernel<<<(unsigned)gx, kSyncThreads, smem, st>>>(f);
     GF3_LAUNCH_CHECK();
@@ -443,7 +442,7 @@ int sync_plan_init(gf3_plan* plan) {
     else { rc = upload_twiddles(SP::LOGN, &plan->d_sync_tw); if (rc) return rc; }
     GF3_CHECK_CUDA(cudaMalloc(&plan->d_chirp_spec, (size_t)plan->sync_parts * SP::M * sizeof(float2)));
     // H_p = rfft_{2B}([h[pB .. pB+B), 0 ... 0]),  h[m] = chirp[Lc-1-m]  (fsweep of OFDM.py:357)
-    rc = run_fwd(plan->d_chirp, 0, 1, p.chirp_len, plan->sync_parts, 1, kB, kB, plan->d_chirp_spec,
+    rc = run_fwd(plan, plan->d_chirp, 0, 1, p.chirp_len, plan->sync_parts, 1, kB, kB, plan->d_chirp_spec,
                  plan->d_sync_tw, nullptr, 0);
     if (rc) return rc;
     GF3_CHECK_CUDA(cudaDeviceSynchronize());
@@ -454,8 +453,7 @@ void sync_plan_free(gf3_plan* plan) {
     if (plan->d_sync_tw && plan->d_sync_tw != plan->d_tw) cudaFree(plan->d_sync_tw);
     if (plan->d_chirp_spec) cudaFree(plan->d_chirp_spec);
     if (plan->d_chirp) cudaFree(plan->d_chirp);
-    if (plan->d_known_time) cudaFree(plan->d_known_time);
-    plan->d_sync_tw = nullptr; plan->d_chirp_spec = nullptr; plan->d_chirp = nullptr; plan->d_known_time = nullptr;
+    plan->d_sync_tw = nullptr; plan->d_chirp_spec = nullptr; plan->d_chirp = nullptr;
 }
 
 struct XcorrGeom { int nblk_out, nblk_in; int64_t out_len; size_t per_stream; int64_t tile; };
@@ -497,7 +495,7 @@ extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride,
     GF3_CHECK_CUDA(cudaFuncSetAttribute(xcorr_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t s0 = 0; s0 < n_streams; s0 += g.tile) {
         const int64_t ns = (n_streams - s0 < g.tile) ? n_streams - s0 : g.tile;
-        int rc = run_fwd(r + s0 * r_stride, r_stride, ns, T, g.nblk_in, 0, 0, 2 * kB, spec, plan->d_sync_tw, pmax + s0, st);
+        int rc = run_fwd(plan, r + s0 * r_stride, r_stride, ns, T, g.nblk_in, 0, 0, 2 * kB, spec, plan->d_sync_tw, pmax + s0, st);
         if (rc) return rc;
         AccArgs a;
         a.spec = spec; a.H = plan->d_chirp_spec; a.tw = plan->d_sync_tw; a.P = P + s0 * p_stride; a.pmax = pmax + s0;

@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(256) tx_frame_kernel(const FrameArgs a) {
         o += a.chirp_len + (int64_t)slot * a.symlen;
         src = a.known_time;
         n = a.symlen;
+        if (o == src) continue;                                         // the slot the waveform was computed into
     }
     if (((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
         const int n4 = n >> 2;
@@ -282,13 +283,17 @@ static unsigned frame_grid_y(const gf3_plan* plan, int64_t rows, int64_t nseg) {
     return (unsigned)(gy > 65535 ? 65535 : gy);
 }
 
+// The known symbol's time waveform is computed once per call straight into the FIRST known-symbol slot
+// of the output (stream 0, packet 0) and copied from there into every other slot by tx_frame_kernel:
+// no scratch in the (immutable, shareable) plan, so concurrent calls on different streams do not meet.
 template <class P>
-static int launch_tx(const gf3_plan* plan, TxArgs a, const float* known, int64_t n_streams, float* known_time, cudaStream_t st) {
+static int launch_tx(const gf3_plan* plan, TxArgs a, const float* known, int64_t n_streams, cudaStream_t st) {
+    float* const known_time = a.out + a.chirp_len;
     constexpr int SF = kTxThreads / P::T;
     const gf3_params& p = plan->p;
     const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)(P::R / 4 + 1) * kTxThreads + 16;   // staged bits: NB bytes per thread
-    // 1. the known symbol's time waveform (one symbol, gain applied) into scratch
-    {
+    // 1. the known symbol's time waveform (one symbol, gain applied)
+    if (a.P > 0 && a.pk_per_stream > 0) {
         TxArgs k = a;
         k.bits = nullptr; k.known = reinterpret_cast<const float2*>(known); k.out = known_time;
         auto kern = tx_symbols_kernel<P, true>;
@@ -330,7 +335,8 @@ static int launch_tx(const gf3_plan* plan, TxArgs a, const float* known, int64_t
 // trailing sync, with the caller's own sync waveform (OFDM.py:244-259).
 template <class P>
 static int launch_frame_known(const gf3_plan* plan, const float* known, const float* sync, int sync_len,
-                              int64_t n_packets, float* out, float* known_time, cudaStream_t st) {
+                              int64_t n_packets, float* out, cudaStream_t st) {
+    float* const known_time = out + sync_len;      // first known-symbol slot of the frame (see launch_tx)
     constexpr int SF = kTxThreads / P::T;
     const gf3_params& p = plan->p;
     const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)(P::R / 4 + 1) * kTxThreads + 16;   // staged bits: NB bytes per thread
@@ -339,10 +345,12 @@ static int launch_frame_known(const gf3_plan* plan, const float* known, const fl
     k.known = reinterpret_cast<const float2*>(known); k.tw = plan->d_tw; k.out = known_time;
     k.cp = p.cp; k.lo = p.lo; k.hi = p.hi; k.P = p.n_pilots; k.L = p.packet_len; k.chirp_len = sync_len;
     k.gain = p.tx_gain / (float)p.N;
-    auto kern = tx_symbols_kernel<P, true>;
-    GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<1, kTxThreads, smem, st>>>(k);
-    GF3_LAUNCH_CHECK();
+    if (p.n_pilots > 0 && n_packets > 0) {
+        auto kern = tx_symbols_kernel<P, true>;
+        GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<1, kTxThreads, smem, st>>>(k);
+        GF3_LAUNCH_CHECK();
+    }
     FrameArgs f;
     f.chirp = sync; f.known_time = known_time; f.out = out;
     f.pk_per_stream = n_packets; f.n_streams = 1; f.symlen = p.N + p.cp; f.P = p.n_pilots; f.L = p.packet_len;
@@ -358,20 +366,14 @@ static int launch_frame_known(const gf3_plan* plan, const float* known, const fl
 
 int tx_frame_known(const gf3_plan* plan, const float* known, const float* sync, int sync_len, int64_t n_packets,
                    float* out, cudaStream_t st) {
-    const gf3_params& p = plan->p;
-    float* known_time = const_cast<gf3_plan*>(plan)->d_known_time;
-    if (!known_time) {
-        GF3_CHECK_CUDA(cudaMalloc(&known_time, (size_t)(p.N + p.cp) * sizeof(float)));
-        const_cast<gf3_plan*>(plan)->d_known_time = known_time;
-    }
     switch (plan->logN) {
-        case 6: return launch_frame_known<FftPlan<6>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
-        case 7: return launch_frame_known<FftPlan<7>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
-        case 8: return launch_frame_known<FftPlan<8>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
-        case 9: return launch_frame_known<FftPlan<9>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
-        case 10: return launch_frame_known<FftPlan<10>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
-        case 11: return launch_frame_known<FftPlan<11>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
-        case 12: return launch_frame_known<FftPlan<12>>(plan, known, sync, sync_len, n_packets, out, known_time, st);
+        case 6: return launch_frame_known<FftPlan<6>>(plan, known, sync, sync_len, n_packets, out, st);
+        case 7: return launch_frame_known<FftPlan<7>>(plan, known, sync, sync_len, n_packets, out, st);
+        case 8: return launch_frame_known<FftPlan<8>>(plan, known, sync, sync_len, n_packets, out, st);
+        case 9: return launch_frame_known<FftPlan<9>>(plan, known, sync, sync_len, n_packets, out, st);
+        case 10: return launch_frame_known<FftPlan<10>>(plan, known, sync, sync_len, n_packets, out, st);
+        case 11: return launch_frame_known<FftPlan<11>>(plan, known, sync, sync_len, n_packets, out, st);
+        case 12: return launch_frame_known<FftPlan<12>>(plan, known, sync, sync_len, n_packets, out, st);
         default: gf3::set_error("unsupported N"); return GF3_ERR_INVALID;
     }
 }
@@ -408,23 +410,16 @@ extern "C" int gf3_tx_modulate(const gf3_plan* plan, const uint8_t* bits_packed,
     a.cp = p.cp; a.lo = p.lo; a.hi = p.hi; a.P = p.n_pilots; a.L = p.packet_len; a.chirp_len = p.chirp_len;
     a.gain = p.tx_gain / (float)p.N;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // scratch for the known symbol lives in the plan-independent per-call tail of `out`? No: keep
-    // it inside the plan (allocated lazily, one symbol).
-    float* known_time = const_cast<gf3_plan*>(plan)->d_known_time;
-    if (!known_time) {
-        GF3_CHECK_CUDA(cudaMalloc(&known_time, (size_t)(p.N + p.cp) * sizeof(float)));
-        const_cast<gf3_plan*>(plan)->d_known_time = known_time;
-    }
     if (pk_per_stream == 0) a.L = 0;
     a.pk_per_stream = pk_per_stream;
     switch (plan->logN) {
-        case 6: return launch_tx<FftPlan<6>>(plan, a, known, n_streams, known_time, st);
-        case 7: return launch_tx<FftPlan<7>>(plan, a, known, n_streams, known_time, st);
-        case 8: return launch_tx<FftPlan<8>>(plan, a, known, n_streams, known_time, st);
-        case 9: return launch_tx<FftPlan<9>>(plan, a, known, n_streams, known_time, st);
-        case 10: return launch_tx<FftPlan<10>>(plan, a, known, n_streams, known_time, st);
-        case 11: return launch_tx<FftPlan<11>>(plan, a, known, n_streams, known_time, st);
-        case 12: return launch_tx<FftPlan<12>>(plan, a, known, n_streams, known_time, st);
+        case 6: return launch_tx<FftPlan<6>>(plan, a, known, n_streams, st);
+        case 7: return launch_tx<FftPlan<7>>(plan, a, known, n_streams, st);
+        case 8: return launch_tx<FftPlan<8>>(plan, a, known, n_streams, st);
+        case 9: return launch_tx<FftPlan<9>>(plan, a, known, n_streams, st);
+        case 10: return launch_tx<FftPlan<10>>(plan, a, known, n_streams, st);
+        case 11: return launch_tx<FftPlan<11>>(plan, a, known, n_streams, st);
+        case 12: return launch_tx<FftPlan<12>>(plan, a, known, n_streams, st);
         default: gf3::set_error("unsupported N"); return GF3_ERR_INVALID;
     }
 }

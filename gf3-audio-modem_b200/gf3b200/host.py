@@ -24,6 +24,7 @@ class HostReceiver:
             self.d_pcm = [torch.empty((self.chunk, phy.pkt_samples), dtype=sample_dtype, device=phy.device) for _ in self.streams]
         self.d_out = [torch.empty((self.chunk, phy.bits_stride), dtype=torch.uint8, device=phy.device) for _ in self.streams]
         self.h_out = torch.empty((n_packets, phy.bits_stride), dtype=torch.uint8).pin_memory()
+        self._done = torch.cuda.Event()
         self.h2d_bytes = n_packets * phy.pkt_samples * torch.empty((), dtype=sample_dtype).element_size()
         self.d2h_bytes = n_packets * phy.bits_stride
 
@@ -47,4 +48,7 @@ class HostReceiver:
                 self.h_out[p0:p0 + n].copy_(self.d_out[k][:n], non_blocking=True)
         for s in self.streams:
             cur.wait_stream(s)
+        # the result is returned as finished host memory: wait for the last device-to-host copy
+        self._done.record(cur)
+        self._done.synchronize()
         return self.h_out

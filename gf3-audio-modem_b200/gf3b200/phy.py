@@ -42,8 +42,7 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+_STREAM = object()      # placeholder for "the current CUDA stream of the plan's device" in Phy._call
 
 
 class Phy:
@@ -58,7 +57,7 @@ class Phy:
                                 "no CUDA device: the GF3 B200 physical layer has no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         p = Gf3Params()
-        check(self.lib.gf3_params_default(ctypes.byref(p), N, cp, lo, hi, n_pilots, packet_len))
+        check(self._call("gf3_params_default", ctypes.byref(p), N, cp, lo, hi, n_pilots, packet_len))
         for name, val in (("fit_lo", fit_lo), ("fit_hi", fit_hi), ("chirp_len", chirp_len),
                           ("thresh", thresh), ("fs", fs), ("f0", f0), ("f1", f1)):
             if val is not None:
@@ -76,7 +75,7 @@ class Phy:
         self.bits_stride = ((self.bits_per_packet + 31) // 32 * 4 + 15) // 16 * 16
         self._plan = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            check(self.lib.gf3_plan_create(ctypes.byref(p), ctypes.byref(self._plan)))
+            check(self._call("gf3_plan_create", ctypes.byref(p), ctypes.byref(self._plan)))
         ks = default_known_sequence() if known_sequence is None else np.asarray(known_sequence).astype(np.int64)
         if len(ks) < 2 * self.K:
             raise ValueError("known_sequence needs at least 2K = %d bits" % (2 * self.K))
@@ -97,6 +96,14 @@ class Phy:
             pass
 
     # ------------------------------------------------------------------ helpers
+    def _call(self, name, *args):
+        """Call a library entry point with the plan's device current (kernels launch on the device that
+        owns the plan's tables and the caller's tensors, whatever torch's current device is) and
+        _STREAM replaced by that device's current stream."""
+        with torch.cuda.device(self.device):
+            st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            return getattr(self.lib, name)(*[st if a is _STREAM else a for a in args])
+
     def _f32(self, t):
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "need contiguous float32 CUDA tensor"
         return t
@@ -115,8 +122,8 @@ class Phy:
         Hs = torch.empty((n_packets, self.K), dtype=torch.complex64, device=self.device)
         He = torch.empty_like(Hs)
         slope = torch.empty((n_packets,), dtype=torch.float64, device=self.device)
-        check(self.lib.gf3_rx_estimate(self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(self.known),
-                                       _ptr(Hs), _ptr(He), _ptr(slope), _stream()))
+        check(self._call("gf3_rx_estimate", self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(self.known),
+                                       _ptr(Hs), _ptr(He), _ptr(slope), _STREAM))
         return Hs, He, slope
 
     def rx_demod(self, samples, n_packets, Hs, He, slope, pkt_offset=None, xor=True, want_eq=False,
@@ -127,8 +134,8 @@ class Phy:
         off = self._offsets(pkt_offset, n_packets)
         bits = out if out is not None else torch.empty((n_packets, self.bits_stride), dtype=torch.uint8, device=self.device)
         eq = torch.empty((n_packets, self.L, self.K), dtype=torch.complex64, device=self.device) if want_eq else None
-        check(self.lib.gf3_rx_demod(self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(Hs), _ptr(He), _ptr(slope),
-                                    _ptr(self.xor2) if xor else None, _ptr(bits), self.bits_stride, _ptr(eq), _stream()))
+        check(self._call("gf3_rx_demod", self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(Hs), _ptr(He), _ptr(slope),
+                                    _ptr(self.xor2) if xor else None, _ptr(bits), self.bits_stride, _ptr(eq), _STREAM))
         return (bits, eq) if want_eq else bits
 
     def rx_known_channel(self, samples, n_packets, Hinv, pkt_offset=None, xor=False, want_eq=False):
@@ -138,8 +145,8 @@ class Phy:
         assert Hinv.is_cuda and Hinv.dtype == torch.complex64 and Hinv.numel() == self.K
         bits = torch.empty((n_packets, self.bits_stride), dtype=torch.uint8, device=self.device)
         eq = torch.empty((n_packets, self.L, self.K), dtype=torch.complex64, device=self.device) if want_eq else None
-        check(self.lib.gf3_rx_known_channel(self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(Hinv.contiguous()),
-                                            _ptr(self.xor2) if xor else None, _ptr(bits), self.bits_stride, _ptr(eq), _stream()))
+        check(self._call("gf3_rx_known_channel", self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(Hinv.contiguous()),
+                                            _ptr(self.xor2) if xor else None, _ptr(bits), self.bits_stride, _ptr(eq), _STREAM))
         return (bits, eq) if want_eq else bits
 
     def spectrum(self, samples, n_symbols, sym_offset=None):
@@ -147,7 +154,7 @@ class Phy:
         self._f32(samples)
         off = self._offsets(sym_offset, n_symbols)
         out = torch.empty((n_symbols, self.K), dtype=torch.complex64, device=self.device)
-        check(self.lib.gf3_rx_spectrum(self._plan, _ptr(samples), _ptr(off), n_symbols, _ptr(out), _stream()))
+        check(self._call("gf3_rx_spectrum", self._plan, _ptr(samples), _ptr(off), n_symbols, _ptr(out), _STREAM))
         return out
 
     def unpack_bits(self, packed, n_packets=None):
@@ -159,7 +166,7 @@ class Phy:
     # ------------------------------------------------------------------ synchronisation
     def sync_chirp(self):
         out = torch.empty((self.chirp_len,), dtype=torch.float32, device=self.device)
-        check(self.lib.gf3_sync_chirp(self._plan, _ptr(out), _stream()))
+        check(self._call("gf3_sync_chirp", self._plan, _ptr(out), _STREAM))
         return out
 
     def xcorr(self, r):
@@ -173,7 +180,7 @@ class Phy:
         pmax = torch.empty((B,), dtype=torch.float32, device=self.device)
         wb = int(self.lib.gf3_xcorr_work_bytes(self._plan, B, T))
         work = torch.empty((wb,), dtype=torch.uint8, device=self.device)
-        check(self.lib.gf3_xcorr(self._plan, _ptr(r), T, B, T, _ptr(P), pstride, _ptr(pmax), _ptr(work), _stream()))
+        check(self._call("gf3_xcorr", self._plan, _ptr(r), T, B, T, _ptr(P), pstride, _ptr(pmax), _ptr(work), _STREAM))
         return P[:, :plen], pmax
 
     def peak_pick(self, P, pmax, T, max_peaks=64):
@@ -183,8 +190,8 @@ class Phy:
         peaks = torch.full((B, max_peaks), -1, dtype=torch.int64, device=self.device)
         count = torch.empty((B,), dtype=torch.int32, device=self.device)
         work = torch.empty((max(1, int(self.lib.gf3_peak_pick_work_bytes(self._plan, B, T))),), dtype=torch.uint8, device=self.device)
-        check(self.lib.gf3_peak_pick(self._plan, _ptr(P), P.stride(0), B, T, _ptr(pmax), _ptr(peaks), max_peaks,
-                                     _ptr(count), _ptr(work), _stream()))
+        check(self._call("gf3_peak_pick", self._plan, _ptr(P), P.stride(0), B, T, _ptr(pmax), _ptr(peaks), max_peaks,
+                                     _ptr(count), _ptr(work), _STREAM))
         return peaks, count
 
     # ------------------------------------------------------------------ transmit chain
@@ -203,8 +210,8 @@ class Phy:
         tstride = (T + 3) // 4 * 4
         if out is None:
             out = torch.empty((n_streams, tstride), dtype=torch.float32, device=self.device)
-        check(self.lib.gf3_tx_modulate(self._plan, _ptr(bits_packed), stride, _ptr(filler), _ptr(self.known),
-                                       n_streams, pk_per_stream, _ptr(out), out.stride(0), _stream()))
+        check(self._call("gf3_tx_modulate", self._plan, _ptr(bits_packed), stride, _ptr(filler), _ptr(self.known),
+                                       n_streams, pk_per_stream, _ptr(out), out.stride(0), _STREAM))
         return out[:, :T]
 
     # ------------------------------------------------------------------ channel + counters
@@ -215,13 +222,13 @@ class Phy:
         taps = taps.to(torch.float32).contiguous()
         y = torch.empty((B, (T + 3) // 4 * 4), dtype=torch.float32, device=self.device)
         sg = sigma.to(torch.float32).contiguous() if sigma is not None else None
-        check(self.lib.gf3_channel_sim(_ptr(x), x.stride(0), B, T, _ptr(taps), taps.shape[1], _ptr(sg),
-                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(y), y.stride(0), _stream()))
+        check(self._call("gf3_channel_sim", _ptr(x), x.stride(0), B, T, _ptr(taps), taps.shape[1], _ptr(sg),
+                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(y), y.stride(0), _STREAM))
         return y[:, :T]
 
     def ber_count(self, a, b, nbits, counter):
         """counter (int64/uint64 [2]) += (bit errors, bits) between two packed rows."""
-        check(self.lib.gf3_ber_count(_ptr(a), _ptr(b), nbits, _ptr(counter), _stream()))
+        check(self._call("gf3_ber_count", _ptr(a), _ptr(b), nbits, _ptr(counter), _STREAM))
         return counter
 
     def pcm_to_f32(self, pcm, out=None):
@@ -229,7 +236,7 @@ class Phy:
         assert pcm.is_cuda and pcm.is_contiguous() and pcm.dtype in (torch.uint8, torch.int16)
         if out is None:
             out = torch.empty(pcm.shape, dtype=torch.float32, device=self.device)
-        check(self.lib.gf3_pcm_to_f32(_ptr(pcm), 0 if pcm.dtype == torch.uint8 else 1, pcm.numel(), _ptr(out), _stream()))
+        check(self._call("gf3_pcm_to_f32", _ptr(pcm), 0 if pcm.dtype == torch.uint8 else 1, pcm.numel(), _ptr(out), _STREAM))
         return out
 
     # ------------------------------------------------------------------ stage-level methods
@@ -242,8 +249,8 @@ class Phy:
         Hs = torch.empty((n, self.K), dtype=torch.complex64, device=self.device)
         He = torch.empty_like(Hs)
         slope = torch.empty((n,), dtype=torch.float64, device=self.device)
-        check(self.lib.gf3_eq_estimate(self._plan, _ptr(start), _ptr(end), n, _ptr(self.known), _ptr(Hs), _ptr(He),
-                                       _ptr(slope), _stream()))
+        check(self._call("gf3_eq_estimate", self._plan, _ptr(start), _ptr(end), n, _ptr(self.known), _ptr(Hs), _ptr(He),
+                                       _ptr(slope), _STREAM))
         return Hs, He, slope
 
     def eq_apply(self, data, Hs, He, slope, want_hest=True):
@@ -253,8 +260,8 @@ class Phy:
         n = data.shape[0]
         eq = torch.empty_like(data)
         hest = torch.empty_like(data) if want_hest else None
-        check(self.lib.gf3_eq_apply(self._plan, _ptr(data), n, _ptr(Hs.contiguous()), _ptr(He.contiguous()),
-                                    _ptr(slope.contiguous()), _ptr(eq), _ptr(hest), _stream()))
+        check(self._call("gf3_eq_apply", self._plan, _ptr(data), n, _ptr(Hs.contiguous()), _ptr(He.contiguous()),
+                                    _ptr(slope.contiguous()), _ptr(eq), _ptr(hest), _STREAM))
         return (eq, hest) if want_hest else eq
 
     def demap(self, symbols, want_hard=True):
@@ -263,7 +270,7 @@ class Phy:
         n = symbols.numel()
         bits = torch.empty(symbols.shape + (2,), dtype=torch.uint8, device=self.device)
         hard = torch.empty_like(symbols) if want_hard else None
-        check(self.lib.gf3_demap(_ptr(symbols), n, _ptr(bits), _ptr(hard), _stream()))
+        check(self._call("gf3_demap", _ptr(symbols), n, _ptr(bits), _ptr(hard), _STREAM))
         return (bits, hard) if want_hard else bits
 
     def tx_frame(self, data_time, sync):
@@ -274,7 +281,7 @@ class Phy:
         n = data_time.shape[0]
         ls = sync.numel()
         out = torch.empty((n * (ls + self.pkt_samples) + ls,), dtype=torch.float32, device=self.device)
-        check(self.lib.gf3_tx_frame(self._plan, _ptr(data_time), n, _ptr(sync), ls, _ptr(self.known), _ptr(out), _stream()))
+        check(self._call("gf3_tx_frame", self._plan, _ptr(data_time), n, _ptr(sync), ls, _ptr(self.known), _ptr(out), _STREAM))
         return out
 
     # ------------------------------------------------------------------ whole receive chain
@@ -288,9 +295,9 @@ class Phy:
         slope = torch.empty((n_packets,), dtype=torch.float64, device=self.device)
         bits = out if out is not None else torch.empty((n_packets, self.bits_stride), dtype=torch.uint8, device=self.device)
         eq = torch.empty((n_packets, self.L, self.K), dtype=torch.complex64, device=self.device) if want_eq else None
-        check(self.lib.gf3_rx_receive(self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(self.known), _ptr(Hs), _ptr(He),
+        check(self._call("gf3_rx_receive", self._plan, _ptr(samples), _ptr(off), n_packets, _ptr(self.known), _ptr(Hs), _ptr(He),
                                       _ptr(slope), _ptr(self.xor2) if xor else None, _ptr(bits), self.bits_stride, _ptr(eq),
-                                      _stream()))
+                                      _STREAM))
         return ((bits, eq) if want_eq else bits), Hs, He, slope
 
     def receive_packets(self, samples, n_packets, pkt_offset=None, xor=True, want_eq=False):

@@ -11,6 +11,9 @@ Fixtures (all outputs are the reference's own, produced under oracle/ref_shim.py
                     (attribute-patched N / CP / bins; int16-quantised channel output as input)
   kat3_weekend.npz  Weekend-Challenge artefacts: channel taps + the decoded output file
   sync_quirk.npz    chirp_method end-of-signal wipe-out quirk (OFDM.py:366-370)
+  kat4_gr5ch2.npz   BASELINE.json configs[1]: the reference transmits
+                    input_Files/gr5ch2.wav (mode A2, XOR, seeded), Handouts/gr5channel.csv FIR + seeded
+                    AWGN + int16 quantisation, reference receive(): 29 packets / 28.2 M samples
 """
 import hashlib
 import os
@@ -182,6 +185,72 @@ def kat3():
     print("kat3: y5tv9o.wav", len(wav), "bytes; channel", len(h), "taps")
 
 
+KAT4_SEED, KAT4_NOISE_SEED, KAT4_SNR_DB, KAT4_LEAD, KAT4_TRAIL, KAT4_FULL_SCALE = 2020, 4, 25.0, 4321, 777, 20000.0
+
+
+def kat4_signal(tx, h, seed=KAT4_NOISE_SEED):
+    """The KAT-4 channel: gr5channel.csv FIR, lead-in / trailing silence, seeded AWGN, int16 PCM.
+    (tests/test_oracle_golden.py repeats these lines on the oracle's transmit() output.)"""
+    from scipy.signal import lfilter
+    y = lfilter(h, 1.0, tx)
+    y = np.concatenate([np.zeros(KAT4_LEAD), y, np.zeros(KAT4_TRAIL)])
+    rng = np.random.default_rng(seed)
+    sp = np.mean(y[KAT4_LEAD:KAT4_LEAD + len(tx)] ** 2)
+    y = y + rng.normal(0.0, np.sqrt(sp / 10 ** (KAT4_SNR_DB / 10)), len(y))
+    scale = KAT4_FULL_SCALE / np.max(np.abs(y))
+    return np.round(y * scale).astype(np.int16)
+
+
+def kat4():
+    """configs[1]: chirp-synchronised decode of a long recording with the channel estimated from the
+    known symbols, every stage run by the UNMODIFIED reference (OFDM.py:296-343, 581-657)."""
+    import time
+    ref = ref_shim.load()
+    payload = np.fromfile(os.path.join(ref_shim.REF_ROOT, "input_Files", "gr5ch2.wav"), dtype=np.uint8)
+    h = np.loadtxt(os.path.join(ref_shim.REF_ROOT, "Handouts", "gr5channel.csv"))
+    tx = ref_shim.make("transmitter", "A2", "XOR")
+    rx = ref_shim.make("receiver", "A2", "XOR")
+    with ref_shim.quiet():
+        bits_in = ref.load_file("gr5ch2.wav")
+    np.random.seed(KAT4_SEED)
+    t0 = time.time()
+    with ref_shim.quiet():
+        sig = tx.transmit(bits_in)
+    t_tx = time.time() - t0
+    assert tx.no_packets == 29 and len(sig) == 29 * 972000 + 21600, (tx.no_packets, len(sig))
+    r_i16 = kat4_signal(sig, h)
+    r = r_i16.astype(np.float64)
+    t0 = time.time()
+    st = run_receive_stages(rx, r)
+    t_rx = time.time() - t0
+    peaks = np.where(st["zeros"])[0]
+    assert len(peaks) == 30 and st["rx_cp"].shape[0] == 29
+    nerr = int(np.sum(st["bits"][: len(bits_in)] != bits_in))
+    packed = np.packbits(st["bits"])
+    eq_d = st["eq"][:, rx.data_carriers - 1]
+    margin = np.minimum(np.abs(eq_d.real), np.abs(eq_d.imag))
+    near5 = np.argwhere(margin < 1e-5)
+    near4 = np.argwhere(margin < 1e-4)
+    rows = np.arange(0, st["eq"].shape[0], 388)                      # strided sample of the constellation
+    with ref_shim.quiet():
+        name, data = ref.save_file(st["bits"])
+    np.savez_compressed(
+        os.path.join(OUT, "kat4_gr5ch2.npz"),
+        payload=payload, gr5channel=h, seed=KAT4_SEED, noise_seed=KAT4_NOISE_SEED,
+        tx_sha256=hashlib.sha256(sig.astype(np.float32).tobytes()).hexdigest(),
+        r_sha256=hashlib.sha256(r_i16.tobytes()).hexdigest(), n_samples=len(r_i16),
+        peaks=peaks, slope=st["slope"], Hs0=st["Hs"][0], He28=st["He"][28],
+        eq_rows=rows, eq_sel=st["eq"][rows].astype(np.complex128),
+        bits_sha256=hashlib.sha256(packed.tobytes()).hexdigest(), n_bits=len(st["bits"]),
+        near_1e5=near5, near_1e4=near4, n_bit_errors=nerr, n_bits_in=len(bits_in),
+        file_name=name, file_errors=int(np.sum(data != payload[: len(data)])) if len(data) == len(payload) else -1,
+        ref_seconds=np.array([t_tx, t_rx]),
+    )
+    print("kat4: %d samples, peaks %s..%s, slopes %.6f..%.6f, %d bit errors of %d, near-boundary <1e-5: %d, <1e-4: %d; "
+          "reference transmit %.1f s, receive %.1f s" % (len(r_i16), peaks[:2], peaks[-1], st["slope"].min(), st["slope"].max(),
+                                                         nerr, len(bits_in), len(near5), len(near4), t_tx, t_rx))
+
+
 def sync_quirk():
     """A signal whose final chirp ends < 2 samples before the end: the reference wipes all
     detections (OFDM.py:366-370); with >= 2 trailing samples it keeps them."""
@@ -204,7 +273,7 @@ def sync_quirk():
 if __name__ == "__main__":
     assert ref_shim.available(), "reference not found"
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["kat1", "stage", "kat3", "quirk"]
+    which = sys.argv[1:] or ["kat1", "stage", "kat3", "quirk", "kat4"]
     if "kat1" in which:
         kat1()
     if "stage" in which:
@@ -214,5 +283,7 @@ if __name__ == "__main__":
         kat3()
     if "quirk" in which:
         sync_quirk()
+    if "kat4" in which:
+        kat4()
     for f in sorted(os.listdir(OUT)):
         print("%-24s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

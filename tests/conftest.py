@@ -35,3 +35,33 @@ def oracle_params(cfg, known_sequence, encoding="XOR"):
 
 
 STAGE_NAMES = ["w1024", "a2_4096", "b1_4096", "n2048"]
+
+
+# ----------------------------------------------------------------------------- decision-boundary policy
+from oracle.parity import BOUNDARY_TOL, classify_bit_diffs  # noqa: E402,F401  (policy and wording: oracle/parity.py)
+
+
+def assert_bits_match(got, ref_bits, ref_eq_data, what):
+    """Bit-exact except decisions within BOUNDARY_TOL of a boundary; those are counted and printed."""
+    c = classify_bit_diffs(got, ref_bits, ref_eq_data)
+    print("%s: %d bits, %d differ (%d within 1e-5 of a boundary, %d within 1e-5*|point|, %d beyond; worst margin %.2e); "
+          "%d oracle points lie within 1e-5 of a boundary" % (what, c["n_bits"], c["n_diff"], c["near_1e5"], c["near_scaled"],
+                                                              c["beyond"], c["worst_margin"], c["n_points_near_1e5"]))
+    assert c["beyond"] == 0, "%s: %d bit mismatches away from decision boundaries (worst margin %.3e)" % (what, c["beyond"], c["worst_margin"])
+    return c
+
+
+def kat4_regenerate(g, known_sequence):
+    """KAT-4 input (BASELINE.json configs[1]): the oracle's pinned transmit() of the golden payload with the
+    golden seed, then the same channel as oracle/make_golden.py -> int16 recording.  The fixture's
+    sha256 of the reference-made recording pins the regeneration."""
+    import hashlib
+    from oracle import gf3_oracle as orc
+    from oracle.make_golden import kat4_signal
+    p = orc.Params.from_mode("A2", known_sequence=known_sequence, encoding="XOR")
+    bits_in = orc.load_file_bits("gr5ch2.wav", g["payload"])
+    np.random.seed(int(g["seed"]))
+    tx = orc.transmit(p, bits_in)
+    r = kat4_signal(tx, g["gr5channel"], int(g["noise_seed"]))
+    assert hashlib.sha256(r.tobytes()).hexdigest() == str(g["r_sha256"]), "KAT-4 recording differs from the reference-made one"
+    return p, bits_in, r

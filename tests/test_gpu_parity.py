@@ -5,13 +5,12 @@ reported separately, per the north star); equalised points within EQ_RTOL (fp32 
 import numpy as np
 import pytest
 
-from conftest import STAGE_NAMES, load_golden, oracle_params
+from conftest import BOUNDARY_TOL, STAGE_NAMES, assert_bits_match, load_golden, oracle_params
 from oracle import gf3_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
 EQ_RTOL = 1e-4          # north star: equalised constellation within 1e-4 relative error
-BOUNDARY_TOL = 1e-4     # decisions this close to a boundary (in units of |point|) may differ in fp32
 
 
 def _torch():
@@ -27,20 +26,8 @@ def _phy(p):
 
 
 def _check_bits(got, ref_bits, ref_eq_data, what):
-    """Bit-exact, except decisions whose oracle point is within BOUNDARY_TOL of a boundary."""
-    got = np.asarray(got).reshape(-1)
-    ref_bits = np.asarray(ref_bits).reshape(-1)
-    assert got.shape == ref_bits.shape
-    bad = np.flatnonzero(got != ref_bits)
-    if len(bad) == 0:
-        return 0
-    pts = np.asarray(ref_eq_data).reshape(-1)
-    comp = np.where(bad % 2 == 0, np.abs(pts[bad // 2].imag), np.abs(pts[bad // 2].real))   # b0 <- imag, b1 <- real
-    margin = comp / np.maximum(np.abs(pts[bad // 2]), 1e-30)
-    assert np.all(margin < BOUNDARY_TOL), "%s: %d bit mismatches away from decision boundaries (worst margin %.3e)" % (
-        what, int(np.sum(margin >= BOUNDARY_TOL)), float(margin.max()))
-    print("%s: %d near-boundary decisions differ (listed separately; margins %s)" % (what, len(bad), margin))
-    return len(bad)
+    """Bit-exact, except decisions whose oracle point is within 1e-5 of a boundary (conftest policy)."""
+    return assert_bits_match(got, ref_bits, ref_eq_data, what)["n_diff"]
 
 
 def _rel_err(a, b):
@@ -221,11 +208,16 @@ def test_kat1_gr5ch1_dropin_receive(known_sequence, capsys):
     assert err.max() < EQ_RTOL, err.max()
     ref_bits = np.unpackbits(g["bits_packed"])[:1512000]
     diff = np.flatnonzero(bits != ref_bits)
-    # every differing decision must be one of the reference's own near-boundary points
-    near = {(int(a), int(b)) for a, b in g["near_boundary"]}
+    # every differing decision must be one of the reference's own points within 1e-5 of a decision boundary
+    # (the golden lists the points below 1e-4 with their margins: 2 of the 756 000 are below 1e-5)
+    near5 = g["near_boundary"][g["near_margin"] < BOUNDARY_TOL]
+    assert len(near5) == 2
+    near = {(int(a), int(b)) for a, b in near5}
     for i in diff:
         assert ((i // 2) // 1400, (i // 2) % 1400) in near, "bit %d differs away from a decision boundary" % i
-    print("KAT-1: %d of 1512000 bits differ, all within 1e-4 of a decision boundary" % len(diff))
+    with capsys.disabled():
+        print("\nKAT-1: %d of 1512000 bits differ from the reference's (allowed only at its %d points within 1e-5 of a boundary)"
+              % (len(diff), len(near5)))
     tx_bits = orc.load_file_bits("gr5ch1.bmp", g["bmp"])
     nerr = int(np.sum(tx_bits != bits[: len(tx_bits)]))
     assert abs(nerr - 24525) <= len(diff)

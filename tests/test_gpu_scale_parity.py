@@ -1,0 +1,175 @@
+"""GPU parity at the sizes that carry the bench numbers (VERDICT r01 "what's weak" 1-3): the fused
+one-launch receive chain and the synchroniser against the float64 oracle on hundreds of noisy
+multipath packets / streams of the BASELINE.json shapes, and KAT-4 (configs[1], the long recording)
+through the drop-in module.  Bits must be identical except decisions within 1e-5 of a decision
+boundary (counted, printed, asserted: tests/conftest.py)."""
+import hashlib
+import time
+
+import numpy as np
+import pytest
+
+from conftest import assert_bits_match, kat4_regenerate, load_golden
+from oracle import gf3_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+EQ_RTOL = 1e-4          # north star: equalised constellation within 1e-4 relative error (fp32 vs float64)
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _pair(known_sequence, **cfg):
+    import gf3b200
+    phy = gf3b200.Phy(known_sequence=known_sequence, **cfg)
+    p = orc.Params(N=cfg["N"], cp=cfg["cp"], lo=cfg["lo"], hi=cfg["hi"], n_pilots=cfg["n_pilots"], packet_len=cfg["packet_len"],
+                   known_sequence=known_sequence, encoding="XOR", fit_lo=cfg.get("fit_lo", 500), fit_hi=cfg.get("fit_hi", 1000))
+    return phy, p
+
+
+# ----------------------------------------------------------------------------- receive chain at C3 scale
+@pytest.mark.parametrize("fit", [(125, 250), (500, 1000)], ids=["fit125-250", "fit500-1000-literal"])
+@pytest.mark.parametrize("snr_db", [20.0, 8.0])
+def test_c3_fused_receive_vs_oracle(snr_db, fit, known_sequence):
+    """256 packets of the C3 shape (N=1024, CP=32, Nd=511, P=20, L=180) through random 30-tap channels
+    with nulls + AWGN, ONE fused launch (gf3_rx_receive) against oracle.receive_symbols on the same
+    float32 samples; both the bench's fit window and the reference's literal [500:1000] (OFDM.py:462),
+    which clips to 11 band-edge bins at K = 511."""
+    torch = _torch()
+    from gf3b200 import synth
+    n = 256
+    phy, p = _pair(known_sequence, N=1024, cp=32, lo=1, hi=512, n_pilots=20, packet_len=180, fit_lo=fit[0], fit_hi=fit[1])
+    assert phy.fused_receive
+    b = synth.make_batch(phy, n, 1, snr_db=snr_db, seed=4242)
+    sym = synth.packets_from_streams(phy, b).contiguous()
+    flat = sym.reshape(-1)
+    (packed_eq, eq), Hs, He, slope = phy.rx_receive(flat, n, xor=True, want_eq=True)      # exact rotation + constellation
+    packed, Hs2, He2, slope2 = phy.rx_receive(flat, n, xor=True)                          # the throughput path the bench times
+    torch.cuda.synchronize()
+    assert torch.equal(Hs, Hs2) and torch.equal(slope, slope2)
+    ref = orc.receive_symbols(p, sym.cpu().numpy().astype(np.float64).reshape(n, p.syms_per_packet, p.sym_len), want_eq=True)
+    hscale = np.max(np.abs(ref["Hs"]), axis=1, keepdims=True)
+    eh = max(float(np.max(np.abs(Hs.cpu().numpy() - ref["Hs"]) / hscale)), float(np.max(np.abs(He.cpu().numpy() - ref["He"]) / hscale)))
+    es = float(np.max(np.abs(slope.cpu().numpy() - ref["slope"])))
+    dc = p.data_carriers - 1
+    ref_eq = ref["eq"][:, dc]
+    got_eq = eq.cpu().numpy().reshape(-1, p.K)[:, dc]
+    rel = np.abs(got_eq - ref_eq) / np.maximum(np.abs(ref_eq), 1e-30)
+    # fp32 keeps 1e-4 relative on every bin that is not a deep channel null: the FFT's rounding error is
+    # relative to the symbol's energy, not to the bin, so bins 40 dB below the strongest carry more
+    strong = (np.abs(ref["Hs"][:, dc]) >= 0.02 * hscale)                                  # [n, Nd]
+    strong_pts = np.repeat(strong, p.packet_len, axis=0)
+    print("C3 %g dB fit %s: H err %.2e of max, slope err %.2e, eq rel err max %.2e (bins >= 2%% of max |H|: %.2e; %.3f%% of bins weaker), "
+          "slope range %.4f..%.4f" % (snr_db, fit, eh, es, rel.max(), rel[strong_pts].max(), 100.0 * (1 - strong.mean()),
+                                      ref["slope"].min(), ref["slope"].max()))
+    assert eh < 2e-6
+    assert es < 1e-6
+    assert rel[strong_pts].max() < EQ_RTOL
+    assert np.quantile(rel, 0.9999) < EQ_RTOL
+    assert_bits_match(phy.unpack_bits(packed_eq), ref["bits"], ref_eq, "C3 %g dB %s exact-rotation path" % (snr_db, fit))
+    assert_bits_match(phy.unpack_bits(packed), ref["bits"], ref_eq, "C3 %g dB %s throughput path" % (snr_db, fit))
+
+
+# ----------------------------------------------------------------------------- synchroniser at scale
+def _sync_compare(phy, p, r, what):
+    """GPU xcorr + peak_pick on r [B, T] against oracle.chirp_method per stream."""
+    torch = _torch()
+    B, T = r.shape
+    P, pmax = phy.xcorr(r)
+    peaks, count = phy.peak_pick(P, pmax, T, 16)
+    torch.cuda.synchronize()
+    peaks, count = peaks.cpu().numpy(), count.cpu().numpy()
+    rh = r.cpu().numpy().astype(np.float64)
+    bad, hist = [], {}
+    for s in range(B):
+        ref = np.flatnonzero(orc.chirp_method(p, rh[s]))
+        got = peaks[s, : count[s]]
+        hist[len(ref)] = hist.get(len(ref), 0) + 1
+        if not np.array_equal(ref, got):
+            bad.append((s, ref.tolist(), got.tolist()))
+    print("%s: %d streams, detections per stream (oracle) %s, %d streams differ %s" % (what, B, sorted(hist.items()), len(bad), bad[:4]))
+    return bad, hist
+
+
+def test_c3_multistream_sync_vs_oracle(known_sequence):
+    """chirp_method (OFDM.py:356-372) on 320 noisy C3 streams (20 dB, random 30-tap channels, random lead-in
+    in [0, 2000), the one-kernel peak picker) gives the oracle's detection indices on every stream --
+    including the streams on which the REFERENCE's rule itself loses the chirps (r01: "1020/1024")."""
+    torch = _torch()
+    from gf3b200 import synth
+    B = 320
+    phy, p = _pair(known_sequence, N=1024, cp=32, lo=1, hi=512, n_pilots=20, packet_len=180, fit_lo=125, fit_hi=250)
+    b = synth.make_batch(phy, B, 1, snr_db=20.0, seed=1234, lead=2000, trail=40)
+    T2 = b["r"].shape[1] - 2000
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    cut = torch.randint(0, 2000, (B,), device="cuda", generator=gen)
+    cut[:8] = torch.tensor([0, 1, 2, 3, 1997, 1998, 1999, 1000], device="cuda")
+    r = torch.empty((B, (T2 + 3) // 4 * 4), dtype=torch.float32, device="cuda")[:, :T2]
+    for s in range(B):
+        r[s] = b["r"][s, int(cut[s]): int(cut[s]) + T2]
+    bad, hist = _sync_compare(phy, p, r, "C3 sync 20 dB")
+    assert not bad
+    assert hist.get(2, 0) >= B * 0.95                      # both chirps of (almost) every stream
+    # the bench's tight framing (no lead-in, 2 trailing samples): same comparison, explains the r01 count
+    b2 = synth.make_batch(phy, B, 1, snr_db=20.0, seed=1234, lead=0, trail=2)
+    bad2, hist2 = _sync_compare(phy, p, b2["r"], "C3 sync 20 dB, trail = 2")
+    assert not bad2
+
+
+def test_a2_multistream_sync_vs_oracle(known_sequence):
+    """The same on 8 A2 streams (N=4096, CP=224, 21 600-sample chirp, 11 filter partitions, ~1 M samples each:
+    the mark + scan peak picker for batches below two waves)."""
+    _torch()
+    from gf3b200 import synth
+    phy, p = _pair(known_sequence, N=4096, cp=224, lo=100, hi=1500, n_pilots=20, packet_len=180)
+    b = synth.make_batch(phy, 8, 1, snr_db=15.0, seed=99, lead=1234, trail=300)
+    bad, hist = _sync_compare(phy, p, b["r"], "A2 sync 15 dB")
+    assert not bad and hist == {2: 8}
+
+
+# ----------------------------------------------------------------------------- KAT-4 (BASELINE.json configs[1])
+def test_kat4_gr5ch2_dropin_receive(known_sequence, capsys):
+    """configs[1]: chirp-synchronised decode of a long recording (29 packets, 28.2 M samples, int16) with
+    the channel estimated from the known symbols, through the drop-in OFDM.receiver("A2","XOR").receive:
+    the reference's 30 sync indices, 29 slopes, constellation sample and 14 616 000 bits (sha256 of the
+    reference's own output; tests/golden/kat4_gr5ch2.npz, made by oracle/make_golden.py kat4)."""
+    _torch()
+    import OFDM
+    g = load_golden("kat4_gr5ch2.npz")
+    p, bits_in, r = kat4_regenerate(g, known_sequence)
+    rx = OFDM.receiver(mode="A2", encoding="XOR")
+    rx.receive(r[: 2 * 972000 + 30000])                   # warm-up: plan creation, allocator, first launches
+    details = {}
+    t0 = time.perf_counter()
+    bits, Hs0, He0 = rx.receive(r, _details=details)
+    t_gpu = time.perf_counter() - t0
+    printed = capsys.readouterr().out
+    assert "Number of received OFDM symbols:    5220" in printed and "Number of received bits:            14616000" in printed
+    assert np.array_equal(details["peaks"], g["peaks"])
+    np.testing.assert_allclose(details["slope"], g["slope"], rtol=0, atol=2e-7)
+    hscale = np.max(np.abs(g["Hs0"]))
+    assert np.max(np.abs(Hs0 - g["Hs0"])) / hscale < 2e-6
+    assert np.max(np.abs(details["He"][28] - g["He28"])) / hscale < 2e-6
+    dc = np.arange(100, 1500) - 1
+    rel = np.abs(details["eq"][g["eq_rows"]][:, dc] - g["eq_sel"][:, dc]) / np.abs(g["eq_sel"][:, dc])
+    assert rel.max() < EQ_RTOL, rel.max()
+    sha = hashlib.sha256(np.packbits(bits).tobytes()).hexdigest()
+    if sha != str(g["bits_sha256"]):
+        # list the differing decisions against the oracle (pinned to the reference's sha256 on this very
+        # recording by tests/test_oracle_golden.py::test_kat4_gr5ch2_long_recording)
+        ref = orc.receive(p, r.astype(np.float64), want_eq=True)
+        assert hashlib.sha256(np.packbits(ref["bits"]).tobytes()).hexdigest() == str(g["bits_sha256"])
+        c = assert_bits_match(bits, ref["bits"], ref["eq"][:, dc], "KAT-4")
+        assert c["n_diff"] <= len(g["near_1e5"]) + len(g["near_1e4"])
+    nerr = int(np.sum(bits[: len(bits_in)] != bits_in))
+    ref_s = g["ref_seconds"]
+    with capsys.disabled():
+        print("\nKAT-4: %d samples -> %d bits in %.3f s through the drop-in receive() (reference: transmit %.1f s, receive %.1f s "
+              "in the build container); bits sha256 %s the reference's; %d bit errors vs the transmitted file (reference %d)"
+              % (len(r), len(bits), t_gpu, ref_s[0], ref_s[1], "==" if sha == str(g["bits_sha256"]) else "!=", nerr, int(g["n_bit_errors"])))
+    name, size, payload = orc.save_file_bytes(bits)
+    assert name == "gr5ch2.wav" and int(size) == len(g["payload"])

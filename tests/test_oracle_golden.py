@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from conftest import STAGE_NAMES, load_golden, oracle_params
+from conftest import STAGE_NAMES, kat4_regenerate, load_golden, oracle_params
 from oracle import gf3_oracle as orc
 
 
@@ -126,3 +126,24 @@ def test_kat3_weekend_known_channel(known_sequence):
     name, size, data = orc.save_file_bytes(out_bits)
     assert name == "y5tv9o.wav" and int(size) == len(wav)
     assert np.array_equal(data, wav) and len(payload) == 44612
+
+
+def test_kat4_gr5ch2_long_recording(known_sequence):
+    """KAT-4 = BASELINE.json configs[1]: the reference transmits input_Files/gr5ch2.wav in mode
+    A2 (29 packets, 28.2 M samples), Handouts/gr5channel.csv FIR + AWGN + int16; the reference's own
+    receive() output is the golden (OFDM.py:296-343, 581-657).  The oracle must regenerate the recording
+    from the seed and decode it to the very same bits, sync indices, slopes and constellation."""
+    g = load_golden("kat4_gr5ch2.npz")
+    p, bits_in, r = kat4_regenerate(g, known_sequence)
+    assert len(r) == int(g["n_samples"]) == 28214698
+    out = orc.receive(p, r.astype(np.float64), want_eq=True)
+    assert np.array_equal(out["peaks"], g["peaks"]) and len(out["peaks"]) == 30
+    np.testing.assert_allclose(out["slope"], g["slope"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(out["Hs"][0], g["Hs0"], rtol=1e-12)
+    np.testing.assert_allclose(out["He"][28], g["He28"], rtol=1e-12)
+    np.testing.assert_allclose(out["eq"][g["eq_rows"]], g["eq_sel"], rtol=1e-10)
+    assert len(out["bits"]) == int(g["n_bits"]) == 29 * 180 * 2800
+    assert hashlib.sha256(np.packbits(out["bits"]).tobytes()).hexdigest() == str(g["bits_sha256"])
+    assert int(np.sum(out["bits"][: len(bits_in)] != bits_in)) == int(g["n_bit_errors"]) == 111558
+    name, size, _ = orc.save_file_bytes(out["bits"])
+    assert name == str(g["file_name"]) == "gr5ch2.wav" and int(size) == len(g["payload"])
