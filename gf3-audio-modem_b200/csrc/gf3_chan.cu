@@ -35,6 +35,7 @@ struct ChanArgs {
     const float* x;
     const float* taps;
     const float* sigma;
+    const int64_t* ids;         // optional: Philox stream id of every row (default: the row index)
     float* y;
     int64_t x_stride, y_stride, T;
     uint64_t seed;
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(256) channel_sim_kernel(const ChanArgs a) {
     const float* x = a.x + stream * a.x_stride;
     float* y = a.y + stream * a.y_stride;
     const float sg = a.sigma ? a.sigma[stream] : 0.f;
+    const int64_t sid = a.ids ? a.ids[stream] : stream;                  // the noise of a row depends on its id only
     const int nblk = (a.n_taps + 3) >> 2;                                // tap blocks of four
     const bool y_al16 = ((reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     for (int64_t tile0 = (int64_t)blockIdx.x * TILE; tile0 < a.T; tile0 += (int64_t)gridDim.x * TILE) {
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(256) channel_sim_kernel(const ChanArgs a) {
             }
             if (sg != 0.f) {
                 const int64_t q = n0 >> 2;
-                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)),
+                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)sid, (uint32_t)(sid >> 32)),
                                                 make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
                 const float2 g0 = box_muller(rnd.x, rnd.y), g1 = box_muller(rnd.z, rnd.w);
                 acc[0] = fmaf(sg, g0.x, acc[0]); acc[1] = fmaf(sg, g0.y, acc[1]);
@@ -124,6 +126,26 @@ __global__ void __launch_bounds__(256) ber_count_kernel(const uint8_t* __restric
     }
 }
 
+// Uniform random bytes, 16 per Philox call; row r draws from the counter stream of row_ids[r] (default r),
+// so a row's bytes depend on (seed, id, position) only -- not on how rows are batched or sharded.
+__global__ void __launch_bounds__(256) random_bytes_kernel(uint8_t* __restrict__ out, int64_t out_stride, int64_t row_bytes,
+                                                          const int64_t* __restrict__ row_ids, uint64_t seed) {
+    const int64_t row = blockIdx.y;
+    const int64_t id = row_ids ? row_ids[row] : row;
+    uint8_t* o = out + row * out_stride;
+    const int64_t n16 = (row_bytes + 15) >> 4;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n16; q += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 rnd = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)id, (uint32_t)(id >> 32) ^ 0x52424e44u),
+                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+        if (16 * q + 16 <= row_bytes && ((reinterpret_cast<uintptr_t>(o) | (uintptr_t)out_stride) & 15) == 0) {
+            reinterpret_cast<uint4*>(o)[q] = rnd;
+        } else {
+            for (int e = 0; e < 16 && 16 * q + e < row_bytes; ++e) o[16 * q + e] = (uint8_t)(w[e >> 2] >> (8 * (e & 3)));
+        }
+    }
+}
+
 // PCM samples -> float32 (exact value conversion), 16 samples per thread step, 128-bit stores
 template <typename T>
 __global__ void __launch_bounds__(256) pcm_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t n) {
@@ -157,22 +179,48 @@ extern "C" int gf3_pcm_to_f32(const void* pcm, int32_t format, int64_t n, float*
     return GF3_OK;
 }
 
-extern "C" int gf3_channel_sim(const float* x, int64_t x_stride, int64_t n_streams, int64_t T,
-                               const float* taps, int32_t n_taps, const float* sigma, uint64_t seed,
-                               float* y, int64_t y_stride, void* stream) {
+static int channel_sim_common(const float* x, int64_t x_stride, int64_t n_streams, int64_t T,
+                              const float* taps, int32_t n_taps, const float* sigma, const int64_t* ids, uint64_t seed,
+                              float* y, int64_t y_stride, void* stream) {
     GF3_REQUIRE(x && taps && y, "channel_sim: null argument");
     GF3_REQUIRE(n_taps >= 1 && n_taps <= kMaxTaps, "channel_sim: n_taps must be in 1..%d", kMaxTaps);
     GF3_REQUIRE(n_streams >= 0 && n_streams <= 65535 && T >= 0, "channel_sim: bad sizes (n_streams <= 65535)");
     GF3_REQUIRE(x != y, "channel_sim: in-place operation is not supported");
     if (n_streams == 0 || T == 0) return GF3_OK;
     ChanArgs a;
-    a.x = x; a.taps = taps; a.sigma = sigma; a.y = y; a.x_stride = x_stride; a.y_stride = y_stride; a.T = T;
+    a.x = x; a.taps = taps; a.sigma = sigma; a.ids = ids; a.y = y; a.x_stride = x_stride; a.y_stride = y_stride; a.T = T;
     a.seed = seed; a.n_taps = n_taps;
     int64_t gx = (T + 1023) / 1024;                  // tiles of 1024 outputs per stream
     const int64_t cap = (148LL * 8 * 4 + n_streams - 1) / n_streams;      // a few waves in total
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     channel_sim_kernel<<<dim3((unsigned)gx, (unsigned)n_streams), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}
+
+extern "C" int gf3_channel_sim(const float* x, int64_t x_stride, int64_t n_streams, int64_t T,
+                               const float* taps, int32_t n_taps, const float* sigma, uint64_t seed,
+                               float* y, int64_t y_stride, void* stream) {
+    return channel_sim_common(x, x_stride, n_streams, T, taps, n_taps, sigma, nullptr, seed, y, y_stride, stream);
+}
+
+extern "C" int gf3_channel_sim_ids(const float* x, int64_t x_stride, int64_t n_streams, int64_t T,
+                                   const float* taps, int32_t n_taps, const float* sigma, const int64_t* stream_ids,
+                                   uint64_t seed, float* y, int64_t y_stride, void* stream) {
+    GF3_REQUIRE(stream_ids != nullptr, "channel_sim_ids: null stream_ids");
+    return channel_sim_common(x, x_stride, n_streams, T, taps, n_taps, sigma, stream_ids, seed, y, y_stride, stream);
+}
+
+extern "C" int gf3_random_bytes(uint8_t* out, int64_t out_stride, int64_t n_rows, int64_t row_bytes,
+                                const int64_t* row_ids, uint64_t seed, void* stream) {
+    GF3_REQUIRE(out != nullptr, "random_bytes: null output");
+    GF3_REQUIRE(n_rows >= 0 && n_rows <= 65535 && row_bytes >= 0 && out_stride >= row_bytes, "random_bytes: bad sizes (n_rows <= 65535)");
+    if (n_rows == 0 || row_bytes == 0) return GF3_OK;
+    int64_t gx = (row_bytes + 16 * 256 - 1) / (16 * 256);
+    if (gx > 64) gx = 64;
+    random_bytes_kernel<<<dim3((unsigned)gx, (unsigned)n_rows), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        out, out_stride, row_bytes, row_ids, seed);
     GF3_LAUNCH_CHECK();
     return GF3_OK;
 }

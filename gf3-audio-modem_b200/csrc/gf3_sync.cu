@@ -415,6 +415,29 @@ __global__ void __launch_bounds__(256) peak_pick_kernel(const PeakArgs a) {
     if (tid == 0) a.count[stream] = wiped ? 0 : found;
 }
 
+// get_symbols' index bookkeeping (OFDM.py:393-397) for a batch of streams on the device: detections ->
+// packet start offsets into the flat sample array.  zero_indicies = where(zeros) + 2, the last one (the
+// terminating chirp) dropped.  A stream is "ok" when it holds exactly pk_expected packets and the last
+// one ends inside the stream; otherwise its offsets are clamped into the stream (the packets decode to
+// garbage instead of reading out of bounds) and ok = 0, so the caller can discount it.
+__global__ void peaks_to_offsets_kernel(const int64_t* __restrict__ peaks, const int32_t* __restrict__ count, int64_t n_streams,
+                                        int32_t max_peaks, int64_t r_stride, int64_t T, int32_t pk_expected, int64_t pkt_samples,
+                                        int64_t* __restrict__ pkt_offset, uint8_t* __restrict__ ok) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_streams * pk_expected) return;
+    const int64_t s = i / pk_expected;
+    const int j = (int)(i - s * pk_expected);
+    const int det = count[s] < max_peaks ? count[s] : max_peaks;
+    const int64_t last = T - pkt_samples;                                 // last start that keeps the packet inside the stream
+    bool good = count[s] == pk_expected + 1 && count[s] <= max_peaks && last >= 0;
+    if (good) good = peaks[s * max_peaks + pk_expected - 1] + 2 <= last;
+    int64_t st = j < det ? peaks[s * max_peaks + j] + 2 : 0;
+    st = st > last ? last : st;
+    st = st < 0 ? 0 : st;
+    pkt_offset[i] = s * r_stride + st;
+    if (j == 0 && ok) ok[s] = good ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static int run_fwd(const gf3_plan* plan, const float* r, int64_t r_stride, int64_t n_streams, int64_t T, int nblk, int reverse,
                    int in_off, int valid_len, float2* spec, const float2* tw, float* pmax, cudaStream_t st) {
@@ -542,6 +565,22 @@ extern "C" int gf3_peak_pick(const gf3_plan* plan, const float* P, int64_t p_str
     peak_mark_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
     GF3_LAUNCH_CHECK();
     peak_scan_kernel<<<(unsigned)n_streams, 256, 0, st>>>(a);
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}
+
+extern "C" int gf3_peaks_to_offsets(const gf3_plan* plan, const int64_t* peaks, const int32_t* count, int64_t n_streams,
+                                    int32_t max_peaks, int64_t r_stride, int64_t T, int32_t pk_expected,
+                                    int64_t* pkt_offset, uint8_t* ok, void* stream) {
+    GF3_REQUIRE(plan && peaks && count && pkt_offset, "peaks_to_offsets: null argument");
+    GF3_REQUIRE(n_streams >= 0 && max_peaks >= 1 && pk_expected >= 1 && pk_expected < max_peaks,
+                "peaks_to_offsets: need 1 <= pk_expected < max_peaks");
+    if (n_streams == 0) return GF3_OK;
+    const gf3_params& p = plan->p;
+    const int64_t pkt_samples = (int64_t)(2 * p.n_pilots + p.packet_len) * (p.N + p.cp);
+    const int64_t n = n_streams * pk_expected;
+    peaks_to_offsets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        peaks, count, n_streams, max_peaks, r_stride, T, pk_expected, pkt_samples, pkt_offset, ok);
     GF3_LAUNCH_CHECK();
     return GF3_OK;
 }

@@ -58,6 +58,9 @@ SIGNATURES = {
     "gf3_demap": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "gf3_tx_frame": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "gf3_channel_sim": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_uint64, c_void_p, c_int64, c_void_p]),
+    "gf3_channel_sim_ids": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_uint64, c_void_p, c_int64, c_void_p]),
+    "gf3_random_bytes": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_uint64, c_void_p]),
+    "gf3_peaks_to_offsets": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "gf3_ber_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "gf3_pcm_to_f32": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
 }

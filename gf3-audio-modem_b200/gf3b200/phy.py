@@ -105,7 +105,7 @@ class Phy:
             return getattr(self.lib, name)(*[st if a is _STREAM else a for a in args])
 
     def _f32(self, t):
-        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "need contiguous float32 CUDA tensor"
+        assert t.is_cuda and t.dtype == torch.float32 and t.stride(-1) == 1, "need a float32 CUDA tensor with unit sample stride"
         return t
 
     def _offsets(self, pkt_offset, n):
@@ -174,13 +174,14 @@ class Phy:
         self._f32(r)
         assert r.dim() == 2
         B, T = r.shape
+        rs = r.stride(0) if B > 1 else T
         plen = T + self.chirp_len - 1
         pstride = (plen + 3) // 4 * 4
         P = torch.empty((B, pstride), dtype=torch.float32, device=self.device)
         pmax = torch.empty((B,), dtype=torch.float32, device=self.device)
         wb = int(self.lib.gf3_xcorr_work_bytes(self._plan, B, T))
         work = torch.empty((wb,), dtype=torch.uint8, device=self.device)
-        check(self._call("gf3_xcorr", self._plan, _ptr(r), T, B, T, _ptr(P), pstride, _ptr(pmax), _ptr(work), _STREAM))
+        check(self._call("gf3_xcorr", self._plan, _ptr(r), rs, B, T, _ptr(P), pstride, _ptr(pmax), _ptr(work), _STREAM))
         return P[:, :plen], pmax
 
     def peak_pick(self, P, pmax, T, max_peaks=64):
@@ -193,6 +194,34 @@ class Phy:
         check(self._call("gf3_peak_pick", self._plan, _ptr(P), P.stride(0), B, T, _ptr(pmax), _ptr(peaks), max_peaks,
                                      _ptr(count), _ptr(work), _STREAM))
         return peaks, count
+
+    def peaks_to_offsets(self, peaks, count, r_stride, T, pk_expected):
+        """get_symbols' bookkeeping on the device (OFDM.py:393-397): detections of a batch of streams ->
+        (pkt_offset int64 [B * pk_expected] into the flat sample array, ok uint8 [B])."""
+        B, max_peaks = peaks.shape
+        assert peaks.is_cuda and peaks.dtype == torch.int64 and peaks.is_contiguous() and count.dtype == torch.int32
+        off = torch.empty((B * pk_expected,), dtype=torch.int64, device=self.device)
+        ok = torch.empty((B,), dtype=torch.uint8, device=self.device)
+        check(self._call("gf3_peaks_to_offsets", self._plan, _ptr(peaks), _ptr(count), B, max_peaks, r_stride, T, pk_expected,
+                         _ptr(off), _ptr(ok), _STREAM))
+        return off, ok
+
+    def receive_streams(self, r, pk_expected, xor=True, want_eq=False, out=None):
+        """receiver.receive (OFDM.py:581-609) for a batch of raw received streams r float32 [B, T] that hold
+        pk_expected packets each: matched filter -> detection rule -> packet offsets -> fused receive chain,
+        everything on the device.  -> dict(bits [B * pk_expected, bits_stride], ok uint8 [B] (1: the stream's
+        chirps were found where the reference's slicing would succeed), peaks, count, Hs, He, slope[, eq])."""
+        self._f32(r)
+        assert r.dim() == 2
+        B, T = r.shape
+        P, pmax = self.xcorr(r)
+        peaks, count = self.peak_pick(P, pmax, T, pk_expected + 3)
+        off, ok = self.peaks_to_offsets(peaks, count, r.stride(0), T, pk_expected)
+        res, Hs, He, slope = self.rx_receive(r, B * pk_expected, off, xor=xor, want_eq=want_eq, out=out)   # offsets are relative to r's first sample
+        d = dict(bits=res[0] if want_eq else res, ok=ok, peaks=peaks, count=count, Hs=Hs, He=He, slope=slope, pkt_offset=off)
+        if want_eq:
+            d["eq"] = res[1]
+        return d
 
     # ------------------------------------------------------------------ transmit chain
     def tx_len(self, pk_per_stream):
@@ -215,16 +244,35 @@ class Phy:
         return out[:, :T]
 
     # ------------------------------------------------------------------ channel + counters
-    def channel_sim(self, x, taps, sigma, seed):
-        """y = lfilter(taps, 1, x) + sigma*N(0,1): x [B, T] (row stride may exceed T)."""
+    def channel_sim(self, x, taps, sigma, seed, stream_ids=None):
+        """y = lfilter(taps, 1, x) + sigma*N(0,1): x [B, T] (row stride may exceed T).  stream_ids (int64 [B]):
+        the noise of a row then depends on (seed, id, sample) only, not on the row's place in the batch."""
         assert x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
         B, T = x.shape
         taps = taps.to(torch.float32).contiguous()
         y = torch.empty((B, (T + 3) // 4 * 4), dtype=torch.float32, device=self.device)
         sg = sigma.to(torch.float32).contiguous() if sigma is not None else None
-        check(self._call("gf3_channel_sim", _ptr(x), x.stride(0), B, T, _ptr(taps), taps.shape[1], _ptr(sg),
-                                       int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(y), y.stride(0), _STREAM))
+        if stream_ids is None:
+            check(self._call("gf3_channel_sim", _ptr(x), x.stride(0), B, T, _ptr(taps), taps.shape[1], _ptr(sg),
+                             int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(y), y.stride(0), _STREAM))
+        else:
+            ids = stream_ids.to(device=self.device, dtype=torch.int64).contiguous()
+            assert ids.numel() == B
+            check(self._call("gf3_channel_sim_ids", _ptr(x), x.stride(0), B, T, _ptr(taps), taps.shape[1], _ptr(sg), _ptr(ids),
+                             int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(y), y.stride(0), _STREAM))
         return y[:, :T]
+
+    def random_bytes(self, n_rows, row_bytes, seed, row_ids=None, out=None):
+        """Uniform random bytes uint8 [n_rows, row_bytes] (Philox; row r from the stream of row_ids[r])."""
+        if out is None:
+            out = torch.empty((n_rows, row_bytes), dtype=torch.uint8, device=self.device)
+        assert out.is_cuda and out.dtype == torch.uint8 and out.stride(1) == 1 and out.shape == (n_rows, row_bytes)
+        ids = row_ids.to(device=self.device, dtype=torch.int64).contiguous() if row_ids is not None else None
+        for r0 in range(0, n_rows, 65535):
+            n = min(65535, n_rows - r0)
+            check(self._call("gf3_random_bytes", _ptr(out[r0:]), out.stride(0), n, row_bytes,
+                             _ptr(ids[r0:]) if ids is not None else None, int(seed) & 0xFFFFFFFFFFFFFFFF, _STREAM))
+        return out
 
     def ber_count(self, a, b, nbits, counter):
         """counter (int64/uint64 [2]) += (bit errors, bits) between two packed rows."""

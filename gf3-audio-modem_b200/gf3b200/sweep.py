@@ -51,59 +51,43 @@ def sweep(count_fn, n_streams, snrs_db, rank=0, world=1, dist=None, tensor_facto
 
 
 def make_gpu_count_fn(phy, pk_per_stream=1, seed=1234, use_sync=True):
-    """tx_modulate -> channel_sim -> xcorr/peak_pick -> rx_receive (estimate + data symbols) -> ber_count on the
-    device, for an explicit list of stream ids."""
+    """tx_modulate -> channel_sim -> xcorr / peak_pick / packet offsets -> rx_receive (estimate + data symbols)
+    -> ber_count, all on the device and batched over an explicit list of stream ids.  A stream's bits,
+    filler, channel and noise depend on (seed, stream id, SNR) only (synth.make_batch), so the counters
+    do not depend on how the streams are sharded over ranks or chunks."""
     import torch
     from . import synth
 
     def count(stream_ids, snr_db):
         n = len(stream_ids)
         dev = phy.device
-        # per-stream reproducible bits: seed derived from the stream id, independent of sharding
-        bits = torch.empty((n, pk_per_stream, phy.bits_stride), dtype=torch.uint8, device=dev)
-        fill = torch.empty((n, max(phy.K - phy.Nd, 1)), dtype=torch.int64, device=dev)
-        for i, sid in enumerate(stream_ids):
-            g = torch.Generator(device=dev).manual_seed(seed * 1000003 + int(sid))
-            bits[i] = torch.randint(0, 256, (pk_per_stream, phy.bits_stride), dtype=torch.uint8, device=dev, generator=g)
-            fill[i] = torch.randint(0, 4, (fill.shape[1],), device=dev, generator=g)
+        b = synth.make_batch(phy, n, pk_per_stream, snr_db=snr_db, seed=seed, lead=64, trail=8, stream_ids=stream_ids)
+        r, bits = b["r"], b["bits"]
         nbytes = (phy.bits_per_packet + 7) // 8
-        bits[:, :, nbytes:] = 0
-        filler = None
-        if phy.K > phy.Nd:
-            filler = (((1 - 2 * (fill & 1)) + 1j * (1 - 2 * (fill >> 1))) / np.sqrt(2)).to(torch.complex64).contiguous()
-        tx = phy.tx_modulate(bits, filler, n, pk_per_stream)
-        lead, trail = 64, 8
-        T = tx.shape[1] + lead + trail
-        x = torch.zeros((n, (T + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :T]
-        x[:, lead:lead + tx.shape[1]] = tx
-        taps = torch.from_numpy(synth.random_channels(n, stream_ids=stream_ids)).to(dev)
-        y0 = phy.channel_sim(x, taps, None, 0)
-        c0 = lead + phy.chirp_len
-        sigma = torch.sqrt(y0[:, c0:c0 + phy.pkt_samples].pow(2).mean(dim=1)) * (10.0 ** (-float(snr_db) / 20.0))
-        seeds = int(seed) * 7919 + int(round(float(snr_db) * 16))
-        # noise must not depend on which rank / chunk a stream lands in: one launch per stream id
-        r = torch.empty_like(y0)
-        for i, sid in enumerate(stream_ids):
-            r[i:i + 1] = phy.channel_sim(x[i:i + 1], taps[i:i + 1], sigma[i:i + 1], seeds * 65537 + int(sid))
-        r = r.contiguous()
-        known_starts = c0 + torch.arange(pk_per_stream, device=dev, dtype=torch.int64) * (phy.chirp_len + phy.pkt_samples)
-        starts = known_starts[None, :].expand(n, pk_per_stream).clone()
         fails = 0
         if use_sync:
-            P, pmax = phy.xcorr(r)
-            peaks, cnt = phy.peak_pick(P, pmax, r.shape[1], pk_per_stream + 4)
-            ok = cnt == pk_per_stream + 1
-            det = peaks[:, :pk_per_stream] + 2
-            starts = torch.where(ok[:, None], det, starts)
-            starts = torch.minimum(starts, torch.tensor(r.shape[1] - phy.pkt_samples, device=dev))
+            out = phy.receive_streams(r, pk_per_stream, xor=False)
+            ok = out["ok"].bool()
+            rx_bits = out["bits"].reshape(n, pk_per_stream, -1)
             fails = int((~ok).sum())
-        off = (starts + (torch.arange(n, device=dev) * r.shape[1])[:, None]).reshape(-1).contiguous()
-        out = phy.rx_receive(r.reshape(-1), n * pk_per_stream, off, xor=False)[0]     # estimate + data symbols, one launch
+            if fails:      # streams whose chirps were not found: decode at the nominal position (counts as received garbage or luck)
+                bad = torch.nonzero(~ok).reshape(-1)
+                off = (b["starts"][bad] + (bad * r.stride(0))[:, None]).reshape(-1).contiguous()
+                rx_bits[bad] = phy.rx_receive(r, len(bad) * pk_per_stream, off, xor=False)[0].reshape(len(bad), pk_per_stream, -1)
+        else:
+            off = (b["starts"] + (torch.arange(n, device=dev) * r.stride(0))[:, None]).reshape(-1).contiguous()
+            rx_bits = phy.rx_receive(r, n * pk_per_stream, off, xor=False)[0].reshape(n, pk_per_stream, -1)
         cntr = torch.zeros(2, dtype=torch.int64, device=dev)
-        a = out[:, :nbytes].contiguous()
-        b = bits.reshape(n * pk_per_stream, -1)[:, :nbytes].contiguous()
-        phy.ber_count(a, b, a.numel() * 8, cntr)
-        e, nb = (int(v) for v in cntr.cpu())
+        a = rx_bits[:, :, :nbytes].contiguous()
+        t = bits[:, :, :nbytes].contiguous()
+        per_row = phy.bits_per_packet
+        if per_row % 8 == 0:
+            phy.ber_count(a, t, a.numel() * 8, cntr)
+            e, nb = (int(v) for v in cntr.cpu())
+        else:   # rows end inside a byte: pad bits are zero on both sides, so count bytes and report the true bit total
+            phy.ber_count(a, t, a.numel() * 8, cntr)
+            e = int(cntr[0])
+            nb = n * pk_per_stream * per_row
         return e, nb, fails
 
     return count
@@ -121,6 +105,7 @@ def main(argv=None):
     ap.add_argument("--lo", type=int, default=1)
     ap.add_argument("--hi", type=int, default=512)
     ap.add_argument("--fit", type=int, nargs=2, default=[125, 250])
+    ap.add_argument("--chunk", type=int, default=512, help="streams per device batch")
     args = ap.parse_args(argv)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -129,12 +114,28 @@ def main(argv=None):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     phy = Phy(N=args.N, cp=args.cp, lo=args.lo, hi=args.hi, fit_lo=args.fit[0], fit_hi=args.fit[1])
-    res = sweep(make_gpu_count_fn(phy), args.streams, args.snr, rank, world, dist if world > 1 else None,
-                tensor_factory=lambda a: torch.tensor(a, dtype=torch.int64, device=phy.device), chunk=64)
+    count_fn = make_gpu_count_fn(phy)
+    count_fn(shard_streams(args.streams, rank, world)[:8], args.snr[0])          # warm-up: plan tables, allocator, first launches
+    if world > 1:
+        dist.barrier(device_ids=[local])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = sweep(count_fn, args.streams, args.snr, rank, world, dist if world > 1 else None,
+                tensor_factory=lambda a: torch.tensor(a, dtype=torch.int64, device=phy.device), chunk=args.chunk)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=phy.device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)          # device-timed, max over ranks
     if rank == 0:
+        import hashlib
         print(json.dumps({"snr_db": args.snr, "bit_errors": res[:, 0].tolist(), "bits": res[:, 1].tolist(),
                           "sync_failures": res[:, 2].tolist(), "ber": (res[:, 0] / np.maximum(res[:, 1], 1)).tolist(),
-                          "world_size": world, "streams": args.streams}))
+                          "world_size": world, "streams": args.streams, "chunk": args.chunk, "seconds": float(ms) * 1e-3,
+                          "stream_snr_points_per_s": args.streams * len(args.snr) / (float(ms) * 1e-3),
+                          "counters_sha256": hashlib.sha256(np.ascontiguousarray(res).tobytes()).hexdigest(),
+                          "geometry": dict(N=args.N, cp=args.cp, lo=args.lo, hi=args.hi, fit=args.fit)}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -160,6 +160,16 @@ GF3_API int gf3_peak_pick(const gf3_plan* plan, const float* P, int64_t p_stride
                   int64_t T, const float* pmax, int64_t* peaks, int32_t max_peaks, int32_t* count,
                   void* work, void* stream);
 
+/* get_symbols' index bookkeeping (OFDM.py:393-397) for a batch of streams, on the device:
+ * zero_indicies = where(zeros) + 2 with the last detection (the terminating chirp) dropped, turned
+ * into packet offsets for gf3_rx_receive: pkt_offset[s*pk_expected + j] = s*r_stride + peaks[s][j] + 2.
+ *   ok [n_streams] uint8 or NULL: 1 when stream s holds exactly pk_expected packets (count ==
+ *   pk_expected + 1) and the last one ends inside its T samples -- where the reference's vstack /
+ *   reshape would succeed (OFDM.py:400-403); otherwise 0 and the offsets are clamped into the stream. */
+GF3_API int gf3_peaks_to_offsets(const gf3_plan* plan, const int64_t* peaks, const int32_t* count, int64_t n_streams,
+                         int32_t max_peaks, int64_t r_stride, int64_t T, int32_t pk_expected,
+                         int64_t* pkt_offset, uint8_t* ok, void* stream);
+
 /* ---- transmit chain ---------------------------------------------- */
 /* map + build_OFDM_symbol + ifft + add_cp + send_to_stream fused (OFDM.py:191-226, 244-259,
  * 322-323).  One launch writes whole packets [chirp | g*(P x known) | g*(L x data) | g*(P x
@@ -202,6 +212,16 @@ GF3_API int gf3_tx_frame(const gf3_plan* plan, const float* data_time, int64_t n
 GF3_API int gf3_channel_sim(const float* x, int64_t x_stride, int64_t n_streams, int64_t T,
                     const float* taps, int32_t n_taps, const float* sigma, uint64_t seed,
                     float* y, int64_t y_stride, void* stream);
+/* The same with an explicit Philox stream id per row (stream_ids [n_streams] int64): the noise of a row
+ * depends on (seed, id, sample index) only, not on the row's position in the batch -- what the
+ * stream-sharded sweep needs to be invariant under sharding. */
+GF3_API int gf3_channel_sim_ids(const float* x, int64_t x_stride, int64_t n_streams, int64_t T,
+                        const float* taps, int32_t n_taps, const float* sigma, const int64_t* stream_ids,
+                        uint64_t seed, float* y, int64_t y_stride, void* stream);
+/* Uniform random bytes for the synthetic workloads (payload bits, filler): row r is drawn from the Philox
+ * counter stream of row_ids[r] (NULL: r), so it does not depend on batching or sharding either. */
+GF3_API int gf3_random_bytes(uint8_t* out, int64_t out_stride, int64_t n_rows, int64_t row_bytes,
+                     const int64_t* row_ids, uint64_t seed, void* stream);
 /* PCM ingest (Final System Test.ipynb:85-86 does `r = r/1.0` on the wav's native samples): plain
  * value conversion to float32 on the device, no DC removal (the reference keeps the uint8 offset of
  * 128), so narrow samples cross PCIe instead of floats.  format: 0 = uint8, 1 = int16.           */
