@@ -408,9 +408,13 @@ def run_gpu_arm(args, cfg, streams, raw, desc):
         rec = (lambda i: ev[i].record()) if ev is not None else (lambda i: None)
         rec(0)
         if raw:
-            P, pmax = phy.xcorr(data)
-            rec(1)
-            pk, cnt = phy.peak_pick(P, pmax, T, 4)
+            if args.split_sync:          # the two entry points separately (stage timings of matched filter / detection walk)
+                P, pmax = phy.xcorr(data)
+                rec(1)
+                pk, cnt = phy.peak_pick(P, pmax, T, 4)
+            else:                        # gf3_sync_streams: matched filter + detection (block maxima let the walk skip most of P)
+                rec(1)
+                _, _, pk, cnt = phy.sync_streams(data, 4)
             off, ok = phy.peaks_to_offsets(pk, cnt, data.stride(0), T, 1)
             rec(2)
             phy.rx_receive(data, n_packets, off, xor=True, out=out_bits)
@@ -553,8 +557,10 @@ def run_gpu_arm(args, cfg, streams, raw, desc):
                 traffic = None
         if raw:
             xc_ms, pk_ms, rx_ms = seg[0], seg[1], seg[2]
+            if not args.split_sync:      # one call: seg[0] is empty, seg[1] = matched filter + detection + offsets
+                xc_ms, pk_ms = seg[1], 0.0
             Tb = 4.0 * T * n_packets                                        # one pass over the streams
-            roof = {"bound": "hbm", "kernel": "xcorr_fwd_kernel + xcorr_acc_kernel (matched filter: 4T read + 4T written per stream)",
+            roof = {"bound": "hbm", "kernel": "xcorr_fused_kernel (matched filter: 4T read + 4T written per stream)" + ("" if args.split_sync else " + detection walk (gf3_sync_streams)"),
                     "achieved": 2 * Tb / (xc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": 2 * Tb, "avg_launch_ms": xc_ms,
                     "stages_ms": {"matched_filter": xc_ms, "peak_pick_and_offsets": pk_ms, "receive_chain": rx_ms},
@@ -610,6 +616,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=None, help="streams per GPU (default: the workload's)")
+    ap.add_argument("--split-sync", action="store_true", help="c3-raw: time gf3_xcorr and gf3_peak_pick separately instead of gf3_sync_streams")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffer) legs (profiling runs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch (profiling runs)")

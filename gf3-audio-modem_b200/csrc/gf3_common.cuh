@@ -63,4 +63,6 @@ struct gf3_plan {
     float2* d_sync_tw;   // twiddles of the sync FFT plan
     float2* d_chirp_spec;  // [sync_parts][NB/2+1] spectrum of the time-reversed chirp partitions
     float* d_chirp;      // [chirp_len] sync chirp
+    float* d_chirp_pairs;  // [sync_parts][8][128] float4: the partitions in the fused matched filter's bin-pair layout, pre-scaled
+    float2* d_chirp_dc;    // [sync_parts] (H[0], H[M]) pre-scaled
 };

@@ -51,6 +51,34 @@ __device__ __forceinline__ float2 mul_nj(float2 a) { return make_float2(a.y, -a.
 __device__ __forceinline__ float2 pk_mul(float2 a, float2 b) { pk64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b))); return pk_unpack(d); }
 __device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) { pk64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk_pack(a)), "l"(pk_pack(b)), "l"(pk_pack(c))); return pk_unpack(d); }
 
+// 128-bit shared-memory load that the compiler may not split into (bank-conflicting) 32-bit loads
+__device__ __forceinline__ float4 lds128(const float4* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+
+// f32x2 arithmetic on values that stay packed in 64-bit register pairs (no repacking per use)
+__device__ __forceinline__ pk64 p_add(pk64 a, pk64 b) { pk64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk64 p_sub(pk64 a, pk64 b) { pk64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk64 p_mul(pk64 a, pk64 b) { pk64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk64 p_fma(pk64 a, pk64 b, pk64 c) { pk64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ pk64 p_neg(pk64 a) { const float2 v = pk_unpack(a); return pk_pack(make_float2(-v.x, -v.y)); }
+__device__ __forceinline__ pk64 p_bc(float s) { return pk_pack(make_float2(s, s)); }
+__device__ __forceinline__ float p_lo(pk64 a) { return pk_unpack(a).x; }
+__device__ __forceinline__ float p_hi(pk64 a) { return pk_unpack(a).y; }
+// Hide how a per-thread constant was derived, so that it is kept in its register pair instead of
+// being rebuilt from a related value (negate + move, or immediates) at every use inside the hot
+// loop.  A volatile round trip through the thread's own shared-memory slot is opaque to both
+// compiler stages.
+__device__ __forceinline__ pk64 p_opaque(pk64 v, void* slot) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
+    asm volatile("st.volatile.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+    pk64 r;
+    asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(r) : "r"(addr) : "memory");
+    return r;
+}
 // Compile-time cos / sin of 2*pi*num/den (exact quadrant reduction on the integers, Taylor series
 // on [0, pi/4]); evaluated in double, rounded to float where used, so in-register twiddles become
 // instruction immediates.
@@ -265,8 +293,12 @@ struct FftPlanT {
     static constexpr int MP = PAIRED ? T * ROWP : M + (M >> LOGPAD);   // complex points reserved per symbol
     __host__ __device__ static constexpr int rad(int p) { return p == 0 ? R0_ : p == 1 ? R1_ : R2_; }
     __host__ __device__ static constexpr int ns(int p) { return p == 0 ? 1 : p == 1 ? R0_ : R0_ * R1_; }
-    // twiddle table: pass p >= 1 holds Q*(rad-1)*T entries at offset tw_off(p)
-    static constexpr int TW1 = (R_ / R1_) * (R1_ - 1) * T;
+    // twiddle table: pass p >= 1 holds Q*(rad-1)*T entries at offset tw_off(p).  DEDUP1: when T is a multiple of
+    // the first radix, the pass-1 twiddle of column j = t + q T depends on j mod R0 = t mod R0 only, so the
+    // table keeps (rad-1)*R0 entries (N = 4096: 240 instead of 1920 -- 13 KB of shared memory per CTA);
+    // lanes t and t + R0 read the same address (broadcast), a warp touches one 128-byte line per load.
+    static constexpr bool DEDUP1 = !(GF3_FFT_PAIRED && (LOGN_ == 10)) && (T > R0_) && (T % R0_ == 0);
+    static constexpr int TW1 = DEDUP1 ? (R1_ - 1) * R0_ : (R_ / R1_) * (R1_ - 1) * T;
     static constexpr int TW2 = NPASS_ > 2 ? (R_ / R2_) * (R2_ - 1) * T : 0;
     __host__ __device__ static constexpr int tw_off(int p) { return p <= 1 ? 0 : TW1; }
     static constexpr int TW_TOTAL = TW1 + TW2;
@@ -316,7 +348,10 @@ __host__ __device__ constexpr int zstride() {
 // instruction of the last pass writes runs of consecutive bins, which are conflict-free in any
 // layout, and the bin-pair walk of the data-symbol kernel (ascending k, descending M-k) then reads
 // conflict-free too (with padding, 16 descending bins straddle a pad slot and collide 2-way).
-template <class P, int NTHREADS, int PASS, bool NATURAL = false>
+// STORE = false (last pass only): the pass ends with its results in registers -- x[q*RAD + i] is bin
+// base(q) + i*NS, base(q) = (j / NS) * (NS * RAD) + j % NS, j = t + q*T -- for callers that consume the
+// transform straight from registers (the matched filter writes its output samples to global memory).
+template <class P, int NTHREADS, int PASS, bool NATURAL = false, bool STORE = true>
 __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__ zs,
                                          const float2* __restrict__ tw, int t, int grp) {
     constexpr int RAD = P::rad(PASS), NS = P::ns(PASS), Q = P::R / RAD, STRIDE = P::M / RAD;
@@ -351,6 +386,15 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
                 x[i] = cmul(x[i], make_float2(w.x, w.y));
                 x[RAD + i] = cmul(x[RAD + i], make_float2(w.z, w.w));
             });
+        } else if constexpr (PASS == 1 && P::DEDUP1) {
+        static_for<Q>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            const float2* twp = tw + (t % NS);
+            static_for<RAD - 1>([&](auto ic) {
+                constexpr int i = decltype(ic)::value + 1;
+                x[q * RAD + i] = cmul(x[q * RAD + i], twp[(i - 1) * NS]);
+            });
+        });
         } else {
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
@@ -367,6 +411,10 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
         constexpr int q = decltype(qc)::value;
         Dft<RAD>::run(&x[q * RAD]);
     });
+    if constexpr (!STORE) {
+        static_assert(PASS == P::NPASS - 1 && !P::PAIRED, "register output is for the last pass of the unpaired plans");
+        return;
+    } else
     if constexpr (P::PAIRED && PASS == 0) {
         // row t of the T x R0 matrix, two columns per 128-bit store
         float4* dst = reinterpret_cast<float4*>(zs + t * P::ROWP);
@@ -418,12 +466,33 @@ __device__ __forceinline__ void fft_forward(float2 (&x)[P::R], float2* __restric
     }
 }
 
+// The same transform with the last pass left in registers (see fft_pass<.., STORE = false>).
+template <class P, int NTHREADS>
+__device__ __forceinline__ void fft_forward_to_regs(float2 (&x)[P::R], float2* __restrict__ zs,
+                                                    const float2* __restrict__ tw, int t, int grp) {
+    fft_pass<P, NTHREADS, 0>(x, zs, tw, t, grp);
+    if constexpr (P::NPASS > 2) {
+        fft_pass<P, NTHREADS, 1>(x, zs, tw, t, grp);
+        fft_pass<P, NTHREADS, 2, true, false>(x, zs, tw, t, grp);
+    } else {
+        fft_pass<P, NTHREADS, 1, true, false>(x, zs, tw, t, grp);
+    }
+}
+
 // Host-side: fill the twiddle table of plan P (double precision, rounded to float).
 template <class P>
 inline void fill_twiddles(float2* out) {
     for (int pass = 1; pass < P::NPASS; ++pass) {
         const int RAD = P::rad(pass), NS = P::ns(pass), Q = P::R / RAD;
         float2* o = out + P::tw_off(pass);
+        if (pass == 1 && P::DEDUP1) {
+            for (int i = 1; i < RAD; ++i)
+                for (int c = 0; c < NS; ++c) {
+                    const double ang = -2.0 * 3.14159265358979323846 * (double)(c * i) / (double)(NS * RAD);
+                    o[(i - 1) * NS + c] = make_float2((float)cos(ang), (float)sin(ang));
+                }
+            continue;
+        }
         for (int q = 0; q < Q; ++q)
             for (int i = 1; i < RAD; ++i)
                 for (int t = 0; t < P::T; ++t) {

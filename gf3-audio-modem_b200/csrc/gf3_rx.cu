@@ -106,34 +106,6 @@ __device__ __forceinline__ void load_symbol(float2 (&x)[P::R], const float* __re
     }
 }
 
-// 128-bit shared-memory load that the compiler may not split into (bank-conflicting) 32-bit loads
-__device__ __forceinline__ float4 lds128(const float4* p) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "r"((unsigned)__cvta_generic_to_shared(p)));
-    return v;
-}
-
-// f32x2 arithmetic on values that stay packed in 64-bit register pairs (no repacking per use)
-__device__ __forceinline__ pk64 p_add(pk64 a, pk64 b) { pk64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ pk64 p_sub(pk64 a, pk64 b) { pk64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ pk64 p_mul(pk64 a, pk64 b) { pk64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ pk64 p_fma(pk64 a, pk64 b, pk64 c) { pk64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ pk64 p_neg(pk64 a) { const float2 v = pk_unpack(a); return pk_pack(make_float2(-v.x, -v.y)); }
-__device__ __forceinline__ pk64 p_bc(float s) { return pk_pack(make_float2(s, s)); }
-__device__ __forceinline__ float p_lo(pk64 a) { return pk_unpack(a).x; }
-__device__ __forceinline__ float p_hi(pk64 a) { return pk_unpack(a).y; }
-// Hide how a per-thread constant was derived, so that it is kept in its register pair instead of
-// being rebuilt from a related value (negate + move, or immediates) at every use inside the hot
-// loop.  A volatile round trip through the thread's own shared-memory slot is opaque to both
-// compiler stages.
-__device__ __forceinline__ pk64 p_opaque(pk64 v, void* slot) {
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
-    asm volatile("st.volatile.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
-    pk64 r;
-    asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(r) : "r"(addr) : "memory");
-    return r;
-}
 // predicated one-byte shared-memory store: the address is an operand, so the compiler cannot sink its
 // computation into a branch around the store
 __device__ __forceinline__ void sts_u8_if(unsigned addr, unsigned val, unsigned cond) {

@@ -8,6 +8,8 @@
 //   xcorr_fwd_kernel : spectrum of every 50 %-overlapped input block           (4 B read, 8 B written / sample)
 //   xcorr_acc_kernel : Y_b = sum_p X_{b-p} H_p, inverse real FFT, last B samples, signed row max
 //   peak_pick_kernel : candidate mask + ascending hold-off scan, one CTA per stream
+#include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "gf3_common.cuh"
@@ -36,7 +38,7 @@ int make_chirp(gf3_plan* plan);                  // gf3_tx.cu
 // Spectrum layout per block: M complex values; element 0 packs (X[0], X[M]) (both real).
 
 struct FwdArgs {
-    const float* r;          // [n_streams, r_stride]
+    const void* r;           // [n_streams, r_stride] float32 / int16 / uint8 samples (template parameter S)
     float2* spec;            // [n_streams, nblk, M]
     const float2* tw;
     float* pmax;             // [n_streams] reset to -inf here (may be null)
@@ -51,6 +53,7 @@ struct FwdArgs {
 // Each 128-thread group transforms one block and untangles it itself: thread t owns the bin pairs
 // (k, M-k), k = t + 128 q, so bin, twiddle and addresses need no per-item index arithmetic.  The
 // next work item's samples are requested right after the FFT, so they fly during the untangle.
+template <class S>
 __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArgs a) {
     using P = SP;
     constexpr int NT = kSyncThreads, T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP, SF = NT / T;
@@ -77,9 +80,9 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
         const int64_t stream = live ? blk_global / a.nblk : 0;
         const int b = (int)(blk_global - stream * a.nblk);
         if (live && b == 0 && t == 0 && a.pmax) a.pmax[stream] = __int_as_float(0xff800000);
-        const float* row = a.r + stream * a.r_stride;
+        const S* row = reinterpret_cast<const S*>(a.r) + stream * a.r_stride;
         const int64_t s0 = (int64_t)b * kB - kB + a.in_off;
-        const bool fast = live && !a.reverse && s0 >= 0 && s0 + 2 * kB <= a.T && a.valid_len >= 2 * kB &&
+        const bool fast = sizeof(S) == 4 && live && !a.reverse && s0 >= 0 && s0 + 2 * kB <= a.T && a.valid_len >= 2 * kB &&
                           ((reinterpret_cast<uintptr_t>(row + s0) & 7) == 0);
         if (fast) {      // interior block, 8-byte aligned: vector loads without bounds checks
 #pragma unroll
@@ -94,11 +97,11 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
                     const bool ok0 = n >= 0 && n < a.T && loc < a.valid_len;
                     const bool ok1 = n + 1 >= 0 && n + 1 < a.T && loc + 1 < a.valid_len;
                     if (!a.reverse) {
-                        if (ok0) v0 = row[n];
-                        if (ok1) v1 = row[n + 1];
+                        if (ok0) v0 = (float)row[n];
+                        if (ok1) v1 = (float)row[n + 1];
                     } else {
-                        if (ok0) v0 = row[a.T - 1 - n];
-                        if (ok1) v1 = row[a.T - 2 - n];
+                        if (ok0) v0 = (float)row[a.T - 1 - n];
+                        if (ok1) v1 = (float)row[a.T - 2 - n];
                     }
                 }
                 x[i] = make_float2(v0, v1);
@@ -270,6 +273,293 @@ __global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fused matched filter: forward FFT + partition multiply-accumulate + inverse FFT of a run of
+// consecutive blocks in ONE persistent kernel.  The spectra of the last (parts - 1) input blocks
+// stay on chip, so DRAM sees every input sample once and every output sample once (the two-kernel
+// form above writes 8 bytes of spectrum per sample and reads them back `parts` times).
+//
+// One 128-thread CTA = one FFT group.  Thread t owns the bin pairs (k, M-k), k = t + 128 q (k = M/2
+// takes the slot of k = 0; thread 0 also carries the real pair (DC, Nyquist)) in every stage: it
+// untangles them after the forward FFT, multiplies them with the chirp partitions and turns them
+// into the inverse FFT's input.  The ring of past spectra is therefore THREAD-PRIVATE: slot s holds
+// the thread's own 8 pairs as float4 (re k, re M-k, im k, im M-k) -- 128-bit conflict-free accesses,
+// no barrier around it -- and the chirp partitions are read from an identically laid out global
+// table (48 KB for three partitions: L1 / L2 resident), pre-scaled by 1 / (2N) so that neither the
+// untangle's 1/2 nor the inverse transform's 1/N costs an instruction.  Both lanes of FFMA2 carry
+// the two bins of a pair.  The inverse FFT's last pass stays in registers and goes straight to
+// global memory (only the last B samples of a block are output samples).
+//
+// Work = (stream, output block) pairs in stream-major order; every CTA takes one contiguous range.
+// A CTA that starts in the middle of a stream first computes the (parts - 1) spectra before its
+// first block (forward FFTs only).
+// ------------------------------------------------------------------------------------------
+struct FusedArgs {
+    const void* r;           // [n_streams, r_stride] samples (float32 / int16 / uint8)
+    const float4* Hs;        // [parts][8][128] pair-interleaved chirp partitions, pre-scaled
+    const float2* Hdc;       // [parts] (H[0], H[M]) pre-scaled
+    const float2* tw;
+    float* P;                // [n_streams, p_stride]
+    float* pmax;             // [n_streams], preset to -inf
+    float* blockmax;         // [n_streams, nblk_out] or null
+    int64_t r_stride, p_stride, T, out_len, n_streams;
+    int nblk_in, nblk_out, parts;
+};
+
+template <class S> __device__ __forceinline__ float sample_to_f32(S v) { return (float)v; }
+
+template <class S, int MINB>
+__global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs a) {
+    using P = SP;
+    constexpr int NT = 128, T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP, Q = (M / 2) / NT;
+    static_assert(T == NT && Q == 8, "one FFT group per CTA");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* W = reinterpret_cast<float2*>(smem_raw);                       // [MP] FFT exchange / spectrum buffer
+    float2* tw = W + MP;                                                   // [TW_TOTAL]
+    float4* ring = reinterpret_cast<float4*>(tw + P::TW_TOTAL);            // [parts-1][Q][NT]
+    float2* ring_dc = reinterpret_cast<float2*>(ring + (size_t)(a.parts - 1) * Q * NT);   // [parts-1] (thread 0)
+    __shared__ float wmax[NT / 32];
+    const int tid = threadIdx.x;
+    const int R1 = a.parts - 1;
+    for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
+
+    // e^{j 2 pi k / N} of this thread's pairs (cos, sin): every twiddle of the two untangles derives from it
+    float2 cs[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int k = (q == 0 && tid == 0) ? M / 2 : tid + q * NT;
+        sincospif(2.0f * (float)k / (float)N, &cs[q].y, &cs[q].x);
+    }
+    const pk64 pm = pk_pack(make_float2(1.f, -1.f));
+
+    const int64_t total = a.n_streams * a.nblk_out;
+    const int64_t c_begin = total * blockIdx.x / gridDim.x, c_end = total * (blockIdx.x + 1) / gridDim.x;
+    const S* base = reinterpret_cast<const S*>(a.r);
+
+    // ---- samples of block bb of stream `st` in the FFT's first-pass layout x[i] = z[t + i T]
+    auto load_block = [&](float2 (&x)[R], int64_t st, int bb) {
+        const S* row = base + st * a.r_stride;
+        const int64_t s0 = (int64_t)bb * kB - kB;
+        const bool inside = bb >= 0 && bb < a.nblk_in && s0 >= 0 && s0 + 2 * kB <= a.T;
+        if constexpr (sizeof(S) == 4) {
+            if (inside && ((reinterpret_cast<uintptr_t>(row + s0) & 7) == 0)) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) x[i] = __ldg(reinterpret_cast<const float2*>(row + s0) + (tid + i * T));
+                return;
+            }
+        } else if constexpr (sizeof(S) == 2) {
+            if (inside && ((reinterpret_cast<uintptr_t>(row + s0) & 3) == 0)) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const short2 v = __ldg(reinterpret_cast<const short2*>(row + s0) + (tid + i * T));
+                    x[i] = make_float2((float)v.x, (float)v.y);
+                }
+                return;
+            }
+        } else {
+            if (inside && ((reinterpret_cast<uintptr_t>(row + s0) & 1) == 0)) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(row + s0) + (tid + i * T));
+                    x[i] = make_float2((float)v.x, (float)v.y);
+                }
+                return;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) {          // edge block / odd alignment: bounds-checked scalar loads, zero outside [0, T)
+            const int64_t n = s0 + 2 * (tid + i * T);
+            float v0 = 0.f, v1 = 0.f;
+            if (bb >= 0 && bb < a.nblk_in) {
+                if (n >= 0 && n < a.T) v0 = sample_to_f32(row[n]);
+                if (n + 1 >= 0 && n + 1 < a.T) v1 = sample_to_f32(row[n + 1]);
+            }
+            x[i] = make_float2(v0, v1);
+        }
+    };
+    // ---- forward FFT of x + untangle: 2 X of this thread's pairs as (re k, re M-k), (im k, im M-k)
+    auto forward = [&](float2 (&x)[R], pk64 (&xre)[Q], pk64 (&xim)[Q], float2& dcny) {
+        __syncthreads();                                   // W is free (previous block's transforms are done with it)
+        fft_forward<P, NT, true>(x, W, tw, tid, 0);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int k = (q == 0 && tid == 0) ? M / 2 : tid + q * NT;
+            const pk64 z1 = *reinterpret_cast<const pk64*>(W + k);
+            const pk64 z2 = *reinterpret_cast<const pk64*>(W + (M - k));
+            const pk64 sa = p_add(z1, z2);                 // (s.x, d.y)
+            const pk64 sd = p_sub(z1, z2);                 // (d.x, s.y)
+            // tt = w d, w = -j e^{-j theta} = (-sin, -cos): A = (wr, wi), B = (-wi, wr)
+            const pk64 wA = pk_pack(make_float2(-cs[q].y, -cs[q].x)), wB = pk_pack(make_float2(cs[q].x, -cs[q].y));
+            const pk64 tt = p_fma(p_bc(p_hi(sa)), wB, p_mul(p_bc(p_lo(sd)), wA));
+            xre[q] = p_fma(p_bc(p_lo(tt)), pm, p_bc(p_lo(sa)));      // (s.x + tt.x, s.x - tt.x)
+            xim[q] = p_fma(p_bc(p_hi(sd)), pm, p_bc(p_hi(tt)));      // (tt.y + s.y, tt.y - s.y)
+        }
+        const float2 z0 = W[0];
+        dcny = make_float2(2.f * (z0.x + z0.y), 2.f * (z0.x - z0.y));   // 2 X[0], 2 X[M] (both real)
+    };
+    auto ring_store = [&](int slot, const pk64 (&xre)[Q], const pk64 (&xim)[Q], float2 dcny) {
+        float4* rs = ring + (size_t)slot * Q * NT + tid;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const float2 re = pk_unpack(xre[q]), im = pk_unpack(xim[q]);
+            rs[q * NT] = make_float4(re.x, re.y, im.x, im.y);
+        }
+        if (tid == 0) ring_dc[slot] = dcny;
+    };
+    auto ring_zero = [&]() {
+        for (int sl = 0; sl < R1; ++sl) {
+            float4* rs = ring + (size_t)sl * Q * NT + tid;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) rs[q * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid == 0) ring_dc[sl] = make_float2(0.f, 0.f);
+        }
+    };
+
+    __syncthreads();                                       // twiddles staged
+    int64_t cur_stream = -1;
+    float2 x[R];
+#pragma unroll 1
+    for (int64_t c = c_begin; c < c_end; ++c) {
+        const int64_t stream = c / a.nblk_out;
+        const int b = (int)(c - stream * a.nblk_out);
+        pk64 xre[Q], xim[Q];
+        float2 dcny;
+        if (stream != cur_stream) {
+            // ---- (re)start: the ring holds the spectra of blocks b-1 .. b-(parts-1) (zero before the stream)
+            cur_stream = stream;
+            ring_zero();
+            for (int bb = b - R1; bb < b; ++bb) {
+                if (bb < 0 || bb >= a.nblk_in) continue;
+                load_block(x, stream, bb);
+                forward(x, xre, xim, dcny);
+                ring_store(bb % R1, xre, xim, dcny);
+            }
+            load_block(x, stream, b);
+        }
+        // ---- X_b
+        if (b < a.nblk_in) {
+            forward(x, xre, xim, dcny);
+        } else {                                            // past the last input sample: an all-zero block
+#pragma unroll
+            for (int q = 0; q < Q; ++q) xre[q] = xim[q] = 0ull;
+            dcny = make_float2(0.f, 0.f);
+        }
+        // the next block's samples fly while this one is multiplied and transformed back
+        if (c + 1 < c_end && (c + 1) / a.nblk_out == stream) load_block(x, stream, b + 1);
+
+        // ---- Y_b = sum_p X_{b-p} H_p   (re = pos - neg; all four products are plain FFMA2)
+        pk64 arp[Q], arn[Q], ai[Q];
+        float dc, ny;
+        {
+            const float4* Hp = a.Hs + tid;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float4 h = __ldg(Hp + q * NT);
+                const pk64 hre = pk_pack(make_float2(h.x, h.y)), him = pk_pack(make_float2(h.z, h.w));
+                arp[q] = p_mul(xre[q], hre);
+                arn[q] = p_mul(xim[q], him);
+                ai[q] = p_fma(xim[q], hre, p_mul(xre[q], him));
+            }
+            const float2 h0 = __ldg(a.Hdc);
+            dc = dcny.x * h0.x;
+            ny = dcny.y * h0.y;
+        }
+#pragma unroll 1
+        for (int p = 1; p <= R1; ++p) {
+            const int slot = ((b - p) % R1 + R1) % R1;
+            const float4* rs = ring + (size_t)slot * Q * NT + tid;
+            const float4* Hp = a.Hs + (size_t)p * Q * NT + tid;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float4 xv = rs[q * NT];
+                const float4 h = __ldg(Hp + q * NT);
+                const pk64 pre = pk_pack(make_float2(xv.x, xv.y)), pim = pk_pack(make_float2(xv.z, xv.w));
+                const pk64 hre = pk_pack(make_float2(h.x, h.y)), him = pk_pack(make_float2(h.z, h.w));
+                arp[q] = p_fma(pre, hre, arp[q]);
+                arn[q] = p_fma(pim, him, arn[q]);
+                ai[q] = p_fma(pre, him, ai[q]);
+                ai[q] = p_fma(pim, hre, ai[q]);
+            }
+            if (tid == 0) {
+                const float2 xv = ring_dc[slot], h0 = __ldg(a.Hdc + p);
+                dc = fmaf(xv.x, h0.x, dc);
+                ny = fmaf(xv.y, h0.y, ny);
+            }
+        }
+        if (R1 > 0) ring_store(b % R1, xre, xim, dcny);   // X_b replaces X_{b-(parts-1)}, which was read just above
+
+        // ---- inverse untangle: Z[k] = E + jO, E = Y[k] + conj Y[M-k], O = (Y[k] - conj Y[M-k]) e^{+j theta};
+        // the forward engine runs on conj Z
+        __syncthreads();                                   // every thread has read its part of the forward spectrum in W
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int k = (q == 0 && tid == 0) ? M / 2 : tid + q * NT;
+            const float2 yre = pk_unpack(p_sub(arp[q], arn[q])), yim = pk_unpack(ai[q]);
+            const float2 E = make_float2(yre.x + yre.y, yim.x - yim.y);
+            const float2 D = make_float2(yre.x - yre.y, yim.x + yim.y);
+            const float2 O = cmul(D, cs[q]);
+            W[k] = make_float2(E.x - O.y, -(E.y + O.x));
+            W[M - k] = make_float2(E.x + O.y, E.y - O.x);  // k = M/2: the same value to the same slot
+        }
+        if (tid == 0) W[0] = make_float2(dc + ny, ny - dc);
+        __syncthreads();
+        float2 y[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) y[i] = W[tid + i * T];
+        __syncthreads();
+        fft_forward_to_regs<P, NT>(y, W, tw, tid, 0);
+        // ---- last B samples of the block: z[m], m in [M/2, M): P[n0 + 2m] = Re z, P[n0 + 2m + 1] = -Im z.
+        // Last pass (radix 8, stride 256): y[q*8 + i] is z[tid + 128 q + 256 i]
+        float* Prow = a.P + stream * a.p_stride;
+        const int64_t n0 = (int64_t)b * kB - kB;
+        float lmax = __int_as_float(0xff800000);
+        const bool fast = n0 + 2 * M <= a.out_len && ((reinterpret_cast<uintptr_t>(Prow + n0) & 7) == 0);
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 4; i < 8; ++i) {
+                const int m = tid + q * T + 256 * i;
+                const float2 v = make_float2(y[q * 8 + i].x, -y[q * 8 + i].y);
+                const int64_t n = n0 + 2 * m;
+                if (fast) {
+                    *reinterpret_cast<float2*>(Prow + n) = v;
+                    lmax = fmaxf(lmax, fmaxf(v.x, v.y));
+                } else {
+                    if (n < a.out_len) { Prow[n] = v.x; lmax = fmaxf(lmax, v.x); }
+                    if (n + 1 < a.out_len) { Prow[n + 1] = v.y; lmax = fmaxf(lmax, v.y); }
+                }
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if ((tid & 31) == 0) wmax[tid >> 5] = lmax;
+        __syncthreads();
+        if (tid == 0) {
+            float mx = wmax[0];
+            for (int w = 1; w < NT / 32; ++w) mx = fmaxf(mx, wmax[w]);
+            if (a.blockmax) a.blockmax[stream * a.nblk_out + b] = mx;
+            if (mx > __int_as_float(0xff800000)) atomic_max_float(a.pmax + stream, mx);
+        }
+    }
+}
+
+// chirp-partition spectra [parts][M] (element 0 packs (H[0], H[M])) -> the fused kernel's pair layout, scaled
+__global__ void xcorr_pack_h_kernel(const float2* __restrict__ H, int parts, float scale, float4* __restrict__ Hs, float2* __restrict__ Hdc) {
+    constexpr int M = SP::M, NT = 128, Q = (M / 2) / NT;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= parts * Q * NT) return;
+    const int p = i / (Q * NT), q = (i / NT) % Q, t = i % NT;
+    const int k = (q == 0 && t == 0) ? M / 2 : t + q * NT;
+    const float2 h1 = H[(size_t)p * M + k], h2 = H[(size_t)p * M + (M - k)];
+    Hs[i] = make_float4(h1.x * scale, h2.x * scale, h1.y * scale, h2.y * scale);
+    if (q == 0 && t == 0) Hdc[p] = make_float2(H[(size_t)p * M].x * scale, H[(size_t)p * M].y * scale);
+}
+
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 // ------------------------------------------------------------------------------------------
 // chirp_method's detection rule + get_symbols' bookkeeping, one CTA per stream.
 //   zeros[i] = (D[i]*D[i+1] <= 0) & (Pn[i+1] > thresh),  Pn = P/pmax, D = diff(Pn), i in [0, len-2)
@@ -286,6 +576,8 @@ struct PeakArgs {
     int64_t n_streams, nw;       // nw = 32-bit words per stream = ceil((plen - 2) / 32)
     int32_t max_peaks, Lc;
     float thresh;
+    const float* blockmax;       // optional [n_streams, nblk]: maximum of every 2048-sample block of P (fused matched filter)
+    int32_t nblk;
 };
 
 // Phase 1, fully parallel: one candidate bit per position of `zeros` (OFDM.py:360-361).  A CTA takes
@@ -374,7 +666,33 @@ __global__ void __launch_bounds__(256) peak_pick_kernel(const PeakArgs a) {
     int64_t pos = 0;
     if (tid < 3) s_first[tid] = kNone;
     __syncthreads();
+    __shared__ int s_blk;
+    const float* bm = a.blockmax ? a.blockmax + stream * a.nblk : nullptr;
     for (int round = 0; pos < nz; ++round) {
+        if (bm) {
+            // A candidate at position i needs P[i+1] / pmax > thresh, so it lies in a block whose maximum passes
+            // the same test (x -> x * inv is monotonic for inv > 0; for inv <= 0 or NaN nothing is skipped).
+            // Jump to the first such block at or after the walk position: with one packet per stream all but a
+            // handful of the ~120 blocks are skipped, and P is read only around the chirp peaks.
+            if (inv > 0.f) {
+                int blk0 = (int)((pos + 1) / kB);
+                int first_hot;
+                for (;;) {
+                    if (tid == 0) s_blk = 0x7fffffff;
+                    __syncthreads();
+                    const int blk = blk0 + tid;
+                    if (blk < a.nblk && bm[blk] * inv > a.thresh) atomicMin(&s_blk, blk);
+                    __syncthreads();
+                    first_hot = s_blk;
+                    __syncthreads();
+                    if (first_hot != 0x7fffffff || blk0 + NT >= a.nblk) break;
+                    blk0 += NT;
+                }
+                if (first_hot == 0x7fffffff) break;                              // no block left that can hold a candidate
+                const int64_t p0 = (int64_t)first_hot * kB - 1;                  // position whose P[i+1] is the block's first sample
+                if (p0 > pos) pos = p0;
+            }
+        }
         const int slot = round % 3;
         const int64_t tb = pos & ~(int64_t)3;
         const int64_t base = tb + (int64_t)tid * PER;
@@ -439,18 +757,26 @@ __global__ void peaks_to_offsets_kernel(const int64_t* __restrict__ peaks, const
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static int run_fwd(const gf3_plan* plan, const float* r, int64_t r_stride, int64_t n_streams, int64_t T, int nblk, int reverse,
+static int run_fwd(const gf3_plan* plan, const void* r, int fmt, int64_t r_stride, int64_t n_streams, int64_t T, int nblk, int reverse,
                    int in_off, int valid_len, float2* spec, const float2* tw, float* pmax, cudaStream_t st) {
     constexpr int SF = kSyncThreads / SP::T;
     FwdArgs f;
     f.r = r; f.spec = spec; f.tw = tw; f.pmax = pmax; f.r_stride = r_stride; f.T = T; f.n_streams = n_streams;
     f.nblk = nblk; f.reverse = reverse; f.in_off = in_off; f.valid_len = valid_len;
     const size_t smem = (size_t)(SF * SP::MP + SP::TW_TOTAL) * sizeof(float2);
-    GF3_CHECK_CUDA(cudaFuncSetAttribute(xcorr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t gx = (n_streams * nblk + SF - 1) / SF;
     const int sms = plan->sm_count;
     if (gx > (int64_t)sms * GF3_XC_FWD_CTAS) gx = (int64_t)sms * GF3_XC_FWD_CTAS;   // 2 CTAs / SM resident, several rounds of them
-    xcorr_fwd_kernel<<<(unsigned)gx, kSyncThreads, smem, st>>>(f);
+    if (fmt == GF3_SAMPLE_F32) {
+        GF3_CHECK_CUDA(cudaFuncSetAttribute(xcorr_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        xcorr_fwd_kernel<float><<<(unsigned)gx, kSyncThreads, smem, st>>>(f);
+    } else if (fmt == GF3_SAMPLE_I16) {
+        GF3_CHECK_CUDA(cudaFuncSetAttribute(xcorr_fwd_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        xcorr_fwd_kernel<int16_t><<<(unsigned)gx, kSyncThreads, smem, st>>>(f);
+    } else {
+        GF3_CHECK_CUDA(cudaFuncSetAttribute(xcorr_fwd_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        xcorr_fwd_kernel<uint8_t><<<(unsigned)gx, kSyncThreads, smem, st>>>(f);
+    }
     GF3_LAUNCH_CHECK();
     return GF3_OK;
 }
@@ -465,14 +791,26 @@ int sync_plan_init(gf3_plan* plan) {
     else { rc = upload_twiddles(SP::LOGN, &plan->d_sync_tw); if (rc) return rc; }
     GF3_CHECK_CUDA(cudaMalloc(&plan->d_chirp_spec, (size_t)plan->sync_parts * SP::M * sizeof(float2)));
     // H_p = rfft_{2B}([h[pB .. pB+B), 0 ... 0]),  h[m] = chirp[Lc-1-m]  (fsweep of OFDM.py:357)
-    rc = run_fwd(plan, plan->d_chirp, 0, 1, p.chirp_len, plan->sync_parts, 1, kB, kB, plan->d_chirp_spec,
+    rc = run_fwd(plan, plan->d_chirp, GF3_SAMPLE_F32, 0, 1, p.chirp_len, plan->sync_parts, 1, kB, kB, plan->d_chirp_spec,
                  plan->d_sync_tw, nullptr, 0);
     if (rc) return rc;
+    {
+        constexpr int QN = (SP::M / 2);
+        GF3_CHECK_CUDA(cudaMalloc(&plan->d_chirp_pairs, (size_t)plan->sync_parts * QN * sizeof(float4)));
+        GF3_CHECK_CUDA(cudaMalloc(&plan->d_chirp_dc, (size_t)plan->sync_parts * sizeof(float2)));
+        const int n = plan->sync_parts * QN;
+        xcorr_pack_h_kernel<<<(n + 255) / 256, 256>>>(plan->d_chirp_spec, plan->sync_parts, 0.5f / (float)SP::N,
+                                                      reinterpret_cast<float4*>(plan->d_chirp_pairs), plan->d_chirp_dc);
+        GF3_LAUNCH_CHECK();
+    }
     GF3_CHECK_CUDA(cudaDeviceSynchronize());
     return GF3_OK;
 }
 
 void sync_plan_free(gf3_plan* plan) {
+    if (plan->d_chirp_pairs) cudaFree(plan->d_chirp_pairs);
+    if (plan->d_chirp_dc) cudaFree(plan->d_chirp_dc);
+    plan->d_chirp_pairs = nullptr; plan->d_chirp_dc = nullptr;
     if (plan->d_sync_tw && plan->d_sync_tw != plan->d_tw) cudaFree(plan->d_sync_tw);
     if (plan->d_chirp_spec) cudaFree(plan->d_chirp_spec);
     if (plan->d_chirp) cudaFree(plan->d_chirp);
@@ -495,30 +833,81 @@ static XcorrGeom xcorr_geom(const gf3_plan* plan, int64_t n_streams, int64_t T) 
     return g;
 }
 
-}  // namespace gf3
-
-using namespace gf3;
-
-extern "C" size_t gf3_xcorr_work_bytes(const gf3_plan* plan, int64_t n_streams, int64_t T) {
-    if (!plan || n_streams <= 0 || T <= 0) return 0;
-    const XcorrGeom g = xcorr_geom(plan, n_streams, T);
-    return g.per_stream * (size_t)g.tile;
+#ifndef GF3_XC_FUSED_MAX_PARTS
+#define GF3_XC_FUSED_MAX_PARTS 4      // ring of (parts - 1) x 16 KB spectra per CTA next to 33 KB of FFT buffer + twiddles
+#endif
+#ifndef GF3_XC_FUSED_MINB
+#define GF3_XC_FUSED_MINB 3
+#endif
+static size_t fused_smem(int parts) {
+    return (size_t)(SP::MP + SP::TW_TOTAL) * sizeof(float2) + (size_t)(parts - 1) * ((SP::M / 2) * sizeof(float4) + sizeof(float2)) + 16;
+}
+template <class S>
+static int fused_grid(const gf3_plan* plan, int* per_sm) {
+    auto kern = xcorr_fused_kernel<S, GF3_XC_FUSED_MINB>;
+    const size_t smem = fused_smem(plan->sync_parts);
+    GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GF3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, 128, smem));
+    if (*per_sm < 1) *per_sm = 1;
+    return GF3_OK;
+}
+// The fused kernel pays (parts - 1) extra forward FFTs per CTA (the spectra before its first block), so it needs
+// runs of blocks that are long against the partition count; otherwise (one long recording with a 21 600-tap
+// chirp: 11 partitions) the two-kernel form stays.  GF3_XCORR_PATH=fused|split overrides (experiments).
+static bool fused_applies(const gf3_plan* plan, int64_t n_streams, const XcorrGeom& g) {
+    if (const char* e = getenv("GF3_XCORR_PATH")) {
+        if (!strcmp(e, "split")) return false;
+        if (!strcmp(e, "fused")) return plan->sync_parts <= 8 && fused_smem(plan->sync_parts) <= 200 * 1024;
+    }
+    if (plan->sync_parts > GF3_XC_FUSED_MAX_PARTS) return false;
+    const int64_t total = n_streams * g.nblk_out;
+    const int64_t ctas = (int64_t)plan->sm_count * GF3_XC_FUSED_MINB;
+    return total / ctas >= 8 * (int64_t)(plan->sync_parts - 1) || total < ctas;
 }
 
-extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride, int64_t n_streams,
-                         int64_t T, float* P, int64_t p_stride, float* pmax, void* work, void* stream) {
-    GF3_REQUIRE(plan && r && P && pmax && work, "xcorr: null argument");
-    GF3_REQUIRE(n_streams >= 0 && T >= 1, "xcorr: bad sizes");
-    if (n_streams == 0) return GF3_OK;
+template <class S>
+static int launch_fused(const gf3_plan* plan, FusedArgs a, cudaStream_t st) {
+    int per_sm = 0;
+    int rc = fused_grid<S>(plan, &per_sm);
+    if (rc) return rc;
+    const int64_t total = a.n_streams * a.nblk_out;
+    int64_t grid = (int64_t)plan->sm_count * per_sm;
+    if (grid > total) grid = total;
+    fill_f32_kernel<<<(unsigned)((a.n_streams + 255) / 256), 256, 0, st>>>(a.pmax, a.n_streams, -INFINITY);
+    GF3_LAUNCH_CHECK();
+    if (getenv("GF3_DEBUG"))
+        fprintf(stderr, "[gf3] xcorr fused: parts=%d smem=%zu B grid=%lld (%d CTAs/SM) blocks=%lld\n", a.parts, fused_smem(a.parts),
+                (long long)grid, per_sm, (long long)total);
+    xcorr_fused_kernel<S, GF3_XC_FUSED_MINB><<<(unsigned)grid, 128, fused_smem(a.parts), st>>>(a);
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}
+
+// chirp_method's convolution for a batch of streams (OFDM.py:357-358); blockmax is optional
+static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_stride, int64_t n_streams, int64_t T,
+                        float* P, int64_t p_stride, float* pmax, float* blockmax, void* work, cudaStream_t st) {
     const XcorrGeom g = xcorr_geom(plan, n_streams, T);
     GF3_REQUIRE(p_stride >= g.out_len, "xcorr: p_stride %lld < T + chirp_len - 1 = %lld", (long long)p_stride, (long long)g.out_len);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    GF3_REQUIRE(fmt == GF3_SAMPLE_F32 || fmt == GF3_SAMPLE_I16 || fmt == GF3_SAMPLE_U8, "xcorr: unknown sample format %d", fmt);
+    if (fused_applies(plan, n_streams, g)) {
+        FusedArgs a;
+        a.r = r; a.Hs = reinterpret_cast<const float4*>(plan->d_chirp_pairs); a.Hdc = plan->d_chirp_dc; a.tw = plan->d_sync_tw;
+        a.P = P; a.pmax = pmax; a.blockmax = blockmax; a.r_stride = r_stride; a.p_stride = p_stride; a.T = T; a.out_len = g.out_len;
+        a.n_streams = n_streams; a.nblk_in = g.nblk_in; a.nblk_out = g.nblk_out; a.parts = plan->sync_parts;
+        if (fmt == GF3_SAMPLE_F32) return launch_fused<float>(plan, a, st);
+        if (fmt == GF3_SAMPLE_I16) return launch_fused<int16_t>(plan, a, st);
+        return launch_fused<uint8_t>(plan, a, st);
+    }
+    GF3_REQUIRE(work != nullptr, "xcorr: null work buffer");
+    GF3_REQUIRE(blockmax == nullptr, "xcorr: internal: block maxima come from the fused kernel only");
     float2* spec = reinterpret_cast<float2*>(work);
     const size_t smem = (size_t)(SP::MP + SP::TW_TOTAL) * sizeof(float2);
     GF3_CHECK_CUDA(cudaFuncSetAttribute(xcorr_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t esz = fmt == GF3_SAMPLE_F32 ? 4 : fmt == GF3_SAMPLE_I16 ? 2 : 1;
     for (int64_t s0 = 0; s0 < n_streams; s0 += g.tile) {
         const int64_t ns = (n_streams - s0 < g.tile) ? n_streams - s0 : g.tile;
-        int rc = run_fwd(plan, r + s0 * r_stride, r_stride, ns, T, g.nblk_in, 0, 0, 2 * kB, spec, plan->d_sync_tw, pmax + s0, st);
+        int rc = run_fwd(plan, reinterpret_cast<const char*>(r) + (size_t)(s0 * r_stride) * esz, fmt, r_stride, ns, T, g.nblk_in, 0, 0, 2 * kB,
+                         spec, plan->d_sync_tw, pmax + s0, st);
         if (rc) return rc;
         AccArgs a;
         a.spec = spec; a.H = plan->d_chirp_spec; a.tw = plan->d_sync_tw; a.P = P + s0 * p_stride; a.pmax = pmax + s0;
@@ -530,6 +919,84 @@ extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride,
         GF3_LAUNCH_CHECK();
     }
     return GF3_OK;
+}
+
+static int peak_pick_common(const gf3_plan* plan, const float* P, int64_t p_stride, int64_t n_streams, int64_t T, const float* pmax,
+                            const float* blockmax, int nblk, int64_t* peaks, int32_t max_peaks, int32_t* count, void* work,
+                            cudaStream_t st) {
+    PeakArgs a;
+    a.P = P; a.pmax = pmax; a.peaks = peaks; a.count = count; a.p_stride = p_stride;
+    a.plen = T + plan->p.chirp_len - 1; a.max_peaks = max_peaks; a.Lc = plan->p.chirp_len; a.thresh = plan->p.thresh;
+    GF3_REQUIRE(a.plen >= 3, "peak_pick: signal too short");
+    a.mask = reinterpret_cast<uint32_t*>(work);
+    a.n_streams = n_streams;
+    a.nw = (a.plen - 2 + 31) / 32;
+    a.blockmax = blockmax; a.nblk = nblk;
+    int64_t blocks = a.n_streams * ((a.nw + 63) / 64);               // chunks of 64 mask words
+    const int64_t cap = (int64_t)plan->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (n_streams >= 2 * (int64_t)plan->sm_count || (blockmax && n_streams >= plan->sm_count / 2)) {
+        // enough streams to fill the GPU: one pass, one CTA each (with block maxima even a few dozen streams are
+        // cheaper this way: the walk touches only the blocks around the chirp peaks)
+        peak_pick_kernel<<<(unsigned)n_streams, 256, 0, st>>>(a);
+        GF3_LAUNCH_CHECK();
+        return GF3_OK;
+    }
+    GF3_REQUIRE(work != nullptr, "peak_pick: null work buffer (gf3_peak_pick_work_bytes)");
+    peak_mark_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    GF3_LAUNCH_CHECK();
+    peak_scan_kernel<<<(unsigned)n_streams, 256, 0, st>>>(a);
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}
+
+}  // namespace gf3
+
+using namespace gf3;
+
+extern "C" size_t gf3_xcorr_work_bytes(const gf3_plan* plan, int64_t n_streams, int64_t T) {
+    if (!plan || n_streams <= 0 || T <= 0) return 0;
+    const XcorrGeom g = xcorr_geom(plan, n_streams, T);
+    if (fused_applies(plan, n_streams, g)) return 16;                 // the fused kernel keeps its spectra on chip
+    return g.per_stream * (size_t)g.tile;
+}
+
+extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride, int64_t n_streams,
+                         int64_t T, float* P, int64_t p_stride, float* pmax, void* work, void* stream) {
+    GF3_REQUIRE(plan && r && P && pmax && work, "xcorr: null argument");
+    GF3_REQUIRE(n_streams >= 0 && T >= 1, "xcorr: bad sizes");
+    if (n_streams == 0) return GF3_OK;
+    return xcorr_common(plan, r, GF3_SAMPLE_F32, r_stride, n_streams, T, P, p_stride, pmax, nullptr, work,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+// layout of gf3_sync_streams' work buffer: [block maxima | matched-filter scratch | candidate bit mask]
+static size_t sync_off_blockmax(const XcorrGeom& g, int64_t n_streams) { return (((size_t)n_streams * g.nblk_out * sizeof(float)) + 255) & ~(size_t)255; }
+
+extern "C" size_t gf3_sync_work_bytes(const gf3_plan* plan, int64_t n_streams, int64_t T) {
+    if (!plan || n_streams <= 0 || T <= 0) return 0;
+    const XcorrGeom g = xcorr_geom(plan, n_streams, T);
+    const size_t xw = (gf3_xcorr_work_bytes(plan, n_streams, T) + 255) & ~(size_t)255;
+    return sync_off_blockmax(g, n_streams) + xw + gf3_peak_pick_work_bytes(plan, n_streams, T) + 256;
+}
+
+extern "C" int gf3_sync_streams(const gf3_plan* plan, const void* r, int32_t sample_format, int64_t r_stride, int64_t n_streams,
+                                int64_t T, float* P, int64_t p_stride, float* pmax, int64_t* peaks, int32_t max_peaks,
+                                int32_t* count, void* work, void* stream) {
+    GF3_REQUIRE(plan && r && P && pmax && peaks && count && work, "sync_streams: null argument");
+    GF3_REQUIRE(max_peaks >= 1 && n_streams >= 0 && n_streams <= 0x7fffffff && T >= 1, "sync_streams: bad sizes");
+    if (n_streams == 0) return GF3_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const XcorrGeom g = xcorr_geom(plan, n_streams, T);
+    char* w = reinterpret_cast<char*>(work);
+    const bool fused = fused_applies(plan, n_streams, g);
+    float* blockmax = fused ? reinterpret_cast<float*>(w) : nullptr;
+    void* xwork = w + sync_off_blockmax(g, n_streams);
+    void* pwork = reinterpret_cast<char*>(xwork) + ((gf3_xcorr_work_bytes(plan, n_streams, T) + 255) & ~(size_t)255);
+    int rc = xcorr_common(plan, r, sample_format, r_stride, n_streams, T, P, p_stride, pmax, blockmax, xwork, st);
+    if (rc) return rc;
+    return peak_pick_common(plan, P, p_stride, n_streams, T, pmax, blockmax, g.nblk_out, peaks, max_peaks, count, pwork, st);
 }
 
 extern "C" size_t gf3_peak_pick_work_bytes(const gf3_plan* plan, int64_t n_streams, int64_t T) {
@@ -545,28 +1012,8 @@ extern "C" int gf3_peak_pick(const gf3_plan* plan, const float* P, int64_t p_str
     GF3_REQUIRE(max_peaks >= 1 && n_streams >= 0 && n_streams <= 0x7fffffff, "peak_pick: bad sizes");
     if (n_streams == 0) return GF3_OK;
     GF3_REQUIRE(work != nullptr, "peak_pick: null work buffer (gf3_peak_pick_work_bytes)");
-    PeakArgs a;
-    a.P = P; a.pmax = pmax; a.peaks = peaks; a.count = count; a.p_stride = p_stride;
-    a.plen = T + plan->p.chirp_len - 1; a.max_peaks = max_peaks; a.Lc = plan->p.chirp_len; a.thresh = plan->p.thresh;
-    GF3_REQUIRE(a.plen >= 3, "peak_pick: signal too short");
-    a.mask = reinterpret_cast<uint32_t*>(work);
-    a.n_streams = n_streams;
-    a.nw = (a.plen - 2 + 31) / 32;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int64_t blocks = a.n_streams * ((a.nw + 63) / 64);               // chunks of 64 mask words
-    const int64_t cap = (int64_t)plan->sm_count * 32;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    if (n_streams >= 2 * (int64_t)plan->sm_count) {                  // enough streams to fill the GPU: one pass, one CTA each
-        peak_pick_kernel<<<(unsigned)n_streams, 256, 0, st>>>(a);
-        GF3_LAUNCH_CHECK();
-        return GF3_OK;
-    }
-    peak_mark_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
-    GF3_LAUNCH_CHECK();
-    peak_scan_kernel<<<(unsigned)n_streams, 256, 0, st>>>(a);
-    GF3_LAUNCH_CHECK();
-    return GF3_OK;
+    return peak_pick_common(plan, P, p_stride, n_streams, T, pmax, nullptr, 0, peaks, max_peaks, count, work,
+                            reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gf3_peaks_to_offsets(const gf3_plan* plan, const int64_t* peaks, const int32_t* count, int64_t n_streams,

@@ -195,6 +195,25 @@ class Phy:
                                      _ptr(count), _ptr(work), _STREAM))
         return peaks, count
 
+    _FMT = {torch.uint8: 0, torch.int16: 1, torch.float32: 2}       # GF3_SAMPLE_*
+
+    def sync_streams(self, r, max_peaks=8):
+        """chirp_method (OFDM.py:356-372) for a batch of streams in one call (gf3_sync_streams): r [B, T] float32,
+        int16 or uint8 -> (P [B, T+Lc-1], pmax [B], peaks int64 [B, max_peaks], count int32 [B])."""
+        assert r.is_cuda and r.dim() == 2 and r.stride(1) == 1 and r.dtype in self._FMT
+        B, T = r.shape
+        rs = r.stride(0) if B > 1 else T
+        plen = T + self.chirp_len - 1
+        pstride = (plen + 3) // 4 * 4
+        P = torch.empty((B, pstride), dtype=torch.float32, device=self.device)
+        pmax = torch.empty((B,), dtype=torch.float32, device=self.device)
+        peaks = torch.full((B, max_peaks), -1, dtype=torch.int64, device=self.device)
+        count = torch.empty((B,), dtype=torch.int32, device=self.device)
+        work = torch.empty((max(16, int(self.lib.gf3_sync_work_bytes(self._plan, B, T))),), dtype=torch.uint8, device=self.device)
+        check(self._call("gf3_sync_streams", self._plan, _ptr(r), self._FMT[r.dtype], rs, B, T, _ptr(P), pstride, _ptr(pmax),
+                         _ptr(peaks), max_peaks, _ptr(count), _ptr(work), _STREAM))
+        return P[:, :plen], pmax, peaks, count
+
     def peaks_to_offsets(self, peaks, count, r_stride, T, pk_expected):
         """get_symbols' bookkeeping on the device (OFDM.py:393-397): detections of a batch of streams ->
         (pkt_offset int64 [B * pk_expected] into the flat sample array, ok uint8 [B])."""
@@ -214,8 +233,7 @@ class Phy:
         self._f32(r)
         assert r.dim() == 2
         B, T = r.shape
-        P, pmax = self.xcorr(r)
-        peaks, count = self.peak_pick(P, pmax, T, pk_expected + 3)
+        _, _, peaks, count = self.sync_streams(r, pk_expected + 3)
         off, ok = self.peaks_to_offsets(peaks, count, r.stride(0), T, pk_expected)
         res, Hs, He, slope = self.rx_receive(r, B * pk_expected, off, xor=xor, want_eq=want_eq, out=out)   # offsets are relative to r's first sample
         d = dict(bits=res[0] if want_eq else res, ok=ok, peaks=peaks, count=count, Hs=Hs, He=He, slope=slope, pkt_offset=off)

@@ -36,6 +36,10 @@ extern "C" {
 #define GF3_API
 #endif
 
+/* sample formats of received audio: float32, or PCM as recorded (Final System Test.ipynb:85-86 reads an
+ * 8-bit wav and converts with r/1.0): plain value conversion, no scaling, no DC removal */
+enum { GF3_SAMPLE_U8 = 0, GF3_SAMPLE_I16 = 1, GF3_SAMPLE_F32 = 2 };
+
 enum {
     GF3_OK = 0,
     GF3_ERR_INVALID = -1,   /* bad argument / unsupported parameter combination */
@@ -159,6 +163,17 @@ GF3_API size_t gf3_peak_pick_work_bytes(const gf3_plan* plan, int64_t n_streams,
 GF3_API int gf3_peak_pick(const gf3_plan* plan, const float* P, int64_t p_stride, int64_t n_streams,
                   int64_t T, const float* pmax, int64_t* peaks, int32_t max_peaks, int32_t* count,
                   void* work, void* stream);
+
+/* chirp_method (OFDM.py:356-372) for a batch of streams in one call: gf3_xcorr + gf3_peak_pick, reading the
+ * samples in their native format (sample_format: GF3_SAMPLE_*; r_stride in samples).  When the chirp spans at
+ * most four 2048-sample partitions the matched filter runs as ONE fused kernel (forward FFT, partition
+ * multiply-accumulate and inverse FFT with the spectra kept on chip) that also records the maximum of every
+ * 2048-sample block of P, and the detection walk then reads P only inside blocks that can reach the threshold.
+ * P, pmax, peaks, count as in gf3_xcorr / gf3_peak_pick; work: gf3_sync_work_bytes() bytes of device scratch. */
+GF3_API size_t gf3_sync_work_bytes(const gf3_plan* plan, int64_t n_streams, int64_t T);
+GF3_API int gf3_sync_streams(const gf3_plan* plan, const void* r, int32_t sample_format, int64_t r_stride, int64_t n_streams,
+                     int64_t T, float* P, int64_t p_stride, float* pmax, int64_t* peaks, int32_t max_peaks,
+                     int32_t* count, void* work, void* stream);
 
 /* get_symbols' index bookkeeping (OFDM.py:393-397) for a batch of streams, on the device:
  * zero_indicies = where(zeros) + 2 with the last detection (the terminating chirp) dropped, turned
