@@ -508,12 +508,13 @@ def run_gpu_arm(args, cfg, streams, raw, desc):
                 q_ms = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=phy.device)
                 if world > 1:
                     dist.all_reduce(q_ms, op=dist.ReduceOp.MAX)
+                # the same entry points on the same samples already resident on the device
                 if qf is None:
                     ref_dev = out_bits
                 elif raw:
-                    ref_dev = phy.receive_streams(qf, 1, xor=True)["bits"]
+                    ref_dev = phy.receive_streams(q, 1, xor=True)["bits"]
                 else:
-                    ref_dev = phy.rx_receive(qf.reshape(-1), n_packets, xor=True)[0]
+                    ref_dev = phy.rx_receive_pcm(q.reshape(-1), n_packets, xor=True)[0]
                 e2e_legs[key] = {"value": world * n_packets * phy.bits_per_packet * e_steps / (float(q_ms) * 1e-3) / 1e6, "unit": UNIT,
                                  "h2d_bytes_per_step": hr.h2d_bytes, "d2h_bytes_per_step": hr.d2h_bytes, "steps": e_steps,
                                  "api": "gf3b200.host.HostReceiver.run (%s %s in pinned host memory -> packed bits in pinned host memory, %d CUDA streams, chunks of %d)"

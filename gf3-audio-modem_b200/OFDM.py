@@ -297,14 +297,13 @@ class receiver(transmitter):
         import torch
         phy = self.phy
         r = np.asarray(r)
-        if r.dtype in (np.uint8, np.int16):      # PCM as recorded: narrow samples cross PCIe, exact conversion on the device
-            d_r = phy.pcm_to_f32(torch.from_numpy(np.ascontiguousarray(r).reshape(1, -1)).to(phy.device))
+        if r.dtype in (np.uint8, np.int16):      # PCM as recorded: the narrow samples cross PCIe and are read by the kernels as they are
+            d_r = torch.from_numpy(np.ascontiguousarray(r).reshape(1, -1)).to(phy.device)
         else:
             d_r = torch.from_numpy(np.ascontiguousarray(r, dtype=np.float32).reshape(1, -1)).to(phy.device)
         T = d_r.shape[1]
-        P, pmax = phy.xcorr(d_r)
         max_peaks = max(4, T // max(1, phy.chirp_len) + 2)
-        peaks, count = phy.peak_pick(P, pmax, T, max_peaks)
+        _, _, peaks, count = phy.sync_streams(d_r, max_peaks)
         n = int(count[0].item())
         return peaks[0, :n].cpu().numpy(), T + phy.chirp_len - 3, d_r
 
@@ -403,8 +402,10 @@ class receiver(transmitter):
         return self._demod_device(d, n_packets, None, want_eq)
 
     def _demod_device(self, d_samples, n_packets, d_off, want_eq):
+        import torch
         phy = self.phy
-        res, Hs, He, slope = phy.rx_receive(d_samples, n_packets, d_off, xor=(self.encoding == "XOR"), want_eq=want_eq)
+        rx = phy.rx_receive if d_samples.dtype == torch.float32 else phy.rx_receive_pcm
+        res, Hs, He, slope = rx(d_samples, n_packets, d_off, xor=(self.encoding == "XOR"), want_eq=want_eq)
         bits_packed, eq = res if want_eq else (res, None)
         out = dict(bits=phy.unpack_bits(bits_packed), Hs=Hs.cpu().numpy().astype(np.complex128),
                    He=He.cpu().numpy().astype(np.complex128), slope=slope.cpu().numpy())

@@ -17,7 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, os.environ.get("GF3_LIB_NAME", "libgf3b200.so"))   # experiments: alternate name + flags
-SOURCES = ["gf3_lib.cu", "gf3_rx.cu", "gf3_tx.cu", "gf3_sync.cu", "gf3_chan.cu", "gf3_stage.cu"]
+SOURCES = ["gf3_lib.cu", "gf3_rx.cu", "gf3_rx_staged_u8.cu", "gf3_rx_staged_i16.cu", "gf3_rx_staged_f32.cu", "gf3_tx.cu", "gf3_sync.cu",
+           "gf3_chan.cu", "gf3_stage.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

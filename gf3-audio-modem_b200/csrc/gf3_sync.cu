@@ -309,7 +309,7 @@ struct FusedArgs {
 
 template <class S> __device__ __forceinline__ float sample_to_f32(S v) { return (float)v; }
 
-template <class S, int MINB>
+template <class S, int PARTS, int MINB>
 __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs a) {
     using P = SP;
     constexpr int NT = 128, T = P::T, R = P::R, M = P::M, N = P::N, MP = P::MP, Q = (M / 2) / NT;
@@ -318,10 +318,10 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
     float2* W = reinterpret_cast<float2*>(smem_raw);                       // [MP] FFT exchange / spectrum buffer
     float2* tw = W + MP;                                                   // [TW_TOTAL]
     float4* ring = reinterpret_cast<float4*>(tw + P::TW_TOTAL);            // [parts-1][Q][NT]
-    float2* ring_dc = reinterpret_cast<float2*>(ring + (size_t)(a.parts - 1) * Q * NT);   // [parts-1] (thread 0)
+    float2* ring_dc = reinterpret_cast<float2*>(ring + (size_t)(PARTS - 1) * Q * NT);     // [parts-1] (thread 0)
     __shared__ float wmax[NT / 32];
     const int tid = threadIdx.x;
-    const int R1 = a.parts - 1;
+    constexpr int R1 = PARTS - 1;
     for (int i = tid; i < P::TW_TOTAL; i += NT) tw[i] = a.tw[i];
 
     // e^{j 2 pi k / N} of this thread's pairs (cos, sin): every twiddle of the two untangles derives from it
@@ -345,7 +345,10 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
         if constexpr (sizeof(S) == 4) {
             if (inside && ((reinterpret_cast<uintptr_t>(row + s0) & 7) == 0)) {
 #pragma unroll
-                for (int i = 0; i < R; ++i) x[i] = __ldg(reinterpret_cast<const float2*>(row + s0) + (tid + i * T));
+                for (int i = 0; i < R; ++i) {            // streaming: do not evict the chirp partitions from L1
+                    const float* sp = reinterpret_cast<const float*>(row + s0) + 2 * (tid + i * T);
+                    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(x[i].x), "=f"(x[i].y) : "l"(sp));
+                }
                 return;
             }
         } else if constexpr (sizeof(S) == 2) {
@@ -408,6 +411,7 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
         if (tid == 0) ring_dc[slot] = dcny;
     };
     auto ring_zero = [&]() {
+#pragma unroll
         for (int sl = 0; sl < R1; ++sl) {
             float4* rs = ring + (size_t)sl * Q * NT + tid;
 #pragma unroll
@@ -429,11 +433,14 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
             // ---- (re)start: the ring holds the spectra of blocks b-1 .. b-(parts-1) (zero before the stream)
             cur_stream = stream;
             ring_zero();
-            for (int bb = b - R1; bb < b; ++bb) {
-                if (bb < 0 || bb >= a.nblk_in) continue;
-                load_block(x, stream, bb);
-                forward(x, xre, xim, dcny);
-                ring_store(bb % R1, xre, xim, dcny);
+            if constexpr (R1 > 0) {
+#pragma unroll 1
+                for (int bb = b - R1; bb < b; ++bb) {
+                    if (bb < 0 || bb >= a.nblk_in) continue;
+                    load_block(x, stream, bb);
+                    forward(x, xre, xim, dcny);
+                    ring_store(bb % R1, xre, xim, dcny);
+                }
             }
             load_block(x, stream, b);
         }
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
             dc = dcny.x * h0.x;
             ny = dcny.y * h0.y;
         }
-#pragma unroll 1
+#pragma unroll
         for (int p = 1; p <= R1; ++p) {
             const int slot = ((b - p) % R1 + R1) % R1;
             const float4* rs = ring + (size_t)slot * Q * NT + tid;
@@ -487,7 +494,7 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
                 ny = fmaf(xv.y, h0.y, ny);
             }
         }
-        if (R1 > 0) ring_store(b % R1, xre, xim, dcny);   // X_b replaces X_{b-(parts-1)}, which was read just above
+        if constexpr (R1 > 0) ring_store(b % R1, xre, xim, dcny);   // X_b replaces X_{b-(parts-1)}, which was read just above
 
         // ---- inverse untangle: Z[k] = E + jO, E = Y[k] + conj Y[M-k], O = (Y[k] - conj Y[M-k]) e^{+j theta};
         // the forward engine runs on conj Z
@@ -842,45 +849,63 @@ static XcorrGeom xcorr_geom(const gf3_plan* plan, int64_t n_streams, int64_t T) 
 static size_t fused_smem(int parts) {
     return (size_t)(SP::MP + SP::TW_TOTAL) * sizeof(float2) + (size_t)(parts - 1) * ((SP::M / 2) * sizeof(float4) + sizeof(float2)) + 16;
 }
-template <class S>
-static int fused_grid(const gf3_plan* plan, int* per_sm) {
-    auto kern = xcorr_fused_kernel<S, GF3_XC_FUSED_MINB>;
-    const size_t smem = fused_smem(plan->sync_parts);
-    GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GF3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, 128, smem));
-    if (*per_sm < 1) *per_sm = 1;
-    return GF3_OK;
+// CTAs per SM of the fused kernel: 3 (<= 168 registers) or 2 (<= 255 registers; the shared-memory carve-out then
+// leaves ~120 KB of L1, enough to keep the chirp partitions resident).  GF3_XC_MINB=2|3 overrides (experiments).
+static int fused_minb() {
+    if (const char* e = getenv("GF3_XC_MINB")) return atoi(e) == 2 ? 2 : 3;
+    return GF3_XC_FUSED_MINB;
 }
 // The fused kernel pays (parts - 1) extra forward FFTs per CTA (the spectra before its first block), so it needs
 // runs of blocks that are long against the partition count; otherwise (one long recording with a 21 600-tap
 // chirp: 11 partitions) the two-kernel form stays.  GF3_XCORR_PATH=fused|split overrides (experiments).
 static bool fused_applies(const gf3_plan* plan, int64_t n_streams, const XcorrGeom& g) {
+    if (plan->sync_parts > GF3_XC_FUSED_MAX_PARTS) return false;
     if (const char* e = getenv("GF3_XCORR_PATH")) {
         if (!strcmp(e, "split")) return false;
-        if (!strcmp(e, "fused")) return plan->sync_parts <= 8 && fused_smem(plan->sync_parts) <= 200 * 1024;
+        if (!strcmp(e, "fused")) return true;
     }
-    if (plan->sync_parts > GF3_XC_FUSED_MAX_PARTS) return false;
     const int64_t total = n_streams * g.nblk_out;
-    const int64_t ctas = (int64_t)plan->sm_count * GF3_XC_FUSED_MINB;
+    const int64_t ctas = (int64_t)plan->sm_count * fused_minb();
     return total / ctas >= 8 * (int64_t)(plan->sync_parts - 1) || total < ctas;
 }
 
-template <class S>
-static int launch_fused(const gf3_plan* plan, FusedArgs a, cudaStream_t st) {
+template <class S, int PARTS, int MINB>
+static int launch_fused_t(const gf3_plan* plan, const FusedArgs& a, cudaStream_t st) {
+    auto kern = xcorr_fused_kernel<S, PARTS, MINB>;
+    const size_t smem = fused_smem(PARTS);
     int per_sm = 0;
-    int rc = fused_grid<S>(plan, &per_sm);
-    if (rc) return rc;
+    GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GF3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > MINB) per_sm = MINB;
     const int64_t total = a.n_streams * a.nblk_out;
     int64_t grid = (int64_t)plan->sm_count * per_sm;
     if (grid > total) grid = total;
     fill_f32_kernel<<<(unsigned)((a.n_streams + 255) / 256), 256, 0, st>>>(a.pmax, a.n_streams, -INFINITY);
     GF3_LAUNCH_CHECK();
     if (getenv("GF3_DEBUG"))
-        fprintf(stderr, "[gf3] xcorr fused: parts=%d smem=%zu B grid=%lld (%d CTAs/SM) blocks=%lld\n", a.parts, fused_smem(a.parts),
+        fprintf(stderr, "[gf3] xcorr fused: parts=%d smem=%zu B grid=%lld (%d CTAs/SM) blocks=%lld\n", PARTS, smem,
                 (long long)grid, per_sm, (long long)total);
-    xcorr_fused_kernel<S, GF3_XC_FUSED_MINB><<<(unsigned)grid, 128, fused_smem(a.parts), st>>>(a);
+    kern<<<(unsigned)grid, 128, smem, st>>>(a);
     GF3_LAUNCH_CHECK();
     return GF3_OK;
+}
+template <class S, int MINB>
+static int launch_fused_p(const gf3_plan* plan, const FusedArgs& a, cudaStream_t st) {
+    switch (a.parts) {
+        case 1: return launch_fused_t<S, 1, MINB>(plan, a, st);
+        case 2: return launch_fused_t<S, 2, MINB>(plan, a, st);
+        case 3: return launch_fused_t<S, 3, MINB>(plan, a, st);
+        case 4: return launch_fused_t<S, 4, MINB>(plan, a, st);
+        default: gf3::set_error("xcorr fused: %d partitions not supported", a.parts); return GF3_ERR_INVALID;
+    }
+}
+template <class S>
+static int launch_fused(const gf3_plan* plan, const FusedArgs& a, cudaStream_t st) {
+    if constexpr (sizeof(S) == 4) {
+        if (fused_minb() == 2) return launch_fused_p<S, 2>(plan, a, st);
+    }
+    return launch_fused_p<S, GF3_XC_FUSED_MINB>(plan, a, st);
 }
 
 // chirp_method's convolution for a batch of streams (OFDM.py:357-358); blockmax is optional

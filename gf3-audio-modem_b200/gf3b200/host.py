@@ -68,10 +68,9 @@ class HostReceiver:
         self.row = raw_T if raw_T is not None else phy.pkt_samples
         self.streams = [torch.cuda.Stream(device=phy.device) for _ in range(n_streams)]
         pcm = sample_dtype != torch.float32
-        # PCM packets are converted inside the receive kernels (no float copy of the batch in HBM); raw PCM streams
-        # are expanded once for the matched filter, which then feeds the receive chain from the same floats
-        self.in_kernel = pcm and raw_T is None and hasattr(phy, "rx_receive_pcm")
-        self.ingest = "float32" if not pcm else ("in-kernel (gf3_rx_receive_pcm)" if self.in_kernel else "device pass (gf3_pcm_to_f32)")
+        # no float copy of a PCM batch ever exists in HBM
+        self.in_kernel = pcm                     # PCM is converted inside the kernels (matched filter and receive chain alike)
+        self.ingest = "float32" if not pcm else "in-kernel (gf3_sync_streams / gf3_rx_receive_pcm read the PCM samples)"
         self.d_in = None if self.in_kernel else [torch.empty((self.chunk, self.row), dtype=torch.float32, device=phy.device) for _ in self.streams]
         self.d_pcm = [torch.empty((self.chunk, self.row), dtype=sample_dtype, device=phy.device) for _ in self.streams] if pcm else None
         self.d_out = [torch.empty((self.chunk, phy.bits_stride), dtype=torch.uint8, device=phy.device) for _ in self.streams]
@@ -99,7 +98,7 @@ class HostReceiver:
                         d = self.d_in[k][:n]
                         phy.pcm_to_f32(self.d_pcm[k][:n], out=d)
                 if self.raw_T is not None:
-                    phy.receive_streams(d, 1, xor=xor, out=self.d_out[k][:n])
+                    phy.receive_streams(self.d_pcm[k][:n] if self.in_kernel else d, 1, xor=xor, out=self.d_out[k][:n])
                 elif self.in_kernel:
                     phy.rx_receive_pcm(self.d_pcm[k][:n].reshape(-1), n, xor=xor, out=self.d_out[k][:n])
                 else:

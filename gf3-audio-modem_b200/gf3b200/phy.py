@@ -84,6 +84,8 @@ class Phy:
         self.known = torch.from_numpy(known).to(self.device)
         # does gf3_rx_receive run the channel estimate inside the data-symbol launch for this geometry?
         self.fused_receive = bool(self.lib.gf3_rx_receive_is_fused(self._plan))
+        # float32 raw streams: staged input for the receive chain?  (GF3_STREAMS_STAGED=0/1 overrides the default)
+        self.staged_streams = os.environ.get("GF3_STREAMS_STAGED", "0") == "1"
         kb = ks[: 2 * self.Nd].reshape(self.Nd, 2)
         self.xor2 = torch.from_numpy(((kb[:, 0] << 1) | kb[:, 1]).astype(np.uint8)).to(self.device)   # OFDM.py:542
 
@@ -230,12 +232,16 @@ class Phy:
         pk_expected packets each: matched filter -> detection rule -> packet offsets -> fused receive chain,
         everything on the device.  -> dict(bits [B * pk_expected, bits_stride], ok uint8 [B] (1: the stream's
         chirps were found where the reference's slicing would succeed), peaks, count, Hs, He, slope[, eq])."""
-        self._f32(r)
-        assert r.dim() == 2
+        assert r.is_cuda and r.dim() == 2 and r.stride(1) == 1 and r.dtype in self._FMT
         B, T = r.shape
         _, _, peaks, count = self.sync_streams(r, pk_expected + 3)
         off, ok = self.peaks_to_offsets(peaks, count, r.stride(0), T, pk_expected)
-        res, Hs, He, slope = self.rx_receive(r, B * pk_expected, off, xor=xor, want_eq=want_eq, out=out)   # offsets are relative to r's first sample
+        # offsets are relative to r's first sample.  PCM samples (and, when staged is set, float32 ones: packets of a
+        # raw stream start at arbitrary sample offsets) enter the receive kernels through the staging buffer
+        if r.dtype != torch.float32 or self.staged_streams:
+            res, Hs, He, slope = self.rx_receive_pcm(r, B * pk_expected, off, xor=xor, want_eq=want_eq, out=out)
+        else:
+            res, Hs, He, slope = self.rx_receive(r, B * pk_expected, off, xor=xor, want_eq=want_eq, out=out)
         d = dict(bits=res[0] if want_eq else res, ok=ok, peaks=peaks, count=count, Hs=Hs, He=He, slope=slope, pkt_offset=off)
         if want_eq:
             d["eq"] = res[1]
@@ -366,6 +372,18 @@ class Phy:
                                       _STREAM))
         return ((bits, eq) if want_eq else bits), Hs, He, slope
 
-    def receive_packets(self, samples, n_packets, pkt_offset=None, xor=True, want_eq=False):
-        """estimate + demod for n_packets packets whose starts are known (one fused launch)."""
-        return self.rx_receive(samples, n_packets, pkt_offset, xor=xor, want_eq=want_eq)
+    def rx_receive_pcm(self, samples, n_packets, pkt_offset=None, xor=True, want_eq=False, out=None):
+        """rx_receive on samples in their recorded format (uint8 / int16 PCM, or float32): the symbols enter the
+        kernels through the cp.async.bulk staging buffer and are converted in registers (gf3_rx_receive_pcm).
+        -> (packed bits [n_packets, bits_stride] (, eq), Hs, He, slope)."""
+        assert samples.is_cuda and samples.stride(-1) == 1 and samples.dtype in self._FMT
+        off = self._offsets(pkt_offset, n_packets)
+        Hs = torch.empty((n_packets, self.K), dtype=torch.complex64, device=self.device)
+        He = torch.empty_like(Hs)
+        slope = torch.empty((n_packets,), dtype=torch.float64, device=self.device)
+        bits = out if out is not None else torch.empty((n_packets, self.bits_stride), dtype=torch.uint8, device=self.device)
+        eq = torch.empty((n_packets, self.L, self.K), dtype=torch.complex64, device=self.device) if want_eq else None
+        check(self._call("gf3_rx_receive_pcm", self._plan, _ptr(samples), self._FMT[samples.dtype], _ptr(off), n_packets,
+                         _ptr(self.known), _ptr(Hs), _ptr(He), _ptr(slope), _ptr(self.xor2) if xor else None, _ptr(bits),
+                         self.bits_stride, _ptr(eq), _STREAM))
+        return ((bits, eq) if want_eq else bits), Hs, He, slope

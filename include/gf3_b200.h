@@ -128,6 +128,16 @@ GF3_API int gf3_rx_receive(const gf3_plan* plan, const float* samples, const int
  * window too wide for the kernel's scratch).  The results are the same either way.               */
 GF3_API int gf3_rx_receive_is_fused(const gf3_plan* plan);
 
+/* gf3_rx_receive on samples in their recorded format (sample_format: GF3_SAMPLE_U8 / _I16 / _F32; pkt_offset and
+ * the contiguous packet stride count SAMPLES).  The symbols enter the kernels through a shared-memory staging
+ * buffer filled by bulk asynchronous copies (cp.async.bulk, completion on an mbarrier) one batch ahead of the
+ * FFT and are converted in registers, so PCM recordings (Final System Test.ipynb:85-86: an 8-bit wav) cost 1 or
+ * 2 bytes of HBM traffic per sample and no float copy of the recording exists; packets may start at any sample.
+ * uint8 samples have their offset of 128 removed (it only reaches FFT bin 0, which the chain never reads). */
+GF3_API int gf3_rx_receive_pcm(const gf3_plan* plan, const void* samples, int32_t sample_format, const int64_t* pkt_offset,
+                       int64_t n_packets, const float* known, float* Hs, float* He, double* slope,
+                       const uint8_t* xor2, uint8_t* bits_packed, int64_t bits_stride, float* eq, void* stream);
+
 /* Known-channel receive (old API, Weekend Challenge.ipynb:162-226): Y/H on bins 1..K, demap.
  * Uses the plan's geometry with its n_pilots leading/trailing symbols skipped (create the plan
  * with n_pilots = 0, packet_len = symbols per block).  Hinv[K] = 1/H on bins 1..K.          */

@@ -94,6 +94,65 @@ def test_stage_receive_chain(name, known_sequence):
     assert torch.equal(packed_f2, packed_f)
 
 
+@pytest.mark.parametrize("dtype", ["int16", "float32"])
+@pytest.mark.parametrize("name", STAGE_NAMES)
+def test_stage_receive_chain_staged_input(name, dtype, known_sequence):
+    """The same goldens through gf3_rx_receive_pcm: the int16 recording read as int16 (converted in registers)
+    and the float32 copy through the same cp.async.bulk staging buffer, packets at the reference's own
+    (arbitrary, mostly unaligned) sync offsets -- same bars as the direct path."""
+    torch = _torch()
+    g = load_golden("stage_%s.npz" % name)
+    p = oracle_params(g["cfg"], known_sequence)
+    phy = _phy(p)
+    starts = (g["peaks"] + 2)[:-1]
+    npk = len(starts)
+    d = torch.from_numpy(g["r_i16"].astype(np.int16 if dtype == "int16" else np.float32)).cuda()
+    off = torch.from_numpy(starts.astype(np.int64)).cuda()
+    (packed, eq), Hs, He, slope = phy.rx_receive_pcm(d, npk, off, xor=True, want_eq=True)
+    hscale = np.max(np.abs(g["Hs"]))
+    assert np.max(np.abs(Hs.cpu().numpy() - g["Hs"])) / hscale < 2e-6
+    assert np.max(np.abs(He.cpu().numpy() - g["He"])) / hscale < 2e-6
+    np.testing.assert_allclose(slope.cpu().numpy(), g["slope"], rtol=0, atol=2e-7)
+    dc = p.data_carriers - 1
+    assert _rel_err(eq.cpu().numpy().reshape(-1, p.K)[:, dc], g["eq"][:, dc]).max() < EQ_RTOL
+    _check_bits(phy.unpack_bits(packed), g["bits"], g["eq"][:, dc], "%s staged %s" % (name, dtype))
+    packed2, _, _, _ = phy.rx_receive_pcm(d, npk, off, xor=True)            # throughput variant (no constellation output)
+    _check_bits(phy.unpack_bits(packed2), g["bits"], g["eq"][:, dc], "%s staged %s, bits only" % (name, dtype))
+    # shifted copies of the recording: every 16-byte misalignment of the bulk copies' source
+    for shift in (1, 2, 3, 5):
+        buf = torch.zeros(d.numel() + 8, dtype=d.dtype, device="cuda")
+        buf[shift:shift + d.numel()] = d
+        p3, _, _, _ = phy.rx_receive_pcm(buf, npk, off + shift, xor=True)
+        assert torch.equal(p3, packed2), shift
+
+
+def test_uint8_receive_at_scale_vs_oracle(known_sequence):
+    """C3 shape, 192 packets quantised to 8-bit PCM with the wav offset of 128 (the reference's recording format,
+    Final System Test.ipynb:85-86): gf3_rx_receive_pcm on the uint8 samples against the oracle on `r/1.0`."""
+    torch = _torch()
+    import gf3b200
+    from gf3b200 import synth
+    n = 192
+    cfg = dict(N=1024, cp=32, lo=1, hi=512, n_pilots=20, packet_len=180, fit_lo=125, fit_hi=250)
+    phy = gf3b200.Phy(known_sequence=known_sequence, **cfg)
+    p = orc.Params(N=1024, cp=32, lo=1, hi=512, n_pilots=20, packet_len=180, known_sequence=known_sequence, encoding="XOR", fit_lo=125, fit_hi=250)
+    b = synth.make_batch(phy, n, 1, snr_db=14.0, seed=31)
+    sym = synth.packets_from_streams(phy, b)
+    q = (torch.round(sym * (110.0 / float(sym.abs().max()))) + 128.0).to(torch.uint8).contiguous()
+    (packed, eq), Hs, He, slope = phy.rx_receive_pcm(q.reshape(-1), n, xor=True, want_eq=True)
+    fast, _, _, _ = phy.rx_receive_pcm(q.reshape(-1), n, xor=True)
+    ref = orc.receive_symbols(p, q.cpu().numpy().astype(np.float64).reshape(n, p.syms_per_packet, p.sym_len), want_eq=True)
+    hscale = np.max(np.abs(ref["Hs"]), axis=1, keepdims=True)
+    assert np.max(np.abs(Hs.cpu().numpy() - ref["Hs"]) / hscale) < 2e-6
+    np.testing.assert_allclose(slope.cpu().numpy(), ref["slope"], rtol=0, atol=2e-7)
+    dc = p.data_carriers - 1
+    ref_eq = ref["eq"][:, dc]
+    rel = np.abs(eq.cpu().numpy().reshape(-1, p.K)[:, dc] - ref_eq) / np.maximum(np.abs(ref_eq), 1.0)
+    assert np.quantile(rel, 0.9999) < EQ_RTOL
+    _check_bits(phy.unpack_bits(packed), ref["bits"], ref_eq, "uint8 C3")
+    _check_bits(phy.unpack_bits(fast), ref["bits"], ref_eq, "uint8 C3, bits only")
+
+
 @pytest.mark.parametrize("name", STAGE_NAMES)
 def test_stage_level_methods(name, known_sequence):
     """receiver.equalise / receiver.demap / transmitter.send_to_stream as separate public methods
