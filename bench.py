@@ -417,7 +417,7 @@ def run_gpu_arm(args, cfg, streams, raw, desc):
                 _, _, pk, cnt = phy.sync_streams(data, 4)
             off, ok = phy.peaks_to_offsets(pk, cnt, data.stride(0), T, 1)
             rec(2)
-            phy.rx_receive(data, n_packets, off, xor=True, out=out_bits)
+            (phy.rx_receive_pcm if phy.staged_streams else phy.rx_receive)(data, n_packets, off, xor=True, out=out_bits)
             rec(3)
             rec(4)
             state["ok"], state["peaks"], state["count"] = ok, pk, cnt

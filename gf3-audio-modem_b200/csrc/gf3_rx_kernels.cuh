@@ -96,18 +96,26 @@ __device__ __forceinline__ float2 ldg_stream2(const float* p) {
 // signal's energy instead of the offset's.
 template <class S> __device__ __forceinline__ float cvt_sample(S v) { return (float)v; }
 template <> __device__ __forceinline__ float cvt_sample<uint8_t>(uint8_t v) { return (float)((int)v - 128); }
+// Narrow loads of the element-aligned-only paths are written in PTX: left to the compiler, the two single-sample
+// loads of a pair get merged into one wider load that faults at odd sample offsets.
+__device__ __forceinline__ int ldg_elem(const int16_t* p) { int v; asm volatile("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ int ldg_elem(const uint8_t* p) { int v; asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ float ldg_elem(const float* p) { float v; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
+__device__ __forceinline__ int lds_s16(const unsigned char* p) { int v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p))); return v; }
+__device__ __forceinline__ int lds_u8(const unsigned char* p) { int v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p))); return v; }
+__device__ __forceinline__ float lds_f32(const unsigned char* p) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(p))); return v; }
 // two consecutive samples from global memory, any alignment (L1-allocating: neighbouring loads share sectors)
 template <class S>
 __device__ __forceinline__ float2 ldg_pair(const S* p) {
     if constexpr (sizeof(S) == 4) {
         if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); return v; }
-        return make_float2(__ldg(p), __ldg(p + 1));
+        return make_float2(ldg_elem(p), ldg_elem(p + 1));
     } else if constexpr (sizeof(S) == 2) {
-        if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) { const short2 v = __ldg(reinterpret_cast<const short2*>(p)); return make_float2(cvt_sample<S>(v.x), cvt_sample<S>(v.y)); }
-        return make_float2(cvt_sample<S>(__ldg(p)), cvt_sample<S>(__ldg(p + 1)));
+        if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) { const short2 v = __ldg(reinterpret_cast<const short2*>(p)); return make_float2((float)v.x, (float)v.y); }
+        return make_float2((float)ldg_elem(p), (float)ldg_elem(p + 1));
     } else {
-        if ((reinterpret_cast<uintptr_t>(p) & 1) == 0) { const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(p)); return make_float2(cvt_sample<S>(v.x), cvt_sample<S>(v.y)); }
-        return make_float2(cvt_sample<S>(__ldg(p)), cvt_sample<S>(__ldg(p + 1)));
+        if ((reinterpret_cast<uintptr_t>(p) & 1) == 0) { const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(p)); return make_float2((float)((int)v.x - 128), (float)((int)v.y - 128)); }
+        return make_float2((float)(ldg_elem(p) - 128), (float)(ldg_elem(p + 1) - 128));
     }
 }
 // the same from the shared-memory staging buffer (byte address)
@@ -115,13 +123,13 @@ template <class S>
 __device__ __forceinline__ float2 lds_pair(const unsigned char* p, bool aligned) {
     if constexpr (sizeof(S) == 4) {
         if (aligned) return *reinterpret_cast<const float2*>(p);
-        return make_float2(*reinterpret_cast<const float*>(p), *reinterpret_cast<const float*>(p + 4));
+        return make_float2(lds_f32(p), lds_f32(p + 4));
     } else if constexpr (sizeof(S) == 2) {
-        if (aligned) { const short2 v = *reinterpret_cast<const short2*>(p); return make_float2(cvt_sample<S>(v.x), cvt_sample<S>(v.y)); }
-        return make_float2(cvt_sample<S>(*reinterpret_cast<const S*>(p)), cvt_sample<S>(*reinterpret_cast<const S*>(p + 2)));
+        if (aligned) { const short2 v = *reinterpret_cast<const short2*>(p); return make_float2((float)v.x, (float)v.y); }
+        return make_float2((float)lds_s16(p), (float)lds_s16(p + 2));
     } else {
-        if (aligned) { const uchar2 v = *reinterpret_cast<const uchar2*>(p); return make_float2(cvt_sample<S>(v.x), cvt_sample<S>(v.y)); }
-        return make_float2(cvt_sample<S>(p[0]), cvt_sample<S>(p[1]));
+        if (aligned) { const uchar2 v = *reinterpret_cast<const uchar2*>(p); return make_float2((float)((int)v.x - 128), (float)((int)v.y - 128)); }
+        return make_float2((float)(lds_u8(p) - 128), (float)(lds_u8(p + 1) - 128));
     }
 }
 
@@ -195,6 +203,63 @@ __device__ __forceinline__ float2 expmj(double a) {
     float s, c;
     sincospif(2.0f * (float)r, &s, &c);
     return make_float2(c, -s);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Exact phases for a SHORT fit window.  The slope of OFDM.py:462 is a least-squares fit through the phases of
+// He / Hs inside the window; the equaliser multiplies it by up to n * w ~ K.  With hundreds of bins in the
+// window the float32 phase error of the channel estimate averages out (slope error ~1e-9), but a window of a
+// few bins -- the reference's literal [500:1000] clips to bins 500..510 at K = 511 -- passes it on almost
+// undamped: 3e-6 rad of phase error becomes 5e-4 rad at the band edge.  For windows of at most
+// kFitExactMax bins the phases are therefore recomputed in double precision: double sums of the P known
+// symbols, then a direct DFT of the window's bins (a rotation recurrence per lane, one warp per bin).
+// sd: N doubles of shared scratch.  Called by all NT threads; phi is complete after the trailing barrier.
+// ------------------------------------------------------------------------------------------
+constexpr int kFitExactMax = 32;
+template <class P, int NT, class S>
+__device__ __noinline__ void refine_fit_phases(const S* base0, const S* base1, int symlen, int Pn, const float2* __restrict__ known,
+                                               int flo, int nfit, double* sd, double* phi, int phi_blk_stride, int phi_off) {
+    constexpr int N = P::N, NW = NT / 32, C = N / 32;       // samples per lane
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int blk = 0; blk < 2; ++blk) {
+        const S* b = blk ? base1 : base0;
+        __syncthreads();                                   // sd is free
+        for (int j = tid; j < N; j += NT) {
+            double acc = 0.0;
+            for (int p = 0; p < Pn; ++p) acc += (double)cvt_sample<S>((S)ldg_elem(b + (int64_t)p * symlen + j));
+            sd[j] = acc;
+        }
+        __syncthreads();
+        for (int i = warp; i < nfit; i += NW) {
+            const int k = flo + i + 1;                     // FFT bin of carrier index flo + i
+            const int j0 = lane * C;
+            double wr, wi, cr, ci;
+            sincospi(-2.0 * (double)k / (double)N, &wi, &wr);                              // step e^{-2 pi i k / N}
+            sincospi(-2.0 * (double)((int64_t)k * j0 % N) / (double)N, &ci, &cr);          // e^{-2 pi i k j0 / N}
+            double xr = 0.0, xi = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < C; ++c) {
+                const double v = sd[j0 + c];
+                xr = fma(v, cr, xr);
+                xi = fma(v, ci, xi);
+                const double t = cr * wr - ci * wi;
+                ci = fma(cr, wi, ci * wr);
+                cr = t;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                xr += __shfl_xor_sync(0xffffffffu, xr, o);
+                xi += __shfl_xor_sync(0xffffffffu, xi, o);
+            }
+            if (lane == 0) {
+                const float2 kn = known[k - 1];            // H = X / known / P: the phase of X conj(known)
+                const double hr = xr * (double)kn.x + xi * (double)kn.y, hi = xi * (double)kn.x - xr * (double)kn.y;
+                phi[blk * phi_blk_stride + phi_off + i] = atan2(hi, hr);
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -304,7 +369,10 @@ __device__ __noinline__ double estimate_packet(const S* pkt_base, int symlen, in
         }
         __syncthreads();
     }
-    // ---- 4. slope
+    // ---- 4. slope (short windows: phases recomputed in double precision first)
+    if (nfit >= 2 && nfit <= kFitExactMax)
+        refine_fit_phases<P, NT, S>(pkt_base + cp, pkt_base + (int64_t)(Pn + Ln) * symlen + cp, symlen, Pn, known, flo, nfit,
+                                    reinterpret_cast<double*>(work), phi, nfit, 0);
     const double sl = fit_slope<NT>(phi - flo, nfit, flo, fhi, warp_tot, red);
     if (tid == 0) *s_slope = sl;
     __syncthreads();
@@ -585,9 +653,13 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                     raw_parity ^= 1u;
                     const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(sym_ptr(c, l0 + b * SF)) & 15);
                     const unsigned char* rb = raw + (size_t)ga * RAWB + sh;
-                    const bool al = (sh & (2 * sizeof(S) - 1)) == 0;
+                    if ((sh & (2 * sizeof(S) - 1)) == 0) {         // pairs are naturally aligned: one load per point
 #pragma unroll
-                    for (int i = 0; i < R; ++i) x[i] = lds_pair<S>(rb + (size_t)(2 * (ta + i * T)) * sizeof(S), al);
+                        for (int i = 0; i < R; ++i) x[i] = lds_pair<S>(rb + (size_t)(2 * (ta + i * T)) * sizeof(S), true);
+                    } else {                                        // (a real branch: as a select both forms would be issued)
+#pragma unroll
+                        for (int i = 0; i < R; ++i) x[i] = lds_pair<S>(rb + (size_t)(2 * (ta + i * T)) * sizeof(S), false);
+                    }
                     __syncthreads();                               // every thread has its samples: the buffer is free again
                     if (tid == 0) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -904,6 +976,9 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
     __syncthreads();
 
     // ---- 4. unwrap both phase rows, difference, LS slope over [fit_lo, fit_hi) (0-based carrier index)
+    if (fhi - flo >= 2 && fhi - flo <= kFitExactMax)       // short window: exact phases (zbuf is dead: N doubles of scratch)
+        refine_fit_phases<P, NT, S>(pkt_base + a.cp, pkt_base + (int64_t)(a.P + a.L) * symlen + a.cp, symlen, a.P, a.known, flo, fhi - flo,
+                                    reinterpret_cast<double*>(zbuf), phi, K, flo);
     const double sl = fit_slope<NT>(phi, K, flo, fhi, warp_tot, red);
     if (tid == 0) a.slope[pkt] = sl;
 }

@@ -338,14 +338,17 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
     const S* base = reinterpret_cast<const S*>(a.r);
 
     // ---- samples of block bb of stream `st` in the FFT's first-pass layout x[i] = z[t + i T]
-    auto load_block = [&](float2 (&x)[R], int64_t st, int bb) {
+    // HALF = 1: only the second half of the block is fetched (x[R/2 ..]); the first half is the previous block's
+    // second half, which the caller kept in registers (consecutive blocks overlap by B samples)
+    auto load_block = [&](float2 (&x)[R], int64_t st, int bb, auto halfc) {
+        constexpr int I0 = decltype(halfc)::value ? R / 2 : 0;
         const S* row = base + st * a.r_stride;
         const int64_t s0 = (int64_t)bb * kB - kB;
         const bool inside = bb >= 0 && bb < a.nblk_in && s0 >= 0 && s0 + 2 * kB <= a.T;
         if constexpr (sizeof(S) == 4) {
             if (inside && ((reinterpret_cast<uintptr_t>(row + s0) & 7) == 0)) {
 #pragma unroll
-                for (int i = 0; i < R; ++i) {            // streaming: do not evict the chirp partitions from L1
+                for (int i = I0; i < R; ++i) {           // streaming: do not evict the chirp partitions from L1
                     const float* sp = reinterpret_cast<const float*>(row + s0) + 2 * (tid + i * T);
                     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(x[i].x), "=f"(x[i].y) : "l"(sp));
                 }
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
         } else if constexpr (sizeof(S) == 2) {
             if (inside && ((reinterpret_cast<uintptr_t>(row + s0) & 3) == 0)) {
 #pragma unroll
-                for (int i = 0; i < R; ++i) {
+                for (int i = I0; i < R; ++i) {
                     const short2 v = __ldg(reinterpret_cast<const short2*>(row + s0) + (tid + i * T));
                     x[i] = make_float2((float)v.x, (float)v.y);
                 }
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
         } else {
             if (inside && ((reinterpret_cast<uintptr_t>(row + s0) & 1) == 0)) {
 #pragma unroll
-                for (int i = 0; i < R; ++i) {
+                for (int i = I0; i < R; ++i) {
                     const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(row + s0) + (tid + i * T));
                     x[i] = make_float2((float)v.x, (float)v.y);
                 }
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
             }
         }
 #pragma unroll
-        for (int i = 0; i < R; ++i) {          // edge block / odd alignment: bounds-checked scalar loads, zero outside [0, T)
+        for (int i = I0; i < R; ++i) {         // edge block / odd alignment: bounds-checked scalar loads, zero outside [0, T)
             const int64_t n = s0 + 2 * (tid + i * T);
             float v0 = 0.f, v1 = 0.f;
             if (bb >= 0 && bb < a.nblk_in) {
@@ -437,13 +440,17 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
 #pragma unroll 1
                 for (int bb = b - R1; bb < b; ++bb) {
                     if (bb < 0 || bb >= a.nblk_in) continue;
-                    load_block(x, stream, bb);
+                    load_block(x, stream, bb, std::false_type{});
                     forward(x, xre, xim, dcny);
                     ring_store(bb % R1, xre, xim, dcny);
                 }
             }
-            load_block(x, stream, b);
+            load_block(x, stream, b, std::false_type{});
         }
+        // the second half of this block is the first half of the next one: keep it (the transform overwrites x)
+        float2 keep[R / 2];
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) keep[i] = x[R / 2 + i];
         // ---- X_b
         if (b < a.nblk_in) {
             forward(x, xre, xim, dcny);
@@ -453,7 +460,11 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
             dcny = make_float2(0.f, 0.f);
         }
         // the next block's samples fly while this one is multiplied and transformed back
-        if (c + 1 < c_end && (c + 1) / a.nblk_out == stream) load_block(x, stream, b + 1);
+        if (c + 1 < c_end && (c + 1) / a.nblk_out == stream) {
+#pragma unroll
+            for (int i = 0; i < R / 2; ++i) x[i] = keep[i];
+            load_block(x, stream, b + 1, std::true_type{});
+        }
 
         // ---- Y_b = sum_p X_{b-p} H_p   (re = pos - neg; all four products are plain FFMA2)
         pk64 arp[Q], arn[Q], ai[Q];
@@ -844,15 +855,16 @@ static XcorrGeom xcorr_geom(const gf3_plan* plan, int64_t n_streams, int64_t T) 
 #define GF3_XC_FUSED_MAX_PARTS 4      // ring of (parts - 1) x 16 KB spectra per CTA next to 33 KB of FFT buffer + twiddles
 #endif
 #ifndef GF3_XC_FUSED_MINB
-#define GF3_XC_FUSED_MINB 3
+#define GF3_XC_FUSED_MINB 2
 #endif
 static size_t fused_smem(int parts) {
     return (size_t)(SP::MP + SP::TW_TOTAL) * sizeof(float2) + (size_t)(parts - 1) * ((SP::M / 2) * sizeof(float4) + sizeof(float2)) + 16;
 }
-// CTAs per SM of the fused kernel: 3 (<= 168 registers) or 2 (<= 255 registers; the shared-memory carve-out then
-// leaves ~120 KB of L1, enough to keep the chirp partitions resident).  GF3_XC_MINB=2|3 overrides (experiments).
+// CTAs per SM of the fused kernel: 2 (<= 255 registers; the shared-memory carve-out then leaves ~120 KB of L1,
+// enough to keep the 48 KB of chirp partitions resident: 1.81 ms per 1024 C3 streams) or 3 (<= 168 registers, spills,
+// 28 KB of L1: 2.3 ms).  GF3_XC_MINB=3 selects the latter (experiments).
 static int fused_minb() {
-    if (const char* e = getenv("GF3_XC_MINB")) return atoi(e) == 2 ? 2 : 3;
+    if (const char* e = getenv("GF3_XC_MINB")) return atoi(e) == 3 ? 3 : 2;
     return GF3_XC_FUSED_MINB;
 }
 // The fused kernel pays (parts - 1) extra forward FFTs per CTA (the spectra before its first block), so it needs
@@ -903,9 +915,9 @@ static int launch_fused_p(const gf3_plan* plan, const FusedArgs& a, cudaStream_t
 template <class S>
 static int launch_fused(const gf3_plan* plan, const FusedArgs& a, cudaStream_t st) {
     if constexpr (sizeof(S) == 4) {
-        if (fused_minb() == 2) return launch_fused_p<S, 2>(plan, a, st);
+        if (fused_minb() == 3) return launch_fused_p<S, 3>(plan, a, st);      // experiment: 3 CTAs / SM, <= 168 registers
     }
-    return launch_fused_p<S, GF3_XC_FUSED_MINB>(plan, a, st);
+    return launch_fused_p<S, 2>(plan, a, st);
 }
 
 // chirp_method's convolution for a batch of streams (OFDM.py:357-358); blockmax is optional

@@ -81,6 +81,10 @@ def main():
         print("| opcode | warp-instructions" + (" per unit |" if units else " |") + " share |\n|---|---|---|")
         for k, v in d["ops"].most_common(18):
             print("| %s | %.1f | %.1f %% |" % (k, v / units if units else v, 100 * v / d["total"]))
+        # asynchronous-copy / mbarrier / tensor-memory opcodes, however rare: the evidence for (or against) TMA use
+        special = [(k, v) for k, v in d["ops"].items() if re.match(r"(UBLKCP|UTMA|SYNCS|UTCBAR|UTCMMA|LDGSTS|BAR|FENCE|MEMBAR|ATOM|RED)", k)]
+        if special:
+            print("\nasync / barrier / atomic opcodes: " + ", ".join("%s %.0f" % (k, v) for k, v in sorted(special)))
         t = sum(d["st"].values()) or 1
         print("\nstall samples: " + ", ".join("%s %.1f %%" % (k.replace("stall_", ""), 100 * v / t) for k, v in d["st"].most_common(8)))
         print()
