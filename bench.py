@@ -526,6 +526,31 @@ def run_gpu_arm(args, cfg, streams, raw, desc):
                 del hr, h_q, q
             except Exception as ex:   # report the failure instead of a made-up number
                 e2e_legs[key] = {"value": None, "unit": UNIT, "error": repr(ex)}
+        # the ceiling of any end-to-end number on this host: pinned-memory H2D bandwidth with every rank copying at once
+        try:
+            hb = torch.empty((256 << 20,), dtype=torch.uint8).pin_memory()
+            db = torch.empty_like(hb, device=phy.device)
+            db.copy_(hb, non_blocking=True)
+            barrier()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(4):
+                db.copy_(hb, non_blocking=True)
+            h1.record()
+            barrier()
+            h_ms = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device=phy.device)
+            if world > 1:
+                dist.all_reduce(h_ms, op=dist.ReduceOp.MAX)
+            gbs = 4 * hb.numel() / (float(h_ms) * 1e-3) / 1e9
+            for key, leg in e2e_legs.items():
+                if leg.get("value"):
+                    rate = leg["h2d_bytes_per_step"] * leg["steps"] / (n_packets * phy.bits_per_packet * leg["steps"] / (leg["value"] / world * 1e6)) / 1e9
+                    leg["h2d_gbs_per_gpu"] = rate
+                    leg["h2d_ceiling_gbs_per_gpu"] = gbs
+                    leg["of_h2d_ceiling"] = rate / gbs
+            del hb, db
+        except Exception as ex:
+            e2e_legs["e2e"]["h2d_probe_error"] = repr(ex)
     else:
         e2e_legs["e2e"] = {"value": None, "unit": UNIT, "error": "skipped (--no-e2e)"}
     sampler.stop()
