@@ -54,6 +54,7 @@ except Exception:
     pass
 Audio = _optional("IPython.display", "Audio")  # OFDM.py:9
 pyldpc = _optional("pyldpc")                  # OFDM.py:10
+pd = _optional("pandas")                      # re-exported by the revisions the older notebooks ran against (Weekend Challenge.ipynb:33)
 
 
 def _find_ci(path):
@@ -75,6 +76,142 @@ def _find_ci(path):
 
 
 #########################################
+#   Old API (older OFDM.py revisions)   #
+#########################################
+# The Weekend-Challenge / Week-2 / Initial-test / Audio notebooks were written against earlier revisions of OFDM.py
+# whose code is not in the reference repository: CamG(N, cp, "QPSK") with K = N, module-level FFT / IFFT /
+# equalise(Y, H), keyword receiver(ofdm_symbol_size=, cp_length=, ...).  These shims give that surface on top of
+# the same device kernels, so the notebooks' cells run unmodified.
+
+_legacy_phys = {}
+
+
+def _legacy_phy(N, cp=0):
+    """Full-band plan without known symbols for an N-point symbol (cached)."""
+    N, cp = int(N), int(cp)
+    if N < 64 or N > 4096 or N & (N - 1):
+        raise ValueError("symbol size %d: the device FFT covers powers of two from 64 to 4096 (there is no CPU path)" % N)
+    key = (N, cp)
+    if key not in _legacy_phys:
+        _legacy_phys[key] = Phy(N=N, cp=cp, lo=1, hi=N // 2, n_pilots=0, packet_len=1)
+    return _legacy_phys[key]
+
+
+def _as_real_rows(x, what):
+    x = np.asarray(x)
+    if np.iscomplexobj(x):
+        if np.max(np.abs(x.imag), initial=0.0) > 1e-9 * max(1.0, np.max(np.abs(x.real), initial=0.0)):
+            raise ValueError("%s: the device transform takes real samples" % what)
+        x = x.real
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def FFT(x):
+    """np.fft.fft of real symbols along the last axis (old API; Weekend Challenge.ipynb:195): bins 1..N/2-1 come from
+    the device kernel (gf3_rx_spectrum), the mirror half is their conjugate, DC / Nyquist are two sums."""
+    import torch
+    x = _as_real_rows(x, "FFT")
+    N = x.shape[-1]
+    phy = _legacy_phy(N)
+    rows = x.reshape(-1, N)
+    spec = phy.spectrum(torch.from_numpy(rows.astype(np.float32).reshape(-1)).to(phy.device), rows.shape[0]).cpu().numpy().astype(np.complex128)
+    out = np.zeros((rows.shape[0], N), dtype=np.complex128)
+    out[:, 1:N // 2] = spec
+    out[:, N // 2 + 1:] = np.conj(spec[:, ::-1])
+    out[:, 0] = rows.sum(axis=1)
+    out[:, N // 2] = rows[:, ::2].sum(axis=1) - rows[:, 1::2].sum(axis=1)
+    return out.reshape(x.shape)
+
+
+def IFFT(X):
+    """np.fft.ifft of Hermitian-symmetric spectra along the last axis (old API; Initial OFDM Test.ipynb cell 13): bins
+    1..N/2-1 go through the device transmit kernel (gf3_tx_ifft); a DC / Nyquist term is a constant / alternating offset."""
+    import torch
+    X = np.asarray(X)
+    N = X.shape[-1]
+    phy = _legacy_phy(N)
+    rows = X.reshape(-1, N).astype(np.complex128)
+    half = np.ascontiguousarray(rows[:, 1:N // 2].astype(np.complex64))
+    if not np.allclose(rows[:, N // 2 + 1:], np.conj(rows[:, 1:N // 2][:, ::-1]), rtol=1e-6, atol=1e-9 * (1.0 + np.max(np.abs(rows)))):
+        raise ValueError("IFFT: the device transform takes Hermitian-symmetric spectra (real symbols)")
+    t = phy.ifft_symbols(torch.from_numpy(half).to(phy.device)).cpu().numpy().astype(np.float64)
+    t += rows[:, :1].real / N + rows[:, N // 2:N // 2 + 1].real / N * np.where(np.arange(N) % 2 == 0, 1.0, -1.0)[None, :]
+    return t.reshape(X.shape).astype(np.complex128)
+
+
+def equalise(Y, H):
+    """Old API (Weekend Challenge.ipynb:225): one-tap equaliser with a KNOWN channel, Y / H on the device."""
+    import torch
+    Y = np.asarray(Y)
+    H = np.asarray(H)
+    phy = _legacy_phy(64)                      # any plan: the divide needs none of its tables
+    rows = np.ascontiguousarray(Y.reshape(-1, Y.shape[-1]).astype(np.complex64))
+    out = phy.cdiv(torch.from_numpy(rows).to(phy.device), torch.from_numpy(np.ascontiguousarray(H.reshape(-1).astype(np.complex64))).to(phy.device))
+    return out.cpu().numpy().astype(np.complex128).reshape(Y.shape)
+
+
+def _is_old_ctor(mode):
+    return isinstance(mode, (int, np.integer)) and not isinstance(mode, bool)
+
+
+class _OldCamG:
+    """CamG(N, cp, "QPSK") of the old API (Weekend Challenge.ipynb:75, Initial OFDM Test.ipynb:34): K is the FFT
+    length, every bin 1..N/2-1 carries data, and the stage helpers live on the parameter object itself."""
+
+    def __init__(self, N, cp, modulation="QPSK"):
+        if modulation != "QPSK":
+            raise ValueError("Invalid Modulation Type")
+        self.ofdm_symbol_size = self.K = int(N)
+        self.cp_length = int(cp)
+        self.modulation, self.mu, self.fs = modulation, 2, 48000
+        self.all_carriers = np.arange(self.K)
+        self.data_carriers = np.arange(1, self.K // 2)
+        self.bits_per_symbol = len(self.data_carriers) * self.mu
+        self.mapping_table = {(0, 0): (1 + 1j) / np.sqrt(2), (1, 0): (1 - 1j) / np.sqrt(2),
+                              (1, 1): (-1 - 1j) / np.sqrt(2), (0, 1): (-1 + 1j) / np.sqrt(2)}
+
+    def SP(self, bits):
+        return np.asarray(bits).reshape(-1, self.mu)
+
+    def map(self, bits):
+        return gf3b200.qpsk_points(bits)
+
+    def OFDM_symbol(self, payload):
+        payload = np.asarray(payload).reshape(-1, len(self.data_carriers))
+        sym = np.zeros((payload.shape[0], self.K), dtype=complex)
+        sym[:, self.data_carriers] = payload
+        sym[:, -self.data_carriers] = np.conj(payload)
+        return sym[0] if sym.shape[0] == 1 else sym
+
+    def add_cp(self, time_data):
+        time_data = np.asarray(time_data)
+        if self.cp_length == 0:
+            return time_data
+        return np.concatenate([time_data[..., -self.cp_length:], time_data], axis=-1)
+
+    def remove_cp(self, rx):
+        return np.asarray(rx)[..., self.cp_length:]
+
+    def get_data(self, spectrum):
+        return np.asarray(spectrum)[..., 1:self.K // 2]
+
+    def demap(self, symbols):
+        """Minimum-distance QPSK decisions on the device (gf3_demap) -> (bits[..., 2], hardDecision)."""
+        import torch
+        if type(symbols) != np.ndarray:                            # noqa: E721
+            raise ValueError("Symbols must be numpy array")
+        phy = _legacy_phy(max(64, self.K))
+        bits, hard = phy.demap(torch.from_numpy(np.ascontiguousarray(symbols, dtype=np.complex64)).to(phy.device))
+        return bits.cpu().numpy().astype(np.int64), hard.cpu().numpy().astype(np.complex128)
+
+    def PS(self, bits):
+        return np.asarray(bits).reshape((-1,))
+
+    def __repr__(self):
+        return "Number of Sub Carriers: {} \nCyclic prefix length: {} \nModulation method: {}".format(self.K, self.cp_length, self.modulation)
+
+
+#########################################
 #                 CamG                  #
 #########################################
 
@@ -83,10 +220,34 @@ class CamG:
     the parameter space its notebooks used through older revisions: any power-of-two symbol size,
     any CP, any data-bin range."""
 
-    def __init__(self, mode, encoding="None", no_pilots=20, packet_length=180, *,
-                 ofdm_symbol_size=None, cp_length=None, lowest_bin=None, highest_bin=None):
+    def __new__(cls, mode=None, *args, **kwargs):
+        if cls is CamG and _is_old_ctor(mode):                     # CamG(N, cp, "QPSK"): the old parameter object
+            return _OldCamG(mode, *args, **kwargs)
+        return super().__new__(cls)
+
+    def __init__(self, mode=None, encoding="None", no_pilots=20, packet_length=180, *,
+                 ofdm_symbol_size=None, cp_length=None, lowest_bin=None, highest_bin=None,
+                 modulation=None, fs=None, end_sync=True, pilot_sequence=None, sync_method="chirp"):
+        # old API of transmitter / receiver: (N, cp, "QPSK") positionally (Audio.ipynb:60,147) or ofdm_symbol_size= / cp_length= /
+        # modulation= / fs= / end_sync= / no_pilots= / pilot_sequence= / sync_method= by keyword (Week 2 Challenge.ipynb:42-45,126,305):
+        # every bin 1..N/2-1 carries data, no bit coding
+        self.old_api = _is_old_ctor(mode) or (mode is None and ofdm_symbol_size is not None)
+        if _is_old_ctor(mode):
+            ofdm_symbol_size, cp_length = int(mode), int(encoding)
+            if isinstance(no_pilots, str):
+                modulation, no_pilots = no_pilots, 20
+            mode, encoding = None, "None"
+        if self.old_api:
+            mode = "A1"
+            lowest_bin = 1 if lowest_bin is None else lowest_bin
+            highest_bin = int(ofdm_symbol_size) // 2 if highest_bin is None else highest_bin
+        if mode is None:
+            raise TypeError("CamG() missing required argument: 'mode'")
+        if modulation is not None and modulation != "QPSK":
+            raise ValueError("Invalid Modulation Type")
+        self.end_sync, self.gap_length, self.Hest = end_sync, 0, None      # old-API attributes (Week 2 Challenge.ipynb:45,305)
         self.encoding = encoding
-        self.fs = 48000
+        self.fs = 48000 if fs is None else fs
         self.ofdm_symbol_size = 4096 if ofdm_symbol_size is None else int(ofdm_symbol_size)
         self.K = self.ofdm_symbol_size // 2 - 1
         K = 2047
@@ -100,7 +261,7 @@ class CamG:
         self.highest_bin = modes[mode][1][1] if highest_bin is None else int(highest_bin)
         self.packet_length = packet_length
         self.no_pilots = no_pilots
-        self.sync_method = "chirp"
+        self.sync_method = sync_method
         self.L = self.K + 1
         self.f0 = 0
         self.f1 = 8000
@@ -122,6 +283,9 @@ class CamG:
             self.known_sequence = (raw - ord("0")).astype(np.int64)
         else:
             self.known_sequence = gf3b200.default_known_sequence()
+        if pilot_sequence is not None:                             # old API: the caller's known bits (Audio.ipynb:147)
+            self.known_sequence = np.asarray(pilot_sequence).astype(np.int64).reshape(-1)
+        self.pilot_sequence = self.known_sequence
         self._phy = None
         self._phy_key = None
 
@@ -138,8 +302,11 @@ class CamG:
     @property
     def phy(self):
         """The device plan for the CURRENT attribute values (rebuilt if they were patched)."""
+        if self.pilot_sequence is not self.known_sequence and self.old_api:     # old API: `tx.pilot_sequence = bits` after construction
+            self.known_sequence = np.asarray(self.pilot_sequence).astype(np.int64).reshape(-1)
+            self.pilot_sequence = self.known_sequence
         key = (self.ofdm_symbol_size, self.cp_length, self.lowest_bin, self.highest_bin, self.no_pilots,
-               self.packet_length, self.chirp_length, self.f0, self.f1, self.fs)
+               self.packet_length, self.chirp_length, self.f0, self.f1, self.fs, self.known_sequence.tobytes()[:64], len(self.known_sequence))
         if self._phy is None or key != self._phy_key:
             self._phy = Phy(N=self.ofdm_symbol_size, cp=self.cp_length, lo=self.lowest_bin, hi=self.highest_bin,
                             n_pilots=self.no_pilots, packet_len=self.packet_length,
@@ -232,8 +399,9 @@ class transmitter(CamG):
         payload_valid = np.tile(payload_valid, self.no_packets)
         return tx, sync_valid, known_valid, payload_valid
 
-    def _modulate(self, bits_encoded, filler):
-        """Fused device transmit chain: encoded bits -> framed waveform (float64 numpy)."""
+    def _modulate(self, bits_encoded, filler, device_xor=False):
+        """Fused device transmit chain: (encoded) bits -> framed waveform (float64 numpy); device_xor: the bits are
+        un-encoded and encode("XOR") runs inside the kernel."""
         import torch
         phy = self.phy
         bpp = phy.bits_per_packet
@@ -246,7 +414,7 @@ class transmitter(CamG):
         packed[:, : pk.shape[1]] = pk
         d_bits = torch.from_numpy(packed).to(phy.device).reshape(1, n_packets, phy.bits_stride)
         d_fill = torch.from_numpy(np.asarray(filler).astype(np.complex64)).to(phy.device).reshape(1, -1) if phy.K > phy.Nd else None
-        out = phy.tx_modulate(d_bits, d_fill, 1, n_packets)
+        out = phy.tx_modulate(d_bits, d_fill, 1, n_packets, xor=device_xor)
         return out[0].cpu().numpy().astype(np.float64)
 
     def graphs(self):
@@ -263,17 +431,33 @@ class transmitter(CamG):
         plt.title("QPSK Constellation with Gray Mapping")
         plt.show()
 
+    def _pad_for_device_encode(self, bits):
+        """encode() with the XOR left to the device (OFDM.py:163-173): the padding is drawn exactly as encode() draws it
+        (same np.random.binomial call) and pre-XORed with the known bits, so that the kernel's XOR of the WHOLE packet
+        (gf3_tx_encode_modulate) leaves the reference's un-encoded padding behind it: x ^ k ^ k = x."""
+        bits = np.asarray(bits)
+        bits_per_packet = self.data_bits_per_symbol * self.packet_length
+        padding_length = (bits_per_packet - len(bits) % bits_per_packet) % bits_per_packet
+        padding = np.random.binomial(n=1, p=0.5, size=(padding_length,))
+        dbs = self.data_bits_per_symbol
+        pos = (len(bits) + np.arange(padding_length)) % dbs
+        return np.hstack([bits, np.bitwise_xor(padding, self.known_sequence[:dbs][pos])])
+
     def transmit(self, bits, graph_output=False):
         """OFDM.py:296-343."""
         print("-" * 42 + "\nTRANSMIT\n" + "-" * 42)
         print("OFDM Paramters:")
         print(self)
-        bits_encoded = self.encode(bits)
+        if self.sync_method != "chirp":
+            raise NotImplementedError("sync_method %r: only the chirp synchronisation is built (OFDM.py:56 hard-wires it; the reference "
+                                      "marks schmidlcox_method as no longer working, OFDM.py:376)" % (self.sync_method,))
+        device_xor = self.encoding == "XOR"
+        bits_encoded = self._pad_for_device_encode(bits) if device_xor else self.encode(bits)
         filler = self.random_qpsk()                     # same draw order as build_OFDM_symbol (OFDM.py:210)
         n_symbols = len(bits_encoded) // self.data_bits_per_symbol
         print("Number of bits to transmit:         " + str(len(bits)))
         print("Number of OFDM symbols to transmit: " + str(n_symbols))
-        signal = self._modulate(bits_encoded, filler)
+        signal = self._modulate(bits_encoded, filler, device_xor)
         print("Number of packets to transmit:      " + str(self.no_packets))
         if graph_output:
             time = np.linspace(0, len(signal) / self.fs, len(signal))
@@ -421,6 +605,9 @@ class receiver(transmitter):
         print(self)
         if self.encoding == "LDPC":
             raise NotImplementedError('encoding "LDPC" is out of scope (broken in the reference, OFDM.py:21)')
+        if self.sync_method != "chirp":
+            raise NotImplementedError("sync_method %r: only the chirp synchronisation is built (OFDM.py:56 hard-wires it; the reference "
+                                      "marks schmidlcox_method as no longer working, OFDM.py:376)" % (self.sync_method,))
         phy = self.phy
         peaks, nz, d_r = self._sync(signal)
         starts = (peaks + 2)[:-1]                                  # OFDM.py:393-395
@@ -438,6 +625,9 @@ class receiver(transmitter):
         print("Number of received bits:            " + str(len(bits)))
         if _details is not None:
             _details.update(out, peaks=peaks, starts=starts)
+        self.Hest = out["Hs"][0]                                   # old API attribute (Week 2 Challenge.ipynb:305)
+        if self.old_api:
+            return bits                                            # the old receive() returned the bits alone (Audio.ipynb:147-161)
         return bits, out["Hs"][0], out["He"][0]
 
 

@@ -135,6 +135,17 @@ static unsigned grid_for(int64_t total, int sm_count) {
     return (unsigned)g;
 }
 
+// Y / H, H broadcast over the rows (the old API's module-level equalise(Y, H), Weekend Challenge.ipynb:225)
+__global__ void __launch_bounds__(256) cdiv_kernel(const float2* __restrict__ Y, const float2* __restrict__ H, int64_t n_rows, int m,
+                                                   float2* __restrict__ out) {
+    const int64_t total = n_rows * m;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 y = Y[i], h = H[i % m];
+        const float d = 1.0f / (h.x * h.x + h.y * h.y);
+        out[i] = make_float2((y.x * h.x + y.y * h.y) * d, (y.y * h.x - y.x * h.y) * d);
+    }
+}
+
 int tx_frame_known(const gf3_plan* plan, const float* known, const float* sync, int sync_len, int64_t n_packets,
                    float* out, cudaStream_t st);     // gf3_tx.cu
 
@@ -214,5 +225,17 @@ extern "C" int gf3_tx_frame(const gf3_plan* plan, const float* data_time, int64_
         frame_data_kernel<<<grid_for(a.total, plan->sm_count), 256, 0, st>>>(a);
         GF3_LAUNCH_CHECK();
     }
+    return GF3_OK;
+}
+
+extern "C" int gf3_cdiv(const float* Y, const float* H, int64_t n_rows, int32_t m, float* out, void* stream) {
+    GF3_REQUIRE(Y && H && out, "cdiv: null argument");
+    GF3_REQUIRE(n_rows >= 0 && m >= 1, "cdiv: bad sizes");
+    if (n_rows == 0) return GF3_OK;
+    int64_t blocks = (n_rows * m + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cdiv_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float2*>(Y), reinterpret_cast<const float2*>(H),
+                                                                                   n_rows, m, reinterpret_cast<float2*>(out));
+    GF3_LAUNCH_CHECK();
     return GF3_OK;
 }

@@ -20,7 +20,8 @@ constexpr int kTxMinBlocks = 512 / GF3_TX_THREADS;
 struct TxArgs {
     const uint8_t* bits;        // [n_streams, pk_per_stream, bits_stride]   (null for the known symbol)
     const float2* filler;       // [n_streams, K - Nd]
-    const float2* known;        // [K] (used when bits == null)
+    const float2* known;        // [K] (used when bits == null); KNOWN_SYMBOL with n_work > 1: [n_work, K] spectra (gf3_tx_ifft)
+    const uint8_t* xor2;        // [Nd] or null: (b0 << 1) | b1 of known_sequence[:2 Nd] -- encode("XOR") fused (OFDM.py:163-166)
     const float2* tw;
     float* out;                 // [n_streams, out_stride]
     int64_t bits_stride, out_stride;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
         if (kk >= a.lo && kk < a.hi) return 2 * (kk - a.lo);
         return -1 - (kk < a.lo ? kk - 1 : kk - 1 - Nd);                    // np.delete keeps ascending order (OFDM.py:49,213)
     };
+    unsigned xk1[PP], xk2[PP];  // encode("XOR") of the thread's bins: the known bit pair moved onto bits 31 (b0) and 30 (b1)
     bool all_data = !KNOWN_SYMBOL;                    // every bin of this thread is a data carrier: no selects, no filler loads
 #pragma unroll
     for (int pp = 0; pp < PP; ++pp) {
@@ -76,12 +78,14 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
         src1[pp] = classify(k);
         src2[pp] = classify(km);
         all_data = all_data && src1[pp] >= 0 && src2[pp] >= 0;
+        xk1[pp] = (a.xor2 && src1[pp] >= 0) ? ((unsigned)a.xor2[src1[pp] >> 1] & 3u) << 30 : 0u;
+        xk2[pp] = (a.xor2 && src2[pp] >= 0) ? ((unsigned)a.xor2[src2[pp] >> 1] & 3u) << 30 : 0u;
         zo1[pp] = k;                                   // plain indexing: the hand-over to the FFT's register layout and the
         zo2[pp] = j != 0 ? km : 0;                     // natural-order output below are conflict-free without padding;            // the k = M/2 slot also clears Z[0] (DC and Nyquist: both 0)
     }
     const int g = tid / T, t = tid % T;
 
-    const int64_t n_work = KNOWN_SYMBOL ? 1 : a.n_work;
+    const int64_t n_work = a.n_work;                  // KNOWN_SYMBOL: symbols given as spectra (1 for the known symbol itself)
     // The packed bits of a work item's symbols are one contiguous byte range of the packet (symbol l
     // starts at bit 2 Nd l).  They are fetched one item ahead into registers (NB bytes per thread), so
     // their latency is covered by the previous item's spectrum / FFT / store phases.
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
             nsym = min(SF, a.L - l_first);
         }
         const int64_t stream = pktg / a.pk_per_stream, pk = pktg % a.pk_per_stream;
-        const float2* fill = KNOWN_SYMBOL ? a.known : a.filler + stream * (K - Nd);
+        const float2* fill = KNOWN_SYMBOL ? a.known + work * K : a.filler + stream * (K - Nd);
 
         // stage the packed bits of the nsym symbols (bit offset l*2Nd is not byte aligned in general)
         if constexpr (!KNOWN_SYMBOL) {      // (the previous item's phase B' reads of sbits are two barriers back)
@@ -130,18 +134,18 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
             float2* zs = zbuf + s * MP;                    //  values, the FFT runs on them and nothing is written out)
             const int bit0 = s * 2 * Nd + (int)(((int64_t)l_first * 2 * Nd) & 7);   // first bit of symbol s in the staged range
             const uint8_t* sym = sbits;
-            auto bin = [&](int src) -> float2 {
+            auto bin = [&](int src, unsigned xk) -> float2 {
                 // data bin: QPSK of the encoded bit pair (OFDM.py:72-77), (b0,b1) -> ((1-2 b1) + j (1-2 b0)) / sqrt(2):
                 // the two bits (MSB first) are moved onto the sign bits of +1/sqrt(2)
                 const int bp = bit0 + (src > 0 ? src : 0);                 // even bit position inside the staged symbol
-                const unsigned w = (unsigned)sym[bp >> 3] << (24 + (bp & 7));   // bit 31 = b0, bit 30 = b1
+                const unsigned w = ((unsigned)sym[bp >> 3] << (24 + (bp & 7))) ^ xk;   // bit 31 = b0, bit 30 = b1
                 float2 v = make_float2(__uint_as_float(0x3f3504f3u | ((w << 1) & 0x80000000u)),
                                        __uint_as_float(0x3f3504f3u | (w & 0x80000000u)));
                 if (src < 0) v = (src == kZero) ? make_float2(0.f, 0.f) : fill[-1 - src];    // unused bin / filler (or known) symbol
                 return v;
             };
-            auto data_bin = [&](int bp) -> float2 {         // bp: even bit position inside the staged range
-                const unsigned w = (unsigned)sym[bp >> 3] << (24 + (bp & 7));   // bit 31 = b0, bit 30 = b1
+            auto data_bin = [&](int bp, unsigned xk) -> float2 {         // bp: even bit position inside the staged range
+                const unsigned w = ((unsigned)sym[bp >> 3] << (24 + (bp & 7))) ^ xk;   // bit 31 = b0, bit 30 = b1
                 return make_float2(__uint_as_float(0x3f3504f3u | ((w << 1) & 0x80000000u)),
                                    __uint_as_float(0x3f3504f3u | (w & 0x80000000u)));
             };
@@ -156,10 +160,10 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
             };
             if (all_data) {
 #pragma unroll
-                for (int pp = 0; pp < PP; ++pp) put_pair(pp, data_bin(bit0 + src1[pp]), data_bin(bit0 + src2[pp]));
+                for (int pp = 0; pp < PP; ++pp) put_pair(pp, data_bin(bit0 + src1[pp], xk1[pp]), data_bin(bit0 + src2[pp], xk2[pp]));
             } else {
 #pragma unroll
-                for (int pp = 0; pp < PP; ++pp) put_pair(pp, bin(src1[pp]), bin(src2[pp]));
+                for (int pp = 0; pp < PP; ++pp) put_pair(pp, bin(src1[pp], xk1[pp]), bin(src2[pp], xk2[pp]));
             }
         }
         __syncthreads();
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
 
         // ---- epilogue: time samples with cyclic prefix (OFDM.py:221-226), gain (OFDM.py:256)
         float* o0;
-        if constexpr (KNOWN_SYMBOL) o0 = a.out;
+        if constexpr (KNOWN_SYMBOL) o0 = a.out + work * symlen;
         else o0 = a.out + stream * a.out_stride + pk * ((int64_t)a.chirp_len + (int64_t)(2 * a.P + a.L) * symlen)
                   + a.chirp_len + (int64_t)(a.P + l_first) * symlen;
         const bool al8 = ((reinterpret_cast<uintptr_t>(o0) | (uintptr_t)(a.cp * 4) | (uintptr_t)(symlen * 4)) & 7) == 0;
@@ -295,7 +299,7 @@ static int launch_tx(const gf3_plan* plan, TxArgs a, const float* known, int64_t
     // 1. the known symbol's time waveform (one symbol, gain applied)
     if (a.P > 0 && a.pk_per_stream > 0) {
         TxArgs k = a;
-        k.bits = nullptr; k.known = reinterpret_cast<const float2*>(known); k.out = known_time;
+        k.bits = nullptr; k.xor2 = nullptr; k.n_work = 1; k.known = reinterpret_cast<const float2*>(known); k.out = known_time;
         auto kern = tx_symbols_kernel<P, true>;
         GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<1, kTxThreads, smem, st>>>(k);
@@ -345,6 +349,7 @@ static int launch_frame_known(const gf3_plan* plan, const float* known, const fl
     k.known = reinterpret_cast<const float2*>(known); k.tw = plan->d_tw; k.out = known_time;
     k.cp = p.cp; k.lo = p.lo; k.hi = p.hi; k.P = p.n_pilots; k.L = p.packet_len; k.chirp_len = sync_len;
     k.gain = p.tx_gain / (float)p.N;
+    k.n_work = 1; k.pk_per_stream = 1;
     if (p.n_pilots > 0 && n_packets > 0) {
         auto kern = tx_symbols_kernel<P, true>;
         GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -389,9 +394,9 @@ extern "C" int gf3_sync_chirp(const gf3_plan* plan, float* out, void* stream) {
     return GF3_OK;
 }
 
-extern "C" int gf3_tx_modulate(const gf3_plan* plan, const uint8_t* bits_packed, int64_t bits_stride,
-                               const float* filler, const float* known, int64_t n_streams,
-                               int64_t pk_per_stream, float* out, int64_t out_stride, void* stream) {
+static int tx_modulate_common(const gf3_plan* plan, const uint8_t* bits_packed, int64_t bits_stride, const uint8_t* xor2,
+                              const float* filler, const float* known, int64_t n_streams,
+                              int64_t pk_per_stream, float* out, int64_t out_stride, void* stream) {
     GF3_REQUIRE(plan && bits_packed && known && out, "tx_modulate: null argument");
     const gf3_params& p = plan->p;
     const int K = p.N / 2 - 1, Nd = p.hi - p.lo;
@@ -404,7 +409,7 @@ extern "C" int gf3_tx_modulate(const gf3_plan* plan, const uint8_t* bits_packed,
     if (n_streams == 0) return GF3_OK;
     TxArgs a;
     memset(&a, 0, sizeof(a));
-    a.bits = bits_packed; a.filler = reinterpret_cast<const float2*>(filler);
+    a.bits = bits_packed; a.xor2 = xor2; a.filler = reinterpret_cast<const float2*>(filler);
     a.known = reinterpret_cast<const float2*>(known); a.tw = plan->d_tw; a.out = out;
     a.bits_stride = bits_stride; a.out_stride = out_stride; a.pk_per_stream = pk_per_stream > 0 ? pk_per_stream : 1;
     a.cp = p.cp; a.lo = p.lo; a.hi = p.hi; a.P = p.n_pilots; a.L = p.packet_len; a.chirp_len = p.chirp_len;
@@ -420,6 +425,57 @@ extern "C" int gf3_tx_modulate(const gf3_plan* plan, const uint8_t* bits_packed,
         case 10: return launch_tx<FftPlan<10>>(plan, a, known, n_streams, st);
         case 11: return launch_tx<FftPlan<11>>(plan, a, known, n_streams, st);
         case 12: return launch_tx<FftPlan<12>>(plan, a, known, n_streams, st);
+        default: gf3::set_error("unsupported N"); return GF3_ERR_INVALID;
+    }
+}
+
+extern "C" int gf3_tx_modulate(const gf3_plan* plan, const uint8_t* bits_packed, int64_t bits_stride,
+                               const float* filler, const float* known, int64_t n_streams,
+                               int64_t pk_per_stream, float* out, int64_t out_stride, void* stream) {
+    return tx_modulate_common(plan, bits_packed, bits_stride, nullptr, filler, known, n_streams, pk_per_stream, out, out_stride, stream);
+}
+
+extern "C" int gf3_tx_encode_modulate(const gf3_plan* plan, const uint8_t* bits_packed, int64_t bits_stride, const uint8_t* xor2,
+                                      const float* filler, const float* known, int64_t n_streams,
+                                      int64_t pk_per_stream, float* out, int64_t out_stride, void* stream) {
+    GF3_REQUIRE(xor2 != nullptr, "tx_encode_modulate: null xor2");
+    return tx_modulate_common(plan, bits_packed, bits_stride, xor2, filler, known, n_streams, pk_per_stream, out, out_stride, stream);
+}
+
+template <class P>
+static int launch_ifft(const gf3_plan* plan, const float2* spec, int64_t n, float* out, cudaStream_t st) {
+    constexpr int SF = kTxThreads / P::T;
+    const gf3_params& p = plan->p;
+    const size_t smem = (size_t)(SF * P::MP + P::TW_TOTAL) * sizeof(float2) + (size_t)(P::R / 4 + 1) * kTxThreads + 16;
+    TxArgs k;
+    memset(&k, 0, sizeof(k));
+    k.known = spec; k.tw = plan->d_tw; k.out = out;
+    k.cp = p.cp; k.lo = p.lo; k.hi = p.hi; k.P = 0; k.L = 1; k.chirp_len = 0;
+    k.gain = 1.0f / (float)p.N;                        // np.fft.ifft scaling, no transmit gain
+    k.n_work = n; k.pk_per_stream = 1;
+    auto kern = tx_symbols_kernel<P, true>;
+    GF3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = (int64_t)plan->sm_count * kTxMinBlocks;
+    if (grid > n) grid = n;
+    kern<<<(unsigned)grid, kTxThreads, smem, st>>>(k);
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}
+
+extern "C" int gf3_tx_ifft(const gf3_plan* plan, const float* spectrum, int64_t n_symbols, float* out, void* stream) {
+    GF3_REQUIRE(plan && spectrum && out, "tx_ifft: null argument");
+    GF3_REQUIRE(n_symbols >= 0, "tx_ifft: negative count");
+    if (n_symbols == 0) return GF3_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const float2* spec = reinterpret_cast<const float2*>(spectrum);
+    switch (plan->logN) {
+        case 6: return launch_ifft<FftPlan<6>>(plan, spec, n_symbols, out, st);
+        case 7: return launch_ifft<FftPlan<7>>(plan, spec, n_symbols, out, st);
+        case 8: return launch_ifft<FftPlan<8>>(plan, spec, n_symbols, out, st);
+        case 9: return launch_ifft<FftPlan<9>>(plan, spec, n_symbols, out, st);
+        case 10: return launch_ifft<FftPlan<10>>(plan, spec, n_symbols, out, st);
+        case 11: return launch_ifft<FftPlan<11>>(plan, spec, n_symbols, out, st);
+        case 12: return launch_ifft<FftPlan<12>>(plan, spec, n_symbols, out, st);
         default: gf3::set_error("unsupported N"); return GF3_ERR_INVALID;
     }
 }

@@ -54,6 +54,9 @@ SIGNATURES = {
     "gf3_peak_pick_work_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
     "gf3_peak_pick": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "gf3_tx_modulate": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "gf3_tx_encode_modulate": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "gf3_tx_ifft": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "gf3_cdiv": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "gf3_eq_estimate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gf3_eq_apply": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gf3_demap": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

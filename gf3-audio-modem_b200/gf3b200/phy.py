@@ -251,10 +251,10 @@ class Phy:
     def tx_len(self, pk_per_stream):
         return pk_per_stream * (self.chirp_len + self.pkt_samples) + self.chirp_len
 
-    def tx_modulate(self, bits_packed, filler, n_streams, pk_per_stream, out=None):
-        """bits_packed uint8 [n_streams, pk_per_stream, bits_stride] (encoded bits, MSB first),
-        filler complex64 [n_streams, K-Nd] -> waveform float32 [n_streams, tx_len]
-        (OFDM.py:191-226, 244-259, 322-323)."""
+    def tx_modulate(self, bits_packed, filler, n_streams, pk_per_stream, out=None, xor=False):
+        """bits_packed uint8 [n_streams, pk_per_stream, bits_stride] (encoded bits, MSB first; with xor=True the
+        UN-encoded bits: encode("XOR") is fused into the kernel), filler complex64 [n_streams, K-Nd]
+        -> waveform float32 [n_streams, tx_len]  (OFDM.py:163-166, 191-226, 244-259, 322-323)."""
         assert bits_packed.is_cuda and bits_packed.dtype == torch.uint8 and bits_packed.is_contiguous()
         stride = bits_packed.shape[-1]
         if filler is not None:
@@ -263,9 +263,30 @@ class Phy:
         tstride = (T + 3) // 4 * 4
         if out is None:
             out = torch.empty((n_streams, tstride), dtype=torch.float32, device=self.device)
-        check(self._call("gf3_tx_modulate", self._plan, _ptr(bits_packed), stride, _ptr(filler), _ptr(self.known),
-                                       n_streams, pk_per_stream, _ptr(out), out.stride(0), _STREAM))
+        if xor:
+            check(self._call("gf3_tx_encode_modulate", self._plan, _ptr(bits_packed), stride, _ptr(self.xor2), _ptr(filler), _ptr(self.known),
+                             n_streams, pk_per_stream, _ptr(out), out.stride(0), _STREAM))
+        else:
+            check(self._call("gf3_tx_modulate", self._plan, _ptr(bits_packed), stride, _ptr(filler), _ptr(self.known),
+                             n_streams, pk_per_stream, _ptr(out), out.stride(0), _STREAM))
         return out[:, :T]
+
+    def ifft_symbols(self, spectrum):
+        """np.fft.ifft of Hermitian spectra given as bins 1..K: complex64 [n, K] -> float32 [n, N + cp] (CP prepended, no gain)."""
+        assert spectrum.is_cuda and spectrum.dtype == torch.complex64 and spectrum.is_contiguous() and spectrum.shape[-1] == self.K
+        n = spectrum.numel() // self.K
+        out = torch.empty((n, self.symlen), dtype=torch.float32, device=self.device)
+        check(self._call("gf3_tx_ifft", self._plan, _ptr(spectrum), n, _ptr(out), _STREAM))
+        return out
+
+    def cdiv(self, Y, H):
+        """Y / H, H broadcast over rows: complex64 [n, m] / [m]."""
+        assert Y.is_cuda and Y.dtype == torch.complex64 and Y.is_contiguous() and H.is_cuda and H.dtype == torch.complex64
+        m = Y.shape[-1]
+        assert H.numel() == m
+        out = torch.empty_like(Y)
+        check(self._call("gf3_cdiv", _ptr(Y), _ptr(H.contiguous()), Y.numel() // m, m, _ptr(out), _STREAM))
+        return out
 
     # ------------------------------------------------------------------ channel + counters
     def channel_sim(self, x, taps, sigma, seed, stream_ids=None):

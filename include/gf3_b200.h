@@ -209,6 +209,21 @@ GF3_API int gf3_tx_modulate(const gf3_plan* plan, const uint8_t* bits_packed, in
                     const float* filler, const float* known, int64_t n_streams,
                     int64_t pk_per_stream, float* out, int64_t out_stride, void* stream);
 
+/* gf3_tx_modulate with transmitter.encode("XOR") fused (OFDM.py:163-166): bits_packed holds the UN-encoded bits and every data
+ * carrier's bit pair is XORed with xor2[carrier] = (b0 << 1) | b1 of known_sequence[:2 Nd] while the symbol is built (the mirror of
+ * the receive kernels' fused decode).  The reference pads AFTER encoding; a caller that pads before passes padding already XORed
+ * with the same table (x ^ k ^ k = x), as the drop-in's transmit() does. */
+GF3_API int gf3_tx_encode_modulate(const gf3_plan* plan, const uint8_t* bits_packed, int64_t bits_stride, const uint8_t* xor2,
+                           const float* filler, const float* known, int64_t n_streams,
+                           int64_t pk_per_stream, float* out, int64_t out_stride, void* stream);
+/* Hermitian spectra -> real symbols: np.fft.ifft(X).real of n_symbols symbols given as bins 1..K (X[0] = X[N/2] = 0,
+ * X[N-k] = conj X[k]) with the plan's cyclic prefix prepended and NO transmit gain (OFDM.py:322-323; the old API's module-level
+ * IFFT, Initial OFDM Test.ipynb cell 13).  spectrum complex64 [n_symbols, K] -> out float32 [n_symbols, N + cp]. */
+GF3_API int gf3_tx_ifft(const gf3_plan* plan, const float* spectrum, int64_t n_symbols, float* out, void* stream);
+/* Y / H with H broadcast over the rows: the old API's module-level equalise(Y, H) (Weekend Challenge.ipynb:225).
+ * Y, out complex64 [n_rows, m]; H complex64 [m]. */
+GF3_API int gf3_cdiv(const float* Y, const float* H, int64_t n_rows, int32_t m, float* out, void* stream);
+
 /* ---- stage-level entry points (SURVEY 8a rows 5, 9, 11 as separate public methods) ------ */
 /* receiver.equalise, first half (OFDM.py:429-462) on spectra the caller already holds:
  *   start, end  complex64 [n_packets, P, K]  bins 1..K of the leading / trailing known symbols

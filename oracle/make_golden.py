@@ -251,6 +251,20 @@ def kat4():
                                                          nerr, len(bits_in), len(near5), len(near4), t_tx, t_rx))
 
 
+def notebook_cells():
+    """Code cells of the notebooks written against the OLD API (older OFDM.py revisions, code not in the repository), as
+    the reference ships them: tests/test_gpu_legacy_api.py executes them unmodified against the drop-in."""
+    import json
+    out = {}
+    for nb in ("Weekend Challenge.ipynb", "Initial OFDM Test.ipynb"):
+        with open(os.path.join(ref_shim.REF_ROOT, nb)) as f:
+            cells = json.load(f)["cells"]
+        out[nb] = [{"index": i, "source": "".join(c["source"])} for i, c in enumerate(cells) if c["cell_type"] == "code"]
+    with open(os.path.join(OUT, "notebook_cells.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("notebook cells:", {k: len(v) for k, v in out.items()})
+
+
 def sync_quirk():
     """A signal whose final chirp ends < 2 samples before the end: the reference wipes all
     detections (OFDM.py:366-370); with >= 2 trailing samples it keeps them."""
@@ -273,7 +287,7 @@ def sync_quirk():
 if __name__ == "__main__":
     assert ref_shim.available(), "reference not found"
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["kat1", "stage", "kat3", "quirk", "kat4"]
+    which = sys.argv[1:] or ["kat1", "stage", "kat3", "quirk", "kat4", "cells"]
     if "kat1" in which:
         kat1()
     if "stage" in which:
@@ -285,5 +299,7 @@ if __name__ == "__main__":
         sync_quirk()
     if "kat4" in which:
         kat4()
+    if "cells" in which:
+        notebook_cells()
     for f in sorted(os.listdir(OUT)):
         print("%-24s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

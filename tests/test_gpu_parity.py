@@ -242,6 +242,16 @@ def test_stage_transmit(name, known_sequence):
     assert np.max(np.abs(out - g["tx"])) < 2e-7 * max(1.0, np.max(np.abs(g["tx"])) / 0.2)
     chirp = phy.sync_chirp().cpu().numpy()
     assert np.max(np.abs(chirp - orc.sync_chirp(p))) < 1e-7
+    # encode("XOR") fused into the kernel (gf3_tx_encode_modulate): the un-encoded bits, padding pre-XORed with the known bits
+    dbs = 2 * p.Nd
+    nb = len(g["bits_in"])
+    raw = np.concatenate([g["bits_in"].astype(np.int64),
+                          np.bitwise_xor(g["pad"].astype(np.int64), known_sequence[:dbs][(nb + np.arange(len(g["pad"]))) % dbs])])
+    packed2 = np.zeros((npk, phy.bits_stride), np.uint8)
+    pb2 = np.packbits(raw.astype(np.uint8).reshape(npk, -1), axis=1)
+    packed2[:, : pb2.shape[1]] = pb2
+    out2 = phy.tx_modulate(torch.from_numpy(packed2).cuda().reshape(1, npk, -1), fill, 1, npk, xor=True)[0].cpu().numpy()
+    assert np.array_equal(out2, out), "device-side encode differs from the host-encoded transmit"
 
 
 # ----------------------------------------------------------------------------- known answers
