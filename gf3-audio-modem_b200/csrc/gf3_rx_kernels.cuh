@@ -41,6 +41,9 @@ constexpr int kThreads = 256;
 #ifndef GF3_PREFETCH
 #define GF3_PREFETCH (-1)      // -1: per-plan default (see rx_demod_kernel)
 #endif
+#ifndef GF3_PREFETCH_PART
+#define GF3_PREFETCH_PART 16   // GF3_PREFETCH == 3: registers (complex points) of the next batch requested ahead
+#endif
 #ifndef GF3_EST_U
 #define GF3_EST_U 20
 #endif
@@ -162,19 +165,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 
 // Load one symbol's N samples (CP already skipped by the caller) into the first-pass layout
 // x[i] = z[t + i*T],  z[m] = (s[2m], s[2m+1]).
-template <class P, class S>
+template <class P, class S, int I0 = 0, int I1 = P::R>
 __device__ __forceinline__ void load_symbol(float2 (&x)[P::R], const S* __restrict__ s, int t) {
     if constexpr (sizeof(S) == 4) {
         if ((reinterpret_cast<uintptr_t>(s) & 7) == 0) {
 #pragma unroll
-            for (int i = 0; i < P::R; ++i) x[i] = ldg_stream2(reinterpret_cast<const float*>(s) + 2 * (t + i * P::T));
+            for (int i = I0; i < I1; ++i) x[i] = ldg_stream2(reinterpret_cast<const float*>(s) + 2 * (t + i * P::T));
             return;
         }
     }
     // odd sample offset (arbitrary sync index) or PCM: scalar / narrow loads.  Each touches part of the same
     // sectors as its neighbours, so these loads DO allocate in L1
 #pragma unroll
-    for (int i = 0; i < P::R; ++i) x[i] = ldg_pair<S>(s + 2 * (t + i * P::T));
+    for (int i = I0; i < I1; ++i) x[i] = ldg_pair<S>(s + 2 * (t + i * P::T));
 }
 
 // predicated one-byte shared-memory store: the address is an operand, so the compiler cannot sink its
@@ -541,8 +544,14 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
             bulk_g2s(raw + (size_t)g * RAWB, reinterpret_cast<const void*>(A & ~(uintptr_t)15), bytes, mbar);
         }
     };
+    // PREFETCH == 3: the first GF3_PREFETCH_PART registers of the next batch are requested before the equaliser phase
+    // (a partial register prefetch: what fits next to the phase's own registers), the rest at the start of the FFT
+    constexpr int PF = (PREFETCH == 3) ? (GF3_PREFETCH_PART < R ? GF3_PREFETCH_PART : R) : 0;
     if constexpr (PREFETCH == 1) {
         if (c_begin < c_end) load_symbol<P, S>(x, sym_ptr(c_begin, (int)(c_begin % cpp) * FLUSH), ta);
+    }
+    if constexpr (PREFETCH == 3) {
+        if (c_begin < c_end) load_symbol<P, S, 0, PF>(x, sym_ptr(c_begin, (int)(c_begin % cpp) * FLUSH), ta);
     }
     if constexpr (STAGED) {       // (the barrier above made the mbarrier's initialisation visible)
         if (tid == 0 && c_begin < c_end) stage_issue(c_begin, (int)(c_begin % cpp) * FLUSH);
@@ -666,7 +675,8 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                         if (b + 1 < nb_eff) stage_issue(c, l0 + (b + 1) * SF);
                         else if (c + 1 < c_end) stage_issue(c + 1, (int)((c + 1) % cpp) * FLUSH);
                     }
-                } else if constexpr (PREFETCH != 1) load_symbol<P, S>(x, sym_ptr(c, l0 + b * SF), ta);
+                } else if constexpr (PREFETCH == 3) load_symbol<P, S, PF, R>(x, sym_ptr(c, l0 + b * SF), ta);
+                else if constexpr (PREFETCH != 1) load_symbol<P, S>(x, sym_ptr(c, l0 + b * SF), ta);
 #endif
 #if GF3_ABL & 2
                 {
@@ -686,6 +696,12 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                         load_symbol<P, S>(x, sym_ptr(c, l0 + (b + 1) * SF), ta);
                     } else if (c + 1 < c_end) {
                         load_symbol<P, S>(x, sym_ptr(c + 1, (int)((c + 1) % cpp) * FLUSH), ta);
+                    }
+                } else if constexpr (PREFETCH == 3) {
+                    if (b + 1 < nb_eff) {
+                        load_symbol<P, S, 0, PF>(x, sym_ptr(c, l0 + (b + 1) * SF), ta);
+                    } else if (c + 1 < c_end) {
+                        load_symbol<P, S, 0, PF>(x, sym_ptr(c + 1, (int)((c + 1) % cpp) * FLUSH), ta);
                     }
                 } else if constexpr (PREFETCH == 2) {
                     const int nl = l0 + (b + 1) * SF + ga;
