@@ -303,7 +303,7 @@ def parity_check(phy, cfg, samples_dev, timed_bits, raw, n_check, extra_results=
             ref_bits = np.concatenate([ref[i]["bits"] for i in keep]) if keep else np.zeros(0, np.int64)
             ref_eq = np.concatenate([ref[i]["eq"][:, dc] for i in keep]) if keep else np.zeros((0, len(dc)), complex)
             got = got[keep]
-            res = classify_bit_diffs(got.reshape(-1), ref_bits, ref_eq) if keep else dict(n_bits=0, n_diff=0, near_1e5=0, near_scaled=0, beyond=0, worst_margin=0.0, n_points_near_1e5=0)
+            res = classify_bit_diffs(got.reshape(-1), ref_bits, ref_eq) if keep else dict(n_bits=0, n_diff=0, near_1e5=0, near_scaled=0, within_eq_tol=0, beyond=0, worst_margin=0.0, n_points_near_1e5=0)
             res["streams_oracle_sync_ok"] = int(sum(sync_ok))
             if peaks_gpu is not None:
                 res["sync_index_mismatches"] = int(sum(not np.array_equal(o["peaks"], pg) for o, pg in zip(ref, peaks_gpu)))

@@ -44,10 +44,12 @@ from oracle.parity import BOUNDARY_TOL, classify_bit_diffs  # noqa: E402,F401  (
 def assert_bits_match(got, ref_bits, ref_eq_data, what):
     """Bit-exact except decisions within BOUNDARY_TOL of a boundary; those are counted and printed."""
     c = classify_bit_diffs(got, ref_bits, ref_eq_data)
-    print("%s: %d bits, %d differ (%d within 1e-5 of a boundary, %d within 1e-5*|point|, %d beyond; worst margin %.2e); "
-          "%d oracle points lie within 1e-5 of a boundary" % (what, c["n_bits"], c["n_diff"], c["near_1e5"], c["near_scaled"],
-                                                              c["beyond"], c["worst_margin"], c["n_points_near_1e5"]))
-    assert c["beyond"] == 0, "%s: %d bit mismatches away from decision boundaries (worst margin %.3e)" % (what, c["beyond"], c["worst_margin"])
+    print("%s: %d bits, %d differ (%d within 1e-5 of a boundary, %d within 1e-5*|point|, %d within the 1e-4*|point| constellation "
+          "tolerance, %d beyond; worst margin %.2e); %d oracle points lie within 1e-5 of a boundary"
+          % (what, c["n_bits"], c["n_diff"], c["near_1e5"], c["near_scaled"], c["within_eq_tol"], c["beyond"], c["worst_margin"],
+             c["n_points_near_1e5"]))
+    far = c["beyond"] + c["within_eq_tol"]
+    assert far == 0, "%s: %d bit mismatches away from decision boundaries (worst margin %.3e)" % (what, far, c["worst_margin"])
     return c
 
 
