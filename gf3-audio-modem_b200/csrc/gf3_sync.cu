@@ -305,6 +305,8 @@ struct FusedArgs {
     float* blockmax;         // [n_streams, nblk_out] or null
     int64_t r_stride, p_stride, T, out_len, n_streams;
     int nblk_in, nblk_out, parts;
+    int sparse;              // 1: detection-only -- blocks that provably hold no candidate are not transformed back
+    float thresh;            // detection threshold (OFDM.py:361), for the sparse rule
 };
 
 template <class S> __device__ __forceinline__ float sample_to_f32(S v) { return (float)v; }
@@ -426,6 +428,19 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
     __syncthreads();                                       // twiddles staged
     int64_t cur_stream = -1;
     float2 x[R];
+    // ---- sparse (detection-only) mode.  A candidate of chirp_method needs P[i+1] > thresh * max(P) (OFDM.py:361).
+    // |y[n]| <= sum_k |Y[k]| for every sample of a block, so a block whose spectrum's l1 norm stays below
+    // thresh * (the largest sample seen so far in this stream, a lower bound of max(P)) holds no candidate and the
+    // global maximum is not in it: its inverse FFT and its stores are skipped (block maximum = -inf).  What the
+    // detection rule reads next to a candidate stays exact: the block after a block that may still turn out hot is
+    // always computed, a computed block also writes the sample before its first one (the circular convolution of a
+    // 2048-tap partition is valid from sample 2047 on) when its predecessor was skipped, and the first and last
+    // block of every CTA's range are always computed.  The detections are identical to the full computation's;
+    // how many blocks are skipped depends on the data (chirp peak against the l1 norm of the data blocks' spectra:
+    // ~93 % at 8 dB and above on the C3 framing, none below ~5 dB).
+    float runmax = __int_as_float(0xff800000);
+    bool prev_hotish = true, prev_skipped = false;
+    __shared__ float wl1[NT / 32];
 #pragma unroll 1
     for (int64_t c = c_begin; c < c_end; ++c) {
         const int64_t stream = c / a.nblk_out;
@@ -435,6 +450,9 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
         if (stream != cur_stream) {
             // ---- (re)start: the ring holds the spectra of blocks b-1 .. b-(parts-1) (zero before the stream)
             cur_stream = stream;
+            runmax = __int_as_float(0xff800000);
+            prev_hotish = true;
+            prev_skipped = false;
             ring_zero();
             if constexpr (R1 > 0) {
 #pragma unroll 1
@@ -507,13 +525,44 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
         }
         if constexpr (R1 > 0) ring_store(b % R1, xre, xim, dcny);   // X_b replaces X_{b-(parts-1)}, which was read just above
 
+        // Y of the thread's pairs
+#pragma unroll
+        for (int q = 0; q < Q; ++q) arp[q] = p_sub(arp[q], arn[q]);
+        float* Prow = a.P + stream * a.p_stride;
+        const int64_t n0 = (int64_t)b * kB - kB;
+        if (a.sparse) {
+            // l1 norm of the block's spectrum (|Y| <= |re| + |im|; bins 1..N/2-1 count twice: Hermitian halves)
+            float l1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float2 yre = pk_unpack(arp[q]), yim = pk_unpack(ai[q]);
+                const float lane0 = fabsf(yre.x) + fabsf(yim.x), lane1 = fabsf(yre.y) + fabsf(yim.y);
+                l1 += (q == 0 && tid == 0) ? lane0 : lane0 + lane1;          // k = M/2 sits in both lanes of its slot
+            }
+            l1 *= 2.f;
+            if (tid == 0) l1 += fabsf(dc) + fabsf(ny);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+            if ((tid & 31) == 0) wl1[tid >> 5] = l1;
+            __syncthreads();
+            float bound = wl1[0];
+#pragma unroll
+            for (int w = 1; w < NT / 32; ++w) bound += wl1[w];
+            const bool forced = c == c_begin || c + 1 == c_end || prev_hotish;
+            if (!forced && bound * 1.001f < a.thresh * runmax) {             // (runmax = -inf or <= 0: never true)
+                if (tid == 0 && a.blockmax) a.blockmax[stream * a.nblk_out + b] = __int_as_float(0xff800000);
+                prev_hotish = false;
+                prev_skipped = true;
+                continue;
+            }
+        }
         // ---- inverse untangle: Z[k] = E + jO, E = Y[k] + conj Y[M-k], O = (Y[k] - conj Y[M-k]) e^{+j theta};
         // the forward engine runs on conj Z
         __syncthreads();                                   // every thread has read its part of the forward spectrum in W
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const int k = (q == 0 && tid == 0) ? M / 2 : tid + q * NT;
-            const float2 yre = pk_unpack(p_sub(arp[q], arn[q])), yim = pk_unpack(ai[q]);
+            const float2 yre = pk_unpack(arp[q]), yim = pk_unpack(ai[q]);
             const float2 E = make_float2(yre.x + yre.y, yim.x - yim.y);
             const float2 D = make_float2(yre.x - yre.y, yim.x + yim.y);
             const float2 O = cmul(D, cs[q]);
@@ -529,9 +578,9 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
         fft_forward_to_regs<P, NT>(y, W, tw, tid, 0);
         // ---- last B samples of the block: z[m], m in [M/2, M): P[n0 + 2m] = Re z, P[n0 + 2m + 1] = -Im z.
         // Last pass (radix 8, stride 256): y[q*8 + i] is z[tid + 128 q + 256 i]
-        float* Prow = a.P + stream * a.p_stride;
-        const int64_t n0 = (int64_t)b * kB - kB;
         float lmax = __int_as_float(0xff800000);
+        // the sample before this block's first one, when the block that owns it was skipped (z[1023], odd part)
+        if (prev_skipped && tid == NT - 1 && b > 0) Prow[n0 + 2 * M / 2 - 1] = -y[8 + 3].y;
         const bool fast = n0 + 2 * M <= a.out_len && ((reinterpret_cast<uintptr_t>(Prow + n0) & 7) == 0);
 #pragma unroll
         for (int q = 0; q < 2; ++q)
@@ -557,6 +606,14 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
             for (int w = 1; w < NT / 32; ++w) mx = fmaxf(mx, wmax[w]);
             if (a.blockmax) a.blockmax[stream * a.nblk_out + b] = mx;
             if (mx > __int_as_float(0xff800000)) atomic_max_float(a.pmax + stream, mx);
+            wmax[0] = mx;
+        }
+        if (a.sparse) {                                    // (uniform: every thread takes the same decisions)
+            __syncthreads();
+            const float mx = wmax[0];
+            runmax = fmaxf(runmax, mx);
+            prev_hotish = mx * 1.001f >= a.thresh * runmax;
+            prev_skipped = false;
         }
     }
 }
@@ -596,6 +653,7 @@ struct PeakArgs {
     float thresh;
     const float* blockmax;       // optional [n_streams, nblk]: maximum of every 2048-sample block of P (fused matched filter)
     int32_t nblk;
+    int32_t sparse;              // P holds valid samples only in (and next to) blocks whose maximum passes the threshold
 };
 
 // Phase 1, fully parallel: one candidate bit per position of `zeros` (OFDM.py:360-361).  A CTA takes
@@ -734,6 +792,16 @@ __global__ void __launch_bounds__(256) peak_pick_kernel(const PeakArgs a) {
                 const float prev = v[e] * inv, cur = v[e + 1] * inv, nxt = v[e + 2] * inv;
                 const float d0 = cur - prev, d1 = nxt - cur;
                 if (d0 * d1 <= 0.f && cur > a.thresh) m |= 1u << e;
+            }
+            if (a.sparse && m) {
+                // a candidate at position i is the sample P[i+1]: it counts only inside a block that can hold one (the
+                // other blocks were not computed: their memory is not P).  24 positions touch at most two blocks
+                const int64_t blo = (base + 1) / kB;
+                const bool hot_lo = blo < a.nblk && bm[blo] * inv > a.thresh;
+                const bool hot_hi = blo + 1 < a.nblk && bm[blo + 1] * inv > a.thresh;
+                const int split = (int)((blo + 1) * kB - (base + 1));            // first e whose sample lies in the next block
+                const unsigned lo_mask = split >= 32 ? 0xffffffffu : ((1u << split) - 1u);
+                m &= (hot_lo ? lo_mask : 0u) | (hot_hi ? ~lo_mask : 0u);
             }
             if (base < pos) m &= 0xffffffffu << (int)(pos - base);       // positions behind the walk
             if (base + PER > nz) m &= 0xffffffffu >> (32 - (int)(nz - base)); // positions past the end
@@ -922,7 +990,7 @@ static int launch_fused(const gf3_plan* plan, const FusedArgs& a, cudaStream_t s
 
 // chirp_method's convolution for a batch of streams (OFDM.py:357-358); blockmax is optional
 static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_stride, int64_t n_streams, int64_t T,
-                        float* P, int64_t p_stride, float* pmax, float* blockmax, void* work, cudaStream_t st) {
+                        float* P, int64_t p_stride, float* pmax, float* blockmax, void* work, cudaStream_t st, bool sparse = false) {
     const XcorrGeom g = xcorr_geom(plan, n_streams, T);
     GF3_REQUIRE(p_stride >= g.out_len, "xcorr: p_stride %lld < T + chirp_len - 1 = %lld", (long long)p_stride, (long long)g.out_len);
     GF3_REQUIRE(fmt == GF3_SAMPLE_F32 || fmt == GF3_SAMPLE_I16 || fmt == GF3_SAMPLE_U8, "xcorr: unknown sample format %d", fmt);
@@ -931,6 +999,7 @@ static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_
         a.r = r; a.Hs = reinterpret_cast<const float4*>(plan->d_chirp_pairs); a.Hdc = plan->d_chirp_dc; a.tw = plan->d_sync_tw;
         a.P = P; a.pmax = pmax; a.blockmax = blockmax; a.r_stride = r_stride; a.p_stride = p_stride; a.T = T; a.out_len = g.out_len;
         a.n_streams = n_streams; a.nblk_in = g.nblk_in; a.nblk_out = g.nblk_out; a.parts = plan->sync_parts;
+        a.sparse = (sparse && blockmax) ? 1 : 0; a.thresh = plan->p.thresh;
         if (fmt == GF3_SAMPLE_F32) return launch_fused<float>(plan, a, st);
         if (fmt == GF3_SAMPLE_I16) return launch_fused<int16_t>(plan, a, st);
         return launch_fused<uint8_t>(plan, a, st);
@@ -958,9 +1027,15 @@ static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_
     return GF3_OK;
 }
 
+// blockmax + one stream per CTA: is the single-pass picker used?  (the sparse matched filter needs it: the mark + scan
+// form reads all of P)
+static bool single_pass_picker(const gf3_plan* plan, int64_t n_streams, bool have_blockmax) {
+    return n_streams >= 2 * (int64_t)plan->sm_count || (have_blockmax && n_streams >= plan->sm_count / 2);
+}
+
 static int peak_pick_common(const gf3_plan* plan, const float* P, int64_t p_stride, int64_t n_streams, int64_t T, const float* pmax,
                             const float* blockmax, int nblk, int64_t* peaks, int32_t max_peaks, int32_t* count, void* work,
-                            cudaStream_t st) {
+                            cudaStream_t st, bool sparse = false) {
     PeakArgs a;
     a.P = P; a.pmax = pmax; a.peaks = peaks; a.count = count; a.p_stride = p_stride;
     a.plen = T + plan->p.chirp_len - 1; a.max_peaks = max_peaks; a.Lc = plan->p.chirp_len; a.thresh = plan->p.thresh;
@@ -968,12 +1043,13 @@ static int peak_pick_common(const gf3_plan* plan, const float* P, int64_t p_stri
     a.mask = reinterpret_cast<uint32_t*>(work);
     a.n_streams = n_streams;
     a.nw = (a.plen - 2 + 31) / 32;
-    a.blockmax = blockmax; a.nblk = nblk;
+    a.blockmax = blockmax; a.nblk = nblk; a.sparse = sparse ? 1 : 0;
+    GF3_REQUIRE(!sparse || (blockmax && single_pass_picker(plan, n_streams, true)), "peak_pick: internal: sparse P needs the block maxima");
     int64_t blocks = a.n_streams * ((a.nw + 63) / 64);               // chunks of 64 mask words
     const int64_t cap = (int64_t)plan->sm_count * 32;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (n_streams >= 2 * (int64_t)plan->sm_count || (blockmax && n_streams >= plan->sm_count / 2)) {
+    if (single_pass_picker(plan, n_streams, blockmax != nullptr)) {
         // enough streams to fill the GPU: one pass, one CTA each (with block maxima even a few dozen streams are
         // cheaper this way: the walk touches only the blocks around the chirp peaks)
         peak_pick_kernel<<<(unsigned)n_streams, 256, 0, st>>>(a);
@@ -1018,9 +1094,9 @@ extern "C" size_t gf3_sync_work_bytes(const gf3_plan* plan, int64_t n_streams, i
     return sync_off_blockmax(g, n_streams) + xw + gf3_peak_pick_work_bytes(plan, n_streams, T) + 256;
 }
 
-extern "C" int gf3_sync_streams(const gf3_plan* plan, const void* r, int32_t sample_format, int64_t r_stride, int64_t n_streams,
-                                int64_t T, float* P, int64_t p_stride, float* pmax, int64_t* peaks, int32_t max_peaks,
-                                int32_t* count, void* work, void* stream) {
+static int sync_common(const gf3_plan* plan, const void* r, int32_t sample_format, int64_t r_stride, int64_t n_streams,
+                       int64_t T, float* P, int64_t p_stride, float* pmax, int64_t* peaks, int32_t max_peaks,
+                       int32_t* count, void* work, void* stream, bool detect_only) {
     GF3_REQUIRE(plan && r && P && pmax && peaks && count && work, "sync_streams: null argument");
     GF3_REQUIRE(max_peaks >= 1 && n_streams >= 0 && n_streams <= 0x7fffffff && T >= 1, "sync_streams: bad sizes");
     if (n_streams == 0) return GF3_OK;
@@ -1031,9 +1107,23 @@ extern "C" int gf3_sync_streams(const gf3_plan* plan, const void* r, int32_t sam
     float* blockmax = fused ? reinterpret_cast<float*>(w) : nullptr;
     void* xwork = w + sync_off_blockmax(g, n_streams);
     void* pwork = reinterpret_cast<char*>(xwork) + ((gf3_xcorr_work_bytes(plan, n_streams, T) + 255) & ~(size_t)255);
-    int rc = xcorr_common(plan, r, sample_format, r_stride, n_streams, T, P, p_stride, pmax, blockmax, xwork, st);
+    // detection only: blocks of P that provably hold no candidate are not computed (the detections are the same)
+    const bool sparse = detect_only && fused && single_pass_picker(plan, n_streams, true) && !getenv("GF3_SYNC_DENSE");
+    int rc = xcorr_common(plan, r, sample_format, r_stride, n_streams, T, P, p_stride, pmax, blockmax, xwork, st, sparse);
     if (rc) return rc;
-    return peak_pick_common(plan, P, p_stride, n_streams, T, pmax, blockmax, g.nblk_out, peaks, max_peaks, count, pwork, st);
+    return peak_pick_common(plan, P, p_stride, n_streams, T, pmax, blockmax, g.nblk_out, peaks, max_peaks, count, pwork, st, sparse);
+}
+
+extern "C" int gf3_sync_streams(const gf3_plan* plan, const void* r, int32_t sample_format, int64_t r_stride, int64_t n_streams,
+                                int64_t T, float* P, int64_t p_stride, float* pmax, int64_t* peaks, int32_t max_peaks,
+                                int32_t* count, void* work, void* stream) {
+    return sync_common(plan, r, sample_format, r_stride, n_streams, T, P, p_stride, pmax, peaks, max_peaks, count, work, stream, false);
+}
+
+extern "C" int gf3_sync_detect(const gf3_plan* plan, const void* r, int32_t sample_format, int64_t r_stride, int64_t n_streams,
+                               int64_t T, float* P_scratch, int64_t p_stride, float* pmax, int64_t* peaks, int32_t max_peaks,
+                               int32_t* count, void* work, void* stream) {
+    return sync_common(plan, r, sample_format, r_stride, n_streams, T, P_scratch, p_stride, pmax, peaks, max_peaks, count, work, stream, true);
 }
 
 extern "C" size_t gf3_peak_pick_work_bytes(const gf3_plan* plan, int64_t n_streams, int64_t T) {

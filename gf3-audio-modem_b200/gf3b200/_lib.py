@@ -66,6 +66,7 @@ SIGNATURES = {
     "gf3_random_bytes": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_uint64, c_void_p]),
     "gf3_sync_work_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
     "gf3_sync_streams": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "gf3_sync_detect": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "gf3_peaks_to_offsets": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "gf3_ber_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "gf3_pcm_to_f32": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_void_p]),

@@ -199,9 +199,11 @@ class Phy:
 
     _FMT = {torch.uint8: 0, torch.int16: 1, torch.float32: 2}       # GF3_SAMPLE_*
 
-    def sync_streams(self, r, max_peaks=8):
+    def sync_streams(self, r, max_peaks=8, detect_only=False):
         """chirp_method (OFDM.py:356-372) for a batch of streams in one call (gf3_sync_streams): r [B, T] float32,
-        int16 or uint8 -> (P [B, T+Lc-1], pmax [B], peaks int64 [B, max_peaks], count int32 [B])."""
+        int16 or uint8 -> (P [B, T+Lc-1], pmax [B], peaks int64 [B, max_peaks], count int32 [B]).
+        detect_only (gf3_sync_detect): the same peaks / count / pmax, but P is scratch -- blocks that provably hold no
+        candidate are not computed."""
         assert r.is_cuda and r.dim() == 2 and r.stride(1) == 1 and r.dtype in self._FMT
         B, T = r.shape
         rs = r.stride(0) if B > 1 else T
@@ -212,7 +214,7 @@ class Phy:
         peaks = torch.full((B, max_peaks), -1, dtype=torch.int64, device=self.device)
         count = torch.empty((B,), dtype=torch.int32, device=self.device)
         work = torch.empty((max(16, int(self.lib.gf3_sync_work_bytes(self._plan, B, T))),), dtype=torch.uint8, device=self.device)
-        check(self._call("gf3_sync_streams", self._plan, _ptr(r), self._FMT[r.dtype], rs, B, T, _ptr(P), pstride, _ptr(pmax),
+        check(self._call("gf3_sync_detect" if detect_only else "gf3_sync_streams", self._plan, _ptr(r), self._FMT[r.dtype], rs, B, T, _ptr(P), pstride, _ptr(pmax),
                          _ptr(peaks), max_peaks, _ptr(count), _ptr(work), _STREAM))
         return P[:, :plen], pmax, peaks, count
 
@@ -234,7 +236,7 @@ class Phy:
         chirps were found where the reference's slicing would succeed), peaks, count, Hs, He, slope[, eq])."""
         assert r.is_cuda and r.dim() == 2 and r.stride(1) == 1 and r.dtype in self._FMT
         B, T = r.shape
-        _, _, peaks, count = self.sync_streams(r, pk_expected + 3)
+        _, _, peaks, count = self.sync_streams(r, pk_expected + 3, detect_only=True)
         off, ok = self.peaks_to_offsets(peaks, count, r.stride(0), T, pk_expected)
         # offsets are relative to r's first sample.  PCM samples (and, when staged is set, float32 ones: packets of a
         # raw stream start at arbitrary sample offsets) enter the receive kernels through the staging buffer

@@ -106,6 +106,9 @@ def _sync_compare(phy, p, r, what):
     P2, pmax2, peaks2, count2 = phy.sync_streams(r, 16)
     assert torch.equal(P2, P) and torch.equal(pmax2, pmax)
     assert np.array_equal(count2.cpu().numpy(), count) and np.array_equal(peaks2.cpu().numpy(), peaks)
+    # detection only (gf3_sync_detect: inverse transforms only where the l1 bound of a block's spectrum allows a candidate)
+    _, pmax3, peaks3, count3 = phy.sync_streams(r, 16, detect_only=True)
+    assert torch.equal(pmax3, pmax) and np.array_equal(count3.cpu().numpy(), count) and np.array_equal(peaks3.cpu().numpy(), peaks)
     scale = 20000.0 / float(r.abs().max())
     q = torch.round(r * scale).to(torch.int16)
     Pq, _, peaks_q, count_q = phy.sync_streams(q, 16)
@@ -141,6 +144,31 @@ def test_c3_multistream_sync_vs_oracle(known_sequence):
     # trips the reference's end-of-signal wipe-out (OFDM.py:366-370): the REFERENCE loses those streams, and so do we
     assert set(hist2) <= {0, 2} and hist2.get(2, 0) >= B * 0.5
     print("trail = 2: the reference's own rule wipes %d of %d streams (GPU identical)" % (hist2.get(0, 0), B))
+
+
+@pytest.mark.parametrize("snr_db", [-3.0, 3.0, 6.0, 12.0])
+def test_sync_detect_equals_dense_across_snr(snr_db, known_sequence):
+    """gf3_sync_detect against gf3_sync_streams where the skip rule is marginal: around the SNR at which the l1 bound of
+    the data blocks crosses the threshold (some streams skip most blocks, others none), noise-dominated streams with
+    many candidates, truncated tails (wipe-out quirk), uint8 input."""
+    torch = _torch()
+    from gf3b200 import synth
+    B = 160
+    phy, p = _pair(known_sequence, N=1024, cp=32, lo=1, hi=512, n_pilots=20, packet_len=180, fit_lo=125, fit_hi=250)
+    b = synth.make_batch(phy, B, 1, snr_db=snr_db, seed=int(100 + snr_db), lead=513, trail=3)
+    r = b["r"]
+    r[5, -3000:] = 0.0                                     # a stream that loses its last chirp
+    r[7] = 0.05 * torch.randn(r.shape[1], device="cuda")   # noise only
+    P, pmax, peaks, count = phy.sync_streams(r, 16)
+    _, pmax2, peaks2, count2 = phy.sync_streams(r, 16, detect_only=True)
+    assert torch.equal(pmax, pmax2) and torch.equal(count, count2) and torch.equal(peaks, peaks2)
+    ref5 = np.flatnonzero(orc.chirp_method(p, r[5].cpu().numpy().astype(np.float64)))
+    assert np.array_equal(peaks2[5, : int(count2[5])].cpu().numpy(), ref5)
+    q = (torch.round(r * (100.0 / float(r.abs().max()))) + 128.0).to(torch.uint8)
+    _, pq, kq, cq = phy.sync_streams(q, 16)
+    _, pq2, kq2, cq2 = phy.sync_streams(q, 16, detect_only=True)
+    assert torch.equal(pq, pq2) and torch.equal(kq, kq2) and torch.equal(cq, cq2)
+    print("sync detect %g dB: detections per stream %s" % (snr_db, sorted({int(c): int((count == c).sum()) for c in count.unique()}.items())))
 
 
 def test_a2_multistream_sync_vs_oracle(known_sequence):
