@@ -307,6 +307,7 @@ struct FusedArgs {
     int nblk_in, nblk_out, parts;
     int sparse;              // 1: detection-only -- blocks that provably hold no candidate are not transformed back
     float thresh;            // detection threshold (OFDM.py:361), for the sparse rule
+    int* counter;            // sparse: next stream to take (zeroed before the launch)
 };
 
 template <class S> __device__ __forceinline__ float sample_to_f32(S v) { return (float)v; }
@@ -435,14 +436,34 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
     // detection rule reads next to a candidate stays exact: the block after a block that may still turn out hot is
     // always computed, a computed block also writes the sample before its first one (the circular convolution of a
     // 2048-tap partition is valid from sample 2047 on) when its predecessor was skipped, and the first and last
-    // block of every CTA's range are always computed.  The detections are identical to the full computation's;
+    // block of a stream are always computed.  The detections are identical to the full computation's;
     // how many blocks are skipped depends on the data (chirp peak against the l1 norm of the data blocks' spectra:
     // ~93 % at 8 dB and above on the C3 framing, none below ~5 dB).
     float runmax = __int_as_float(0xff800000);
     bool prev_hotish = true, prev_skipped = false;
     __shared__ float wl1[NT / 32];
+    // Work distribution.  Dense: one contiguous, equally sized range of blocks per CTA (uniform cost).  Sparse: the
+    // cost of a block depends on the data, and the skip rule needs the stream's chirp peak, which lies at the stream's
+    // beginning -- so CTAs take WHOLE streams from a global counter (dynamic: a CTA whose streams cannot skip much
+    // simply takes fewer of them).
+    __shared__ long long s_unit;
 #pragma unroll 1
-    for (int64_t c = c_begin; c < c_end; ++c) {
+    for (int64_t unit = 0;; ++unit) {
+    int64_t c_lo = c_begin, c_hi = c_end;
+    if (a.sparse) {
+        __syncthreads();
+        if (tid == 0) s_unit = (long long)atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int64_t sidx = s_unit;
+        if (sidx >= a.n_streams) break;
+        c_lo = sidx * a.nblk_out;
+        c_hi = c_lo + a.nblk_out;
+    } else if (unit > 0) {
+        break;
+    }
+    cur_stream = -1;
+#pragma unroll 1
+    for (int64_t c = c_lo; c < c_hi; ++c) {
         const int64_t stream = c / a.nblk_out;
         const int b = (int)(c - stream * a.nblk_out);
         pk64 xre[Q], xim[Q];
@@ -478,7 +499,7 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
             dcny = make_float2(0.f, 0.f);
         }
         // the next block's samples fly while this one is multiplied and transformed back
-        if (c + 1 < c_end && (c + 1) / a.nblk_out == stream) {
+        if (c + 1 < c_hi && (c + 1) / a.nblk_out == stream) {
 #pragma unroll
             for (int i = 0; i < R / 2; ++i) x[i] = keep[i];
             load_block(x, stream, b + 1, std::true_type{});
@@ -531,12 +552,14 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
         float* Prow = a.P + stream * a.p_stride;
         const int64_t n0 = (int64_t)b * kB - kB;
         if (a.sparse) {
-            // l1 norm of the block's spectrum (|Y| <= |re| + |im|; bins 1..N/2-1 count twice: Hermitian halves)
+            // l1 norm of the block's spectrum, sum_k |Y[k]| (bins 1..N/2-1 count twice: Hermitian halves).  |Y| by
+            // rsqrt (relative error 2^-22, covered by the 1.001 slack of the comparison below)
             float l1 = 0.f;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                const float2 yre = pk_unpack(arp[q]), yim = pk_unpack(ai[q]);
-                const float lane0 = fabsf(yre.x) + fabsf(yim.x), lane1 = fabsf(yre.y) + fabsf(yim.y);
+                const pk64 m2 = p_fma(arp[q], arp[q], p_mul(ai[q], ai[q]));   // |Y|^2 of both bins of the pair
+                const float2 e = pk_unpack(m2);
+                const float lane0 = e.x * rsqrtf(fmaxf(e.x, 1e-37f)), lane1 = e.y * rsqrtf(fmaxf(e.y, 1e-37f));
                 l1 += (q == 0 && tid == 0) ? lane0 : lane0 + lane1;          // k = M/2 sits in both lanes of its slot
             }
             l1 *= 2.f;
@@ -548,7 +571,7 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
             float bound = wl1[0];
 #pragma unroll
             for (int w = 1; w < NT / 32; ++w) bound += wl1[w];
-            const bool forced = c == c_begin || c + 1 == c_end || prev_hotish;
+            const bool forced = c == c_lo || c + 1 == c_hi || prev_hotish;
             if (!forced && bound * 1.001f < a.thresh * runmax) {             // (runmax = -inf or <= 0: never true)
                 if (tid == 0 && a.blockmax) a.blockmax[stream * a.nblk_out + b] = __int_as_float(0xff800000);
                 prev_hotish = false;
@@ -616,6 +639,7 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
             prev_skipped = false;
         }
     }
+    }   // units
 }
 
 // chirp-partition spectra [parts][M] (element 0 packs (H[0], H[M])) -> the fused kernel's pair layout, scaled
@@ -990,7 +1014,8 @@ static int launch_fused(const gf3_plan* plan, const FusedArgs& a, cudaStream_t s
 
 // chirp_method's convolution for a batch of streams (OFDM.py:357-358); blockmax is optional
 static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_stride, int64_t n_streams, int64_t T,
-                        float* P, int64_t p_stride, float* pmax, float* blockmax, void* work, cudaStream_t st, bool sparse = false) {
+                        float* P, int64_t p_stride, float* pmax, float* blockmax, void* work, cudaStream_t st, bool sparse = false,
+                        int* counter = nullptr) {
     const XcorrGeom g = xcorr_geom(plan, n_streams, T);
     GF3_REQUIRE(p_stride >= g.out_len, "xcorr: p_stride %lld < T + chirp_len - 1 = %lld", (long long)p_stride, (long long)g.out_len);
     GF3_REQUIRE(fmt == GF3_SAMPLE_F32 || fmt == GF3_SAMPLE_I16 || fmt == GF3_SAMPLE_U8, "xcorr: unknown sample format %d", fmt);
@@ -999,7 +1024,11 @@ static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_
         a.r = r; a.Hs = reinterpret_cast<const float4*>(plan->d_chirp_pairs); a.Hdc = plan->d_chirp_dc; a.tw = plan->d_sync_tw;
         a.P = P; a.pmax = pmax; a.blockmax = blockmax; a.r_stride = r_stride; a.p_stride = p_stride; a.T = T; a.out_len = g.out_len;
         a.n_streams = n_streams; a.nblk_in = g.nblk_in; a.nblk_out = g.nblk_out; a.parts = plan->sync_parts;
-        a.sparse = (sparse && blockmax) ? 1 : 0; a.thresh = plan->p.thresh;
+        a.sparse = (sparse && blockmax && counter) ? 1 : 0; a.thresh = plan->p.thresh; a.counter = counter;
+        if (a.sparse) {
+            fill_f32_kernel<<<1, 32, 0, st>>>(reinterpret_cast<float*>(counter), 1, 0.0f);      // int 0
+            GF3_LAUNCH_CHECK();
+        }
         if (fmt == GF3_SAMPLE_F32) return launch_fused<float>(plan, a, st);
         if (fmt == GF3_SAMPLE_I16) return launch_fused<int16_t>(plan, a, st);
         return launch_fused<uint8_t>(plan, a, st);
@@ -1085,7 +1114,7 @@ extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride,
 }
 
 // layout of gf3_sync_streams' work buffer: [block maxima | matched-filter scratch | candidate bit mask]
-static size_t sync_off_blockmax(const XcorrGeom& g, int64_t n_streams) { return (((size_t)n_streams * g.nblk_out * sizeof(float)) + 255) & ~(size_t)255; }
+static size_t sync_off_blockmax(const XcorrGeom& g, int64_t n_streams) { return ((((size_t)n_streams * g.nblk_out * sizeof(float)) + 255) & ~(size_t)255) + 256; }   // + the stream counter
 
 extern "C" size_t gf3_sync_work_bytes(const gf3_plan* plan, int64_t n_streams, int64_t T) {
     if (!plan || n_streams <= 0 || T <= 0) return 0;
@@ -1109,7 +1138,8 @@ static int sync_common(const gf3_plan* plan, const void* r, int32_t sample_forma
     void* pwork = reinterpret_cast<char*>(xwork) + ((gf3_xcorr_work_bytes(plan, n_streams, T) + 255) & ~(size_t)255);
     // detection only: blocks of P that provably hold no candidate are not computed (the detections are the same)
     const bool sparse = detect_only && fused && single_pass_picker(plan, n_streams, true) && !getenv("GF3_SYNC_DENSE");
-    int rc = xcorr_common(plan, r, sample_format, r_stride, n_streams, T, P, p_stride, pmax, blockmax, xwork, st, sparse);
+    int* counter = reinterpret_cast<int*>(w + sync_off_blockmax(g, n_streams) - 256);
+    int rc = xcorr_common(plan, r, sample_format, r_stride, n_streams, T, P, p_stride, pmax, blockmax, xwork, st, sparse, counter);
     if (rc) return rc;
     return peak_pick_common(plan, P, p_stride, n_streams, T, pmax, blockmax, g.nblk_out, peaks, max_peaks, count, pwork, st, sparse);
 }

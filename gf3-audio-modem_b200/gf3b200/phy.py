@@ -216,6 +216,7 @@ class Phy:
         work = torch.empty((max(16, int(self.lib.gf3_sync_work_bytes(self._plan, B, T))),), dtype=torch.uint8, device=self.device)
         check(self._call("gf3_sync_detect" if detect_only else "gf3_sync_streams", self._plan, _ptr(r), self._FMT[r.dtype], rs, B, T, _ptr(P), pstride, _ptr(pmax),
                          _ptr(peaks), max_peaks, _ptr(count), _ptr(work), _STREAM))
+        self._last_sync_work = work            # (diagnostics: the first B * ceil(plen / 2048) floats are the block maxima)
         return P[:, :plen], pmax, peaks, count
 
     def peaks_to_offsets(self, peaks, count, r_stride, T, pk_expected):
