@@ -279,6 +279,9 @@ template <> struct Dft<64> {
 #ifndef GF3_FFT_PAIRED
 #define GF3_FFT_PAIRED 1
 #endif
+#ifndef GF3_TW_AB
+#define GF3_TW_AB 0      // measured slower on C3 (1.23 vs 0.98 ms: twice the twiddle bytes through shared memory, spills at 128 registers)
+#endif
 template <int LOGN_, int R_, int NPASS_, int R0_, int R1_, int R2_>
 struct FftPlanT {
     static constexpr int LOGN = LOGN_, N = 1 << LOGN_, M = N / 2, R = R_, T = M / R_;
@@ -298,7 +301,10 @@ struct FftPlanT {
     // table keeps (rad-1)*R0 entries (N = 4096: 240 instead of 1920 -- 13 KB of shared memory per CTA);
     // lanes t and t + R0 read the same address (broadcast), a warp touches one 128-byte line per load.
     static constexpr bool DEDUP1 = !(GF3_FFT_PAIRED && (LOGN_ == 10)) && (T > R0_) && (T % R0_ == 0);
-    static constexpr int TW1 = DEDUP1 ? (R1_ - 1) * R0_ : (R_ / R1_) * (R1_ - 1) * T;
+    // TWAB (paired plan): every twiddle is stored as the two operand pairs of a packed complex multiply, A = (wr, wi) and
+    // B = (-wi, wr), so x * w is FMUL2 + FFMA2 instead of 2 FMUL + 2 FFMA (twice the table, half the multiply instructions)
+    static constexpr bool TWAB = GF3_TW_AB && PAIRED;
+    static constexpr int TW1 = DEDUP1 ? (R1_ - 1) * R0_ : (TWAB ? 2 : 1) * (R_ / R1_) * (R1_ - 1) * T;
     static constexpr int TW2 = NPASS_ > 2 ? (R_ / R2_) * (R2_ - 1) * T : 0;
     __host__ __device__ static constexpr int tw_off(int p) { return p <= 1 ? 0 : TW1; }
     static constexpr int TW_TOTAL = TW1 + TW2;
@@ -377,7 +383,16 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
             });
         });
         }
-        if constexpr (P::PAIRED) {
+        if constexpr (P::PAIRED && P::TWAB) {
+            // (A, B) pairs of the two adjacent columns: two 128-bit loads, two packed instructions per multiply
+            // (layout [i][column parity][t]: the lanes of a load read consecutive 16-byte entries)
+            const float4* twp = reinterpret_cast<const float4*>(tw + P::tw_off(PASS)) + t;
+            static_for<RAD - 1>([&](auto ic) {
+                constexpr int i = decltype(ic)::value + 1;
+                x[i] = cmul_ab(x[i], twp[(i - 1) * 2 * P::T]);
+                x[RAD + i] = cmul_ab(x[RAD + i], twp[(i - 1) * 2 * P::T + P::T]);
+            });
+        } else if constexpr (P::PAIRED) {
             // the twiddles of the two adjacent columns sit side by side: one 128-bit load for both
             const float4* twp = reinterpret_cast<const float4*>(tw + P::tw_off(PASS) + 2 * t);
             static_for<RAD - 1>([&](auto ic) {
@@ -498,6 +513,12 @@ inline void fill_twiddles(float2* out) {
                 for (int t = 0; t < P::T; ++t) {
                     const int j = P::PAIRED ? 2 * t + q : t + q * P::T;
                     const double ang = -2.0 * 3.14159265358979323846 * (double)((j % NS) * i) / (double)(NS * RAD);
+                    if (P::TWAB) {            // float4 (wr, wi, -wi, wr) at [(i-1)][q][t]
+                        const int idx4 = ((i - 1) * 2 + q) * P::T + t;
+                        o[2 * idx4] = make_float2((float)cos(ang), (float)sin(ang));
+                        o[2 * idx4 + 1] = make_float2(-(float)sin(ang), (float)cos(ang));
+                        continue;
+                    }
                     const int idx = P::PAIRED ? (i - 1) * 2 * P::T + 2 * t + q : (q * (RAD - 1) + (i - 1)) * P::T + t;
                     o[idx] = make_float2((float)cos(ang), (float)sin(ang));
                 }
