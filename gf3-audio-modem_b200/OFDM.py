@@ -372,6 +372,14 @@ class transmitter(CamG):
             return time_data
         return np.hstack([time_data[:, -self.cp_length:], time_data])
 
+    def build_schmidlcox(self):
+        """OFDM.py:230-238 (host-side formatting; like the reference it only works for geometries whose known sequence
+        reshapes into whole symbols)."""
+        symbols = self.map(self.SP(self.known_sequence))
+        p = np.zeros(self.K, dtype=complex)
+        p[::2] = symbols[0, :self.K // 2]
+        return p.reshape(-1, self.K)
+
     def send_to_stream(self, time_data, sync):
         """OFDM.py:242-276: frame time-domain symbols (CP included) into packets with the known
         symbols and the caller's sync waveform; the frame is assembled on the device."""
@@ -497,6 +505,20 @@ class receiver(transmitter):
         zeros = np.zeros(nz, dtype=bool)
         zeros[peaks] = True
         return zeros
+
+    def schmidlcox_method(self, r):
+        """OFDM.py:376-387: Schmidl & Cox timing metric over the first 5 s (a prefix-sum kernel on the device) ->
+        argmax |P| + N - 1.  Unused by receive() in the reference too ("no longer works with packets")."""
+        import torch
+        phy = self.phy
+        r = np.asarray(r)
+        dt = r.dtype if r.dtype in (np.uint8, np.int16) else np.float32
+        d_r = torch.from_numpy(np.ascontiguousarray(r, dtype=dt).reshape(1, -1)).to(phy.device)
+        search = 5 * int(self.fs)
+        if d_r.shape[1] < search - 1 + 2 * self.L:
+            raise IndexError("index %d is out of bounds for axis 0 with size %d" % (search - 2 + 2 * self.L, d_r.shape[1]))
+        idx, _ = phy.schmidlcox(d_r, search)
+        return int(idx[0].item()) + self.ofdm_symbol_size - 1
 
     def get_symbols(self, r, zeros):
         """OFDM.py:391-403 (index bookkeeping on the host)."""

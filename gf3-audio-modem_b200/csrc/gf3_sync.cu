@@ -866,6 +866,92 @@ __global__ void peaks_to_offsets_kernel(const int64_t* __restrict__ peaks, const
     if (j == 0 && ok) ok[s] = good ? 1 : 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Schmidl & Cox timing metric (OFDM.py:376-387; unused by receive() since the chirp became the standard, kept as a
+// public method).  The reference runs the recursion  P[d+1] = P[d] + r[d+L] r[d+2L] - r[d] r[d+L]  over the first
+// `search` samples in a Python loop and returns argmax |P| + N - 1.  The recursion is a prefix sum: one CTA per
+// stream scans tiles of 2048 terms in double precision (thread-local scan of 8 terms, warp shuffle scan, carry
+// across tiles) and keeps the first index of the largest |P|.
+// ------------------------------------------------------------------------------------------
+struct ScArgs {
+    const void* r;
+    int64_t r_stride, search;     // P has `search` entries: P[0] = 0, P[d+1] from d = 0 .. search-2
+    int64_t* index;               // [n_streams] argmax |P| (first occurrence), WITHOUT the + N - 1
+    double* value;                // [n_streams] |P| there (may be null)
+    int L;
+};
+
+template <class S>
+__global__ void __launch_bounds__(256) schmidlcox_kernel(const ScArgs a) {
+    constexpr int NT = 256, PER = 8, TILE = NT * PER;
+    __shared__ double wsum[NT / 32];
+    __shared__ double s_best[NT / 32];
+    __shared__ long long s_idx[NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const S* r = reinterpret_cast<const S*>(a.r) + (int64_t)blockIdx.x * a.r_stride;
+    const int64_t nterms = a.search - 1;
+    double carry = 0.0, best = 0.0;                       // P[0] = 0 at index 0
+    long long best_i = 0;
+    for (int64_t t0 = 0; t0 < nterms; t0 += TILE) {
+        const int64_t d0 = t0 + (int64_t)tid * PER;
+        double v[PER];
+        double run = 0.0;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int64_t d = d0 + e;
+            double term = 0.0;
+            if (d < nterms) {
+                const double x0 = (double)r[d], x1 = (double)r[d + a.L], x2 = (double)r[d + 2 * (int64_t)a.L];
+                term = x1 * x2 - x0 * x1;
+            }
+            run += term;
+            v[e] = run;                                   // inclusive scan inside the thread
+        }
+        double incl = run;                                // warp scan of the thread totals
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        double before = carry + (incl - run);
+        double tile_total = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) {
+            if (w < warp) before += wsum[w];
+            tile_total += wsum[w];
+        }
+        // P[d + 1] = before + v[e]: candidates at indices d0 + e + 1 (ascending inside the thread: ">" keeps the first)
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int64_t d = d0 + e;
+            if (d < nterms) {
+                const double m = fabs(before + v[e]);
+                if (m > best) { best = m; best_i = d + 1; }
+            }
+        }
+        carry += tile_total;
+        __syncthreads();
+    }
+    // first index of the maximum over the CTA
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    if (lane == 0) { s_best[warp] = best; s_idx[warp] = best_i; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NT / 32; ++w)
+            if (s_best[w] > best || (s_best[w] == best && s_idx[w] < best_i)) { best = s_best[w]; best_i = s_idx[w]; }
+        a.index[blockIdx.x] = best_i;
+        if (a.value) a.value[blockIdx.x] = best;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static int run_fwd(const gf3_plan* plan, const void* r, int fmt, int64_t r_stride, int64_t n_streams, int64_t T, int nblk, int reverse,
                    int in_off, int valid_len, float2* spec, const float2* tw, float* pmax, cudaStream_t st) {
@@ -1185,6 +1271,26 @@ extern "C" int gf3_peaks_to_offsets(const gf3_plan* plan, const int64_t* peaks, 
     const int64_t n = n_streams * pk_expected;
     peaks_to_offsets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         peaks, count, n_streams, max_peaks, r_stride, T, pk_expected, pkt_samples, pkt_offset, ok);
+    GF3_LAUNCH_CHECK();
+    return GF3_OK;
+}
+
+extern "C" int gf3_schmidlcox(const gf3_plan* plan, const void* r, int32_t sample_format, int64_t r_stride, int64_t n_streams,
+                              int64_t T, int64_t search, int64_t* index, double* value, void* stream) {
+    GF3_REQUIRE(plan && r && index, "schmidlcox: null argument");
+    GF3_REQUIRE(n_streams >= 0 && n_streams <= 0x7fffffff && search >= 1, "schmidlcox: bad sizes");
+    const int L = plan->p.N / 2;                               // CamG.L = K + 1 (OFDM.py:54)
+    // the recursion reads r[d + 2L] for d <= search - 2: the reference raises IndexError on a shorter recording
+    GF3_REQUIRE(T >= search - 1 + 2 * (int64_t)L, "schmidlcox: %lld samples, %lld needed (search - 1 + 2L)", (long long)T,
+                (long long)(search - 1 + 2 * (int64_t)L));
+    if (n_streams == 0) return GF3_OK;
+    ScArgs a;
+    a.r = r; a.r_stride = r_stride; a.search = search; a.index = index; a.value = value; a.L = L;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (sample_format == GF3_SAMPLE_F32) schmidlcox_kernel<float><<<(unsigned)n_streams, 256, 0, st>>>(a);
+    else if (sample_format == GF3_SAMPLE_I16) schmidlcox_kernel<int16_t><<<(unsigned)n_streams, 256, 0, st>>>(a);
+    else if (sample_format == GF3_SAMPLE_U8) schmidlcox_kernel<uint8_t><<<(unsigned)n_streams, 256, 0, st>>>(a);
+    else { gf3::set_error("schmidlcox: unknown sample format %d", sample_format); return GF3_ERR_INVALID; }
     GF3_LAUNCH_CHECK();
     return GF3_OK;
 }

@@ -67,6 +67,7 @@ SIGNATURES = {
     "gf3_sync_work_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
     "gf3_sync_streams": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "gf3_sync_detect": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "gf3_schmidlcox": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "gf3_peaks_to_offsets": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "gf3_ber_count": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "gf3_pcm_to_f32": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_void_p]),

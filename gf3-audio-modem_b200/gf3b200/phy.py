@@ -219,6 +219,17 @@ class Phy:
         self._last_sync_work = work            # (diagnostics: the first B * ceil(plen / 2048) floats are the block maxima)
         return P[:, :plen], pmax, peaks, count
 
+    def schmidlcox(self, r, search):
+        """Schmidl & Cox timing metric of OFDM.py:376-387 for a batch of streams r [B, T]: -> (index int64 [B] = first
+        argmax |P| over the first `search` samples, value float64 [B]); the reference returns index + N - 1."""
+        assert r.is_cuda and r.dim() == 2 and r.stride(1) == 1 and r.dtype in self._FMT
+        B, T = r.shape
+        idx = torch.empty((B,), dtype=torch.int64, device=self.device)
+        val = torch.empty((B,), dtype=torch.float64, device=self.device)
+        check(self._call("gf3_schmidlcox", self._plan, _ptr(r), self._FMT[r.dtype], r.stride(0) if B > 1 else T, B, T, int(search),
+                         _ptr(idx), _ptr(val), _STREAM))
+        return idx, val
+
     def peaks_to_offsets(self, peaks, count, r_stride, T, pk_expected):
         """get_symbols' bookkeeping on the device (OFDM.py:393-397): detections of a batch of streams ->
         (pkt_offset int64 [B * pk_expected] into the flat sample array, ok uint8 [B])."""

@@ -195,6 +195,13 @@ GF3_API int gf3_sync_detect(const gf3_plan* plan, const void* r, int32_t sample_
                     int64_t T, float* P_scratch, int64_t p_stride, float* pmax, int64_t* peaks, int32_t max_peaks,
                     int32_t* count, void* work, void* stream);
 
+/* receiver.schmidlcox_method (OFDM.py:376-387; unused by receive() since the chirp became the standard, still a public
+ * method): the timing metric P[d+1] = P[d] + r[d+L] r[d+2L] - r[d] r[d+L], L = N/2, over the first `search` samples as a
+ * double-precision prefix sum; index[s] = first argmax |P| (the reference returns index + N - 1), value[s] = |P| there
+ * (or NULL).  Needs T >= search - 1 + 2L samples per stream (the reference raises IndexError otherwise). */
+GF3_API int gf3_schmidlcox(const gf3_plan* plan, const void* r, int32_t sample_format, int64_t r_stride, int64_t n_streams,
+                   int64_t T, int64_t search, int64_t* index, double* value, void* stream);
+
 /* get_symbols' index bookkeeping (OFDM.py:393-397) for a batch of streams, on the device:
  * zero_indicies = where(zeros) + 2 with the last detection (the terminating chirp) dropped, turned
  * into packet offsets for gf3_rx_receive: pkt_offset[s*pk_expected + j] = s*r_stride + peaks[s][j] + 2.

@@ -23,7 +23,7 @@ import numpy as np
 __all__ = [
     "Params", "MODES", "load_known_sequence", "sync_chirp", "qpsk_map", "known_symbols",
     "encode", "decode", "random_qpsk", "build_ofdm_symbols", "add_cp", "send_to_stream",
-    "transmit", "matched_filter", "chirp_method", "get_symbols", "rx_fft", "get_data",
+    "transmit", "matched_filter", "chirp_method", "schmidlcox_method", "get_symbols", "rx_fft", "get_data",
     "equalise", "demap", "receive", "receive_symbols", "known_channel_decode",
     "load_file_bits", "save_file_bytes",
 ]
@@ -252,6 +252,19 @@ def chirp_method(p, r, P=None):
         out[idx] = True
         next_free = idx + Lc + 1
     return out
+
+
+def schmidlcox_method(p, r):
+    """OFDM.py:376-387 -- Schmidl & Cox timing metric over the first 5 s: the recursion
+    P[d+1] = P[d] + r[d+L] r[d+2L] - r[d] r[d+L] (L = K + 1 = N/2, OFDM.py:54) is a cumulative sum (np.cumsum adds in
+    the same sequential order as the reference's loop); returns argmax |P| + N - 1 (first occurrence)."""
+    r = np.asarray(r, dtype=np.float64)
+    n = 5 * p.fs
+    L = p.N // 2
+    d = np.arange(n - 1)
+    terms = r[d + L] * r[d + 2 * L] - r[d] * r[d + L]
+    P = np.concatenate([[0.0], np.cumsum(terms)])
+    return int(np.where(np.abs(P) == np.amax(np.abs(P)))[0][0]) + p.N - 1
 
 
 def get_symbols(p, r, zeros):

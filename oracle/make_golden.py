@@ -11,6 +11,7 @@ Fixtures (all outputs are the reference's own, produced under oracle/ref_shim.py
                     (attribute-patched N / CP / bins; int16-quantised channel output as input)
   kat3_weekend.npz  Weekend-Challenge artefacts: channel taps + the decoded output file
   sync_quirk.npz    chirp_method end-of-signal wipe-out quirk (OFDM.py:366-370)
+  sync_schmidlcox.npz  receiver.schmidlcox_method (OFDM.py:376-387) on seeded signals
   kat4_gr5ch2.npz   BASELINE.json configs[1]: the reference transmits
                     input_Files/gr5ch2.wav (mode A2, XOR, seeded), Handouts/gr5channel.csv FIR + seeded
                     AWGN + int16 quantisation, reference receive(): 29 packets / 28.2 M samples
@@ -251,6 +252,28 @@ def kat4():
                                                          nerr, len(bits_in), len(near5), len(near4), t_tx, t_rx))
 
 
+def sc_signal(seed=17, n=5 * 48000 + 2 * 2048 + 100):
+    """Noise with one repeated 2048-sample half-symbol (what the metric locks on), regenerated from the seed in the tests."""
+    rng = np.random.default_rng(seed)
+    r = rng.normal(0, 0.05, n)
+    half = rng.normal(0, 0.3, 2048)
+    r[91234:91234 + 2048] += half
+    r[91234 + 2048:91234 + 4096] += half
+    return r
+
+
+def schmidlcox():
+    """receiver.schmidlcox_method (OFDM.py:376-387) of the unmodified reference on a seeded signal."""
+    rx = ref_shim.make("receiver", "A2", "XOR")
+    out = {}
+    for seed in (17, 18):
+        r = sc_signal(seed)
+        out["index_seed%d" % seed] = int(rx.schmidlcox_method(r))
+        out["index_i16_seed%d" % seed] = int(rx.schmidlcox_method(np.round(r * 8000).astype(np.int16).astype(np.float64)))
+    np.savez_compressed(os.path.join(OUT, "sync_schmidlcox.npz"), **out)
+    print("schmidlcox:", out)
+
+
 def notebook_cells():
     """Code cells of the notebooks written against the OLD API (older OFDM.py revisions, code not in the repository), as
     the reference ships them: tests/test_gpu_legacy_api.py executes them unmodified against the drop-in."""
@@ -287,7 +310,7 @@ def sync_quirk():
 if __name__ == "__main__":
     assert ref_shim.available(), "reference not found"
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["kat1", "stage", "kat3", "quirk", "kat4", "cells"]
+    which = sys.argv[1:] or ["kat1", "stage", "kat3", "quirk", "kat4", "cells", "sc"]
     if "kat1" in which:
         kat1()
     if "stage" in which:
@@ -301,5 +324,7 @@ if __name__ == "__main__":
         kat4()
     if "cells" in which:
         notebook_cells()
+    if "sc" in which:
+        schmidlcox()
     for f in sorted(os.listdir(OUT)):
         print("%-24s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

@@ -577,3 +577,29 @@ def test_fused_receive_is_deterministic_and_equals_two_launches(known_sequence):
     cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
     phy.ber_count(one.contiguous(), two.contiguous(), n * phy.bits_stride * 8, cnt)
     assert int(cnt[0]) <= n // 50, int(cnt[0])
+
+
+def test_schmidlcox_prefix_sum_kernel(known_sequence, capsys):
+    """OFDM.py:376-387 on the device (gf3_schmidlcox): the reference's indices on the golden signals (float32, and int16
+    read natively), a batch against the oracle, and the drop-in method; a recording that is too short raises IndexError."""
+    torch = _torch()
+    import gf3b200
+    import OFDM
+    from oracle.make_golden import sc_signal
+    g = load_golden("sync_schmidlcox.npz")
+    p = orc.Params.from_mode("A2", known_sequence=known_sequence)
+    rx = OFDM.receiver(mode="A2", encoding="XOR")
+    for seed in (17, 18):
+        r = sc_signal(seed)
+        assert rx.schmidlcox_method(r) == int(g["index_seed%d" % seed])
+        assert rx.schmidlcox_method(np.round(r * 8000).astype(np.int16)) == int(g["index_i16_seed%d" % seed])
+    phy = gf3b200.Phy(known_sequence=known_sequence)
+    rng = np.random.default_rng(5)
+    batch = np.stack([sc_signal(100 + i) * (1 + 0.1 * i) for i in range(6)])
+    batch[3] = rng.normal(0, 1.0, batch.shape[1])                       # noise only: argmax anywhere
+    q = np.round(batch * 4000).astype(np.int16)
+    idx, val = phy.schmidlcox(torch.from_numpy(q).cuda(), 5 * 48000)
+    ref = [orc.schmidlcox_method(p, q[i].astype(np.float64)) - p.N + 1 for i in range(6)]
+    assert idx.cpu().tolist() == ref
+    with pytest.raises(IndexError):
+        rx.schmidlcox_method(np.zeros(5 * 48000))

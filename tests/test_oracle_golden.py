@@ -147,3 +147,15 @@ def test_kat4_gr5ch2_long_recording(known_sequence):
     assert int(np.sum(out["bits"][: len(bits_in)] != bits_in)) == int(g["n_bit_errors"]) == 111558
     name, size, _ = orc.save_file_bytes(out["bits"])
     assert name == str(g["file_name"]) == "gr5ch2.wav" and int(size) == len(g["payload"])
+
+
+def test_schmidlcox_metric(known_sequence):
+    """receiver.schmidlcox_method (OFDM.py:376-387): the oracle's cumulative sum gives the reference's indices."""
+    from oracle.make_golden import sc_signal
+    g = load_golden("sync_schmidlcox.npz")
+    p = orc.Params.from_mode("A2", known_sequence=known_sequence)
+    for seed in (17, 18):
+        r = sc_signal(seed)
+        assert orc.schmidlcox_method(p, r) == int(g["index_seed%d" % seed])
+        assert orc.schmidlcox_method(p, np.round(r * 8000).astype(np.int16).astype(np.float64)) == int(g["index_i16_seed%d" % seed])
+    assert abs(int(g["index_seed17"]) - (91234 + 4096 - 1)) < 64          # locks on the repeated half-symbol
