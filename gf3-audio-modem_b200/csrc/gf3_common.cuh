@@ -49,6 +49,14 @@ static inline int ilog2(int v) {
 
 }  // namespace gf3
 
+// Plan of the N = 4096 data-symbol kernel: 0 = 16 x 16 x 8 on 128 threads per symbol, 1 = 32 x 8 x 8 on 64 threads
+#ifndef GF3_RX12_ALT
+#define GF3_RX12_ALT 0
+#endif
+#ifndef GF3_FUSE12
+#define GF3_FUSE12 0           // with the 32 x 8 x 8 plan both pilot blocks fit the spectrum buffer: fuse the estimate at N = 4096 too?
+#endif
+
 // The opaque handle of include/gf3_b200.h.
 struct gf3_plan {
     gf3_params p;
@@ -56,6 +64,7 @@ struct gf3_plan {
     int device;
     int sm_count;
     float2* d_tw;        // FFT twiddle table of the N-point symbol plan
+    float2* d_tw_demod;  // twiddle table of the data-symbol kernel's plan (== d_tw unless that kernel uses another factorisation)
     float2* d_ones;      // K ones (unit channel for gf3_rx_spectrum)
     // sync (overlap-save matched filter): block FFT size NB real samples, hop HB
     int sync_logN;       // log2 of the overlap-save FFT length

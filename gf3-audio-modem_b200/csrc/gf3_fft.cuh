@@ -321,6 +321,9 @@ GF3_PLAN(10, 32, 2, 32, 16, 1)   // N=1024  M=512   T=16
 GF3_PLAN(11, 32, 2, 32, 32, 1)   // N=2048  M=1024  T=32
 GF3_PLAN(12, 16, 3, 16, 16, 8)   // N=4096  M=2048  T=128
 #undef GF3_PLAN
+// N = 4096 as 32 x 8 x 8 on 64 threads (two warps per symbol, 32 points per thread): the data-symbol kernel's alternative
+// to the 16 x 16 x 8 plan above (which the matched filter and the estimate kernel keep)
+struct FftPlan12B : FftPlanT<12, 32, 3, 32, 8, 8> {};
 
 template <class P>
 __device__ __forceinline__ int zpad(int i) { return i + (i >> P::LOGPAD); }

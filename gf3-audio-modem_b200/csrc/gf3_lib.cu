@@ -35,6 +35,7 @@ static bool host_twiddles(int logN, std::vector<float2>& v) {
         case 10: fill_tw_vec<FftPlan<10>>(v); return true;
         case 11: fill_tw_vec<FftPlan<11>>(v); return true;
         case 12: fill_tw_vec<FftPlan<12>>(v); return true;
+        case 112: fill_tw_vec<FftPlan12B>(v); return true;        // N = 4096 as 32 x 8 x 8 (data-symbol kernel)
         default: return false;
     }
 }
@@ -115,6 +116,10 @@ extern "C" int gf3_plan_create(const gf3_params* p, gf3_plan** out) {
         GF3_CHECK_CUDA(cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device));
         int r = upload_twiddles(plan->logN, &plan->d_tw);
         if (r) return r;
+        plan->d_tw_demod = plan->d_tw;
+#if GF3_RX12_ALT
+        if (plan->logN == 12) { r = upload_twiddles(112, &plan->d_tw_demod); if (r) return r; }
+#endif
         const int K = p->N / 2 - 1;
         std::vector<float2> ones(K, make_float2(1.f, 0.f));
         GF3_CHECK_CUDA(cudaMalloc(&plan->d_ones, K * sizeof(float2)));
@@ -130,6 +135,7 @@ extern "C" int gf3_plan_create(const gf3_params* p, gf3_plan** out) {
 extern "C" int gf3_plan_destroy(gf3_plan* plan) {
     if (!plan) return GF3_OK;
     sync_plan_free(plan);
+    if (plan->d_tw_demod && plan->d_tw_demod != plan->d_tw) cudaFree(plan->d_tw_demod);
     if (plan->d_tw) cudaFree(plan->d_tw);
     if (plan->d_ones) cudaFree(plan->d_ones);
     delete plan;

@@ -107,11 +107,13 @@ extern "C" int gf3_rx_demod(const gf3_plan* plan, const float* samples, const in
                         bits_stride, eq, false, -1, -1, stream);
 }
 
-template <class P>
+template <class P0>
 static int receive_is_fused(const gf3_plan* plan) {
-    using C = DemodCfg<P::LOGN>;
+    using C = DemodCfg<P0::LOGN>;
+    using P = typename C::Plan;
     constexpr int NT = (P::T > C::NT) ? P::T : C::NT, SF = NT / P::T;
     if (demod_est_par<P, NT>() < 2 && !GF3_FUSE_SEQUENTIAL) return 0;
+    if (P::LOGN == 12 && !GF3_FUSE12 && !GF3_FUSE_SEQUENTIAL) return 0;
     const gf3_params& p = plan->p;
     const int K = P::M - 1, Nd = p.hi - p.lo;
     const int flo = p.fit_lo < 0 ? 0 : (p.fit_lo > K ? K : p.fit_lo), fhi = p.fit_hi < flo ? flo : (p.fit_hi > K ? K : p.fit_hi);

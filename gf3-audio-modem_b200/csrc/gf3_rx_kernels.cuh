@@ -1014,7 +1014,11 @@ template <int LOGN> struct DemodCfg { using Plan = FftPlan<LOGN>; static constex
 #define GF3_DEMOD12_THREADS 256
 #define GF3_DEMOD12_MINB 2
 #endif
+#if GF3_RX12_ALT
+template <> struct DemodCfg<12> { using Plan = FftPlan12B; static constexpr int NT = GF3_DEMOD12_THREADS, MINB = GF3_DEMOD12_MINB; };
+#else
 template <> struct DemodCfg<12> { using Plan = FftPlan<12>; static constexpr int NT = GF3_DEMOD12_THREADS, MINB = GF3_DEMOD12_MINB; };
+#endif
 // N = 2048: a warp per symbol (32 x 32).  128-thread CTAs would give every thread 4 bin pairs next to
 // its 32 complex samples and spill; 256 threads (8 symbols per batch, 2 pairs per thread) fit:
 // chain 1.118 vs 1.154 ms on 2048 streams.
@@ -1043,7 +1047,7 @@ static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaS
     while ((flush * Nd) % 16 != 0 || flush < 8) flush += SF;
     GF3_REQUIRE(kReseed % flush == 0, "rx_demod: flush period %d does not divide the re-seed block", flush);
     a.flush = flush;
-    a.tw = plan->d_tw;
+    a.tw = plan->d_tw_demod;
     a.n_packets = n_packets;
     a.chunks_per_packet = (a.L + flush - 1) / flush;
     size_t smem = demod_stage_offset<P, NT>() + (((size_t)flush * Nd + 15) & ~(size_t)15) + 16
@@ -1054,6 +1058,7 @@ static int launch_demod(const gf3_plan* plan, RxArgs a, int64_t n_packets, cudaS
     if constexpr (FUSE_EST) {
         // sequential pilot blocks (N = 4096) make the in-kernel estimate slower than a separate launch
         if (demod_est_par<P, NT>() < 2 && !GF3_FUSE_SEQUENTIAL) return GF3_FUSE_UNFIT;
+        if (LOGN == 12 && !GF3_FUSE12 && !GF3_FUSE_SEQUENTIAL) return GF3_FUSE_UNFIT;
         // the fused estimate keeps its fit-window phases (2 x window doubles) in the code staging area
         const int K = P::M - 1;
         const int flo = a.fit_lo < 0 ? 0 : (a.fit_lo > K ? K : a.fit_lo), fhi = a.fit_hi < flo ? flo : (a.fit_hi > K ? K : a.fit_hi);
