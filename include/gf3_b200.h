@@ -190,7 +190,7 @@ GF3_API int gf3_sync_streams(const gf3_plan* plan, const void* r, int32_t sample
  * P[i+1] > thresh * max(P) (OFDM.py:361) and every sample of a 2048-sample block is bounded by the l1 norm of the
  * block's spectrum, so a block whose bound stays below thresh * (the largest sample seen so far in its stream) is not
  * transformed back to the time domain.  peaks / count / pmax are identical to gf3_sync_streams' (tested); how much
- * work is skipped depends on the recording (about 93 % of the inverse transforms on the C3 framing at 8 dB and above). */
+ * work is skipped depends on the recording (88 % of the inverse transforms on the C3 framing at 20 dB, 83 % at 8 dB, none below ~5 dB). */
 GF3_API int gf3_sync_detect(const gf3_plan* plan, const void* r, int32_t sample_format, int64_t r_stride, int64_t n_streams,
                     int64_t T, float* P_scratch, int64_t p_stride, float* pmax, int64_t* peaks, int32_t max_peaks,
                     int32_t* count, void* work, void* stream);
