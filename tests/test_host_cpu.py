@@ -218,3 +218,33 @@ def test_sharded_sweep_gloo_world2(tmp_path):
         out, _ = pr.communicate(timeout=120)
         assert pr.returncode == 0, out
         assert "ok" in out
+
+
+def test_numa_placement_helper_is_harmless_without_a_gpu():
+    """bind_to_gpu_numa (bench.py calls it before pinning host buffers) reports what it found and never raises:
+    no NVML / no device here, so it must come back with an error note and change nothing."""
+    import os
+    from gf3b200.host import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    info = bind_to_gpu_numa(0)
+    assert isinstance(info, dict) and info["gpu"] == 0
+    assert os.sched_getaffinity(0) == before or info.get("cpus_bound")
+
+
+def test_old_api_parameter_objects_without_a_device():
+    """The old-API constructors only build parameter objects (no device needed until a stage method runs)."""
+    import OFDM
+    wc = OFDM.CamG(1024, 32, "QPSK")
+    assert (wc.K, wc.cp_length, wc.bits_per_symbol, len(wc.all_carriers)) == (1024, 32, 1022, 1024)
+    x = np.arange(2 * 1056.0).reshape(2, 1056)
+    assert wc.remove_cp(x).shape == (2, 1024) and np.array_equal(wc.add_cp(wc.remove_cp(x))[:, 32:], x[:, 32:])
+    bits = np.array([0, 0, 1, 0, 1, 1, 0, 1])
+    assert np.allclose(wc.map(wc.SP(bits)) * np.sqrt(2), [1 + 1j, 1 - 1j, -1 - 1j, -1 + 1j])
+    rx = OFDM.receiver(ofdm_symbol_size=4096, cp_length=0, modulation="QPSK", fs=48000, end_sync=False)
+    assert (rx.K, rx.cp_length, rx.data_carriers_per_symbol, rx.old_api, rx.end_sync) == (2047, 0, 2047, True, False)
+    tx = OFDM.transmitter(1024, 128, "QPSK")
+    assert (tx.ofdm_symbol_size, tx.cp_length, tx.data_carriers_per_symbol, tx.bits_per_symbol) == (1024, 128, 511, 1022)
+    with pytest.raises(ValueError):
+        OFDM.CamG(1024, 32, "16QAM")
+    new = OFDM.CamG("A2", "XOR")
+    assert not new.old_api and new.K == 2047
