@@ -324,6 +324,8 @@ GF3_PLAN(12, 16, 3, 16, 16, 8)   // N=4096  M=2048  T=128
 // N = 4096 as 32 x 8 x 8 on 64 threads (two warps per symbol, 32 points per thread): the data-symbol kernel's alternative
 // to the 16 x 16 x 8 plan above (which the matched filter and the estimate kernel keep)
 struct FftPlan12B : FftPlanT<12, 32, 3, 32, 8, 8> {};
+// N = 4096 as 64 x 32 on ONE warp per symbol (64 points per thread, one exchange, __syncwarp only)
+struct FftPlan12C : FftPlanT<12, 64, 2, 64, 32, 1> {};
 
 template <class P>
 __device__ __forceinline__ int zpad(int i) { return i + (i >> P::LOGPAD); }

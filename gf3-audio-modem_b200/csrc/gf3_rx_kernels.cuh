@@ -1014,7 +1014,9 @@ template <int LOGN> struct DemodCfg { using Plan = FftPlan<LOGN>; static constex
 #define GF3_DEMOD12_THREADS 256
 #define GF3_DEMOD12_MINB 2
 #endif
-#if GF3_RX12_ALT
+#if GF3_RX12_ALT == 2
+template <> struct DemodCfg<12> { using Plan = FftPlan12C; static constexpr int NT = 128, MINB = 2; };
+#elif GF3_RX12_ALT
 template <> struct DemodCfg<12> { using Plan = FftPlan12B; static constexpr int NT = GF3_DEMOD12_THREADS, MINB = GF3_DEMOD12_MINB; };
 #else
 template <> struct DemodCfg<12> { using Plan = FftPlan<12>; static constexpr int NT = GF3_DEMOD12_THREADS, MINB = GF3_DEMOD12_MINB; };
