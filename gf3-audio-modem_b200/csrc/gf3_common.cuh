@@ -49,9 +49,11 @@ static inline int ilog2(int v) {
 
 }  // namespace gf3
 
-// Plan of the N = 4096 data-symbol kernel: 0 = 16 x 16 x 8 on 128 threads per symbol, 1 = 32 x 8 x 8 on 64 threads
+// Plan of the N = 4096 data-symbol kernel: 3 = 16 x 16 x 8 on 128 threads per symbol with the last pass on adjacent
+// columns (128-bit exchange; C4 0.604 vs 0.607 ms), 0 = the same with 64-bit accesses throughout (the plan of the
+// matched filter and the estimate kernel), 1 = 32 x 8 x 8 on 64 threads (0.759), 2 = 64 x 32 on one warp (0.749)
 #ifndef GF3_RX12_ALT
-#define GF3_RX12_ALT 0
+#define GF3_RX12_ALT 3
 #endif
 #ifndef GF3_FUSE12
 #define GF3_FUSE12 0           // with the 32 x 8 x 8 plan both pilot blocks fit the spectrum buffer: fuse the estimate at N = 4096 too?

@@ -282,7 +282,7 @@ template <> struct Dft<64> {
 #ifndef GF3_TW_AB
 #define GF3_TW_AB 0      // measured slower on C3 (1.23 vs 0.98 ms: twice the twiddle bytes through shared memory, spills at 128 registers)
 #endif
-template <int LOGN_, int R_, int NPASS_, int R0_, int R1_, int R2_>
+template <int LOGN_, int R_, int NPASS_, int R0_, int R1_, int R2_, bool PAIRLAST_ = false>
 struct FftPlanT {
     static constexpr int LOGN = LOGN_, N = 1 << LOGN_, M = N / 2, R = R_, T = M / R_;
     static constexpr int NPASS = NPASS_;
@@ -304,6 +304,11 @@ struct FftPlanT {
     // TWAB (paired plan): every twiddle is stored as the two operand pairs of a packed complex multiply, A = (wr, wi) and
     // B = (-wi, wr), so x * w is FMUL2 + FFMA2 instead of 2 FMUL + 2 FFMA (twice the table, half the multiply instructions)
     static constexpr bool TWAB = GF3_TW_AB && PAIRED;
+    // PAIRLAST (three-pass plans with two sub-transforms per thread in the last pass): the last pass takes the adjacent
+    // columns j = 2t, 2t+1 as in PAIRED -- its loads, its twiddles and the natural-order stores are 128 bits wide; the
+    // pass before it stores WITHOUT padding (its stores are runs of R0 consecutive points, conflict-free in any layout)
+    static constexpr bool PAIRLAST = PAIRLAST_;
+    static_assert(!PAIRLAST_ || (NPASS_ == 3 && R_ / R2_ == 2 && !PAIRED), "PAIRLAST: three passes, two sub-transforms in the last");
     static constexpr int TW1 = DEDUP1 ? (R1_ - 1) * R0_ : (TWAB ? 2 : 1) * (R_ / R1_) * (R1_ - 1) * T;
     static constexpr int TW2 = NPASS_ > 2 ? (R_ / R2_) * (R2_ - 1) * T : 0;
     __host__ __device__ static constexpr int tw_off(int p) { return p <= 1 ? 0 : TW1; }
@@ -326,6 +331,8 @@ GF3_PLAN(12, 16, 3, 16, 16, 8)   // N=4096  M=2048  T=128
 struct FftPlan12B : FftPlanT<12, 32, 3, 32, 8, 8> {};
 // N = 4096 as 64 x 32 on ONE warp per symbol (64 points per thread, one exchange, __syncwarp only)
 struct FftPlan12C : FftPlanT<12, 64, 2, 64, 32, 1> {};
+// N = 4096 as 16 x 16 x 8 with the last pass on adjacent columns (128-bit loads, twiddles and stores)
+struct FftPlan12P : FftPlanT<12, 16, 3, 16, 16, 8, true> {};
 
 template <class P>
 __device__ __forceinline__ int zpad(int i) { return i + (i >> P::LOGPAD); }
@@ -378,6 +385,14 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
                 x[i] = make_float2(v.x, v.y);
                 x[RAD + i] = make_float2(v.z, v.w);
             });
+        } else if constexpr (P::PAIRLAST && PASS == P::NPASS - 1) {
+            const float4* src = reinterpret_cast<const float4*>(zs + 2 * t);       // unpadded: columns 2t and 2t+1
+            static_for<RAD>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                const float4 v = src[i * (STRIDE / 2)];
+                x[i] = make_float2(v.x, v.y);
+                x[RAD + i] = make_float2(v.z, v.w);
+            });
         } else {
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
@@ -397,7 +412,7 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
                 x[i] = cmul_ab(x[i], twp[(i - 1) * 2 * P::T]);
                 x[RAD + i] = cmul_ab(x[RAD + i], twp[(i - 1) * 2 * P::T + P::T]);
             });
-        } else if constexpr (P::PAIRED) {
+        } else if constexpr (P::PAIRED || (P::PAIRLAST && PASS == P::NPASS - 1)) {
             // the twiddles of the two adjacent columns sit side by side: one 128-bit load for both
             const float4* twp = reinterpret_cast<const float4*>(tw + P::tw_off(PASS) + 2 * t);
             static_for<RAD - 1>([&](auto ic) {
@@ -432,7 +447,7 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
         Dft<RAD>::run(&x[q * RAD]);
     });
     if constexpr (!STORE) {
-        static_assert(PASS == P::NPASS - 1 && !P::PAIRED, "register output is for the last pass of the unpaired plans");
+        static_assert(PASS == P::NPASS - 1 && !P::PAIRED && !P::PAIRLAST, "register output is for the last pass of the unpaired plans");
         return;
     } else
     if constexpr (P::PAIRED && PASS == 0) {
@@ -442,7 +457,7 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
             constexpr int m = decltype(mc)::value;
             dst[m] = make_float4(x[2 * m].x, x[2 * m].y, x[2 * m + 1].x, x[2 * m + 1].y);
         });
-    } else if constexpr (P::PAIRED && NATURAL) {
+    } else if constexpr ((P::PAIRED || P::PAIRLAST) && NATURAL) {
         // bins k = 2t + NS*i and k + 1 (the two sub-transforms of this thread) are neighbours
         float4* dst = reinterpret_cast<float4*>(zs + 2 * t);
         static_for<RAD>([&](auto ic) {
@@ -452,9 +467,9 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
     } else
     static_for<Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
-        const int j = P::PAIRED ? 2 * t + q : t + q * P::T;
+        const int j = (P::PAIRED || (P::PAIRLAST && PASS == P::NPASS - 1)) ? 2 * t + q : t + q * P::T;
         const int base = (j / NS) * (NS * RAD) + (j % NS);
-        if constexpr (NATURAL) {
+        if constexpr (NATURAL || (P::PAIRLAST && PASS == P::NPASS - 2)) {
             float2* dst = zs + base;
             static_for<RAD>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
@@ -513,10 +528,11 @@ inline void fill_twiddles(float2* out) {
                 }
             continue;
         }
+        const bool pair = P::PAIRED || (P::PAIRLAST && pass == P::NPASS - 1);
         for (int q = 0; q < Q; ++q)
             for (int i = 1; i < RAD; ++i)
                 for (int t = 0; t < P::T; ++t) {
-                    const int j = P::PAIRED ? 2 * t + q : t + q * P::T;
+                    const int j = pair ? 2 * t + q : t + q * P::T;
                     const double ang = -2.0 * 3.14159265358979323846 * (double)((j % NS) * i) / (double)(NS * RAD);
                     if (P::TWAB) {            // float4 (wr, wi, -wi, wr) at [(i-1)][q][t]
                         const int idx4 = ((i - 1) * 2 + q) * P::T + t;
@@ -524,7 +540,7 @@ inline void fill_twiddles(float2* out) {
                         o[2 * idx4 + 1] = make_float2(-(float)sin(ang), (float)cos(ang));
                         continue;
                     }
-                    const int idx = P::PAIRED ? (i - 1) * 2 * P::T + 2 * t + q : (q * (RAD - 1) + (i - 1)) * P::T + t;
+                    const int idx = pair ? (i - 1) * 2 * P::T + 2 * t + q : (q * (RAD - 1) + (i - 1)) * P::T + t;
                     o[idx] = make_float2((float)cos(ang), (float)sin(ang));
                 }
     }

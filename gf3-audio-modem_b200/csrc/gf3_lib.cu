@@ -37,6 +37,7 @@ static bool host_twiddles(int logN, std::vector<float2>& v) {
         case 12: fill_tw_vec<FftPlan<12>>(v); return true;
         case 112: fill_tw_vec<FftPlan12B>(v); return true;        // N = 4096 as 32 x 8 x 8 (data-symbol kernel)
         case 212: fill_tw_vec<FftPlan12C>(v); return true;        // N = 4096 as 64 x 32
+        case 312: fill_tw_vec<FftPlan12P>(v); return true;        // N = 4096 as 16 x 16 x 8, last pass paired
         default: return false;
     }
 }
@@ -119,7 +120,7 @@ extern "C" int gf3_plan_create(const gf3_params* p, gf3_plan** out) {
         if (r) return r;
         plan->d_tw_demod = plan->d_tw;
 #if GF3_RX12_ALT
-        if (plan->logN == 12) { r = upload_twiddles(GF3_RX12_ALT == 2 ? 212 : 112, &plan->d_tw_demod); if (r) return r; }
+        if (plan->logN == 12) { r = upload_twiddles(GF3_RX12_ALT * 100 + 12, &plan->d_tw_demod); if (r) return r; }
 #endif
         const int K = p->N / 2 - 1;
         std::vector<float2> ones(K, make_float2(1.f, 0.f));

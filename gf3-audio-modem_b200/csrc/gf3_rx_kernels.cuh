@@ -175,7 +175,9 @@ __device__ __forceinline__ void load_symbol(float2 (&x)[P::R], const S* __restri
         }
     }
     // odd sample offset (arbitrary sync index) or PCM: scalar / narrow loads.  Each touches part of the same
-    // sectors as its neighbours, so these loads DO allocate in L1
+    // sectors as its neighbours, so these loads DO allocate in L1.  (Measured alternative for float32: 8-byte aligned
+    // loads of (s[2m-1], s[2m]) completed by a lane shuffle -- 32 SHFL per symbol and spills at 128 registers made the
+    // odd-offset data symbols 2.2x SLOWER, 0.610 vs 0.273 ms per 1024 C3 streams; profiles/r02_summary.md)
 #pragma unroll
     for (int i = I0; i < I1; ++i) x[i] = ldg_pair<S>(s + 2 * (t + i * P::T));
 }
@@ -1008,13 +1010,15 @@ __global__ void __launch_bounds__(kThreads) rx_estimate_kernel(const EstArgs a) 
 #define GF3_DEMOD_MINB (512 / GF3_DEMOD_THREADS)
 #endif
 template <int LOGN> struct DemodCfg { using Plan = FftPlan<LOGN>; static constexpr int NT = GF3_DEMOD_THREADS, MINB = GF3_DEMOD_MINB; };
-// N = 4096: 128 threads per symbol (16 x 16 x 8), two symbols per 256-thread CTA.  (A warp-per-symbol
-// 64 x 32 plan with ~255 registers / thread was measured slower: 8 warps per SM cannot hide latency.)
+// N = 4096: 128 threads per symbol (16 x 16 x 8, last pass on adjacent columns), two symbols per 256-thread CTA.
+// (A warp-per-symbol 64 x 32 plan with ~255 registers / thread was measured slower: 8 warps per SM cannot hide latency.)
 #ifndef GF3_DEMOD12_THREADS
 #define GF3_DEMOD12_THREADS 256
 #define GF3_DEMOD12_MINB 2
 #endif
-#if GF3_RX12_ALT == 2
+#if GF3_RX12_ALT == 3
+template <> struct DemodCfg<12> { using Plan = FftPlan12P; static constexpr int NT = GF3_DEMOD12_THREADS, MINB = GF3_DEMOD12_MINB; };
+#elif GF3_RX12_ALT == 2
 template <> struct DemodCfg<12> { using Plan = FftPlan12C; static constexpr int NT = 128, MINB = 2; };
 #elif GF3_RX12_ALT
 template <> struct DemodCfg<12> { using Plan = FftPlan12B; static constexpr int NT = GF3_DEMOD12_THREADS, MINB = GF3_DEMOD12_MINB; };

@@ -41,6 +41,8 @@ CASES = [
     (512, 64, 200, 201, 3, 17, 20, 200, 3),    # a single data carrier
     (1024, 32, 1, 512, 4, 1, 125, 250, 6),     # one data symbol per packet
     (1024, 32, 17, 400, 20, 180, 125, 250, 2),
+    (1024, 33, 1, 512, 3, 19, 125, 250, 3),    # odd symbol length: the two symbols of a warp differ in alignment
+    (2048, 63, 1, 1024, 2, 11, 250, 500, 2),
     (2048, 64, 5, 900, 3, 65, 250, 500, 2),    # crosses the 64-symbol re-seed period
     (4096, 224, 100, 1500, 4, 21, 500, 1000, 2),
     (4096, 1184, 1, 2047, 2, 9, 500, 1000, 1),

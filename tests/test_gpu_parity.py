@@ -35,7 +35,8 @@ def _rel_err(a, b):
 
 
 # ----------------------------------------------------------------------------- FFT front end
-@pytest.mark.parametrize("N,cp", [(64, 16), (128, 0), (256, 16), (512, 64), (1024, 32), (2048, 64), (4096, 224), (4096, 704)])
+@pytest.mark.parametrize("N,cp", [(64, 16), (128, 0), (256, 16), (512, 64), (1024, 32), (2048, 64), (4096, 224), (4096, 704),
+                                  (1024, 33), (2048, 7)])                  # odd symbol length: every other symbol 4-byte aligned only
 def test_spectrum_matches_numpy_fft(N, cp, known_sequence):
     torch = _torch()
     p = orc.Params(N=N, cp=cp, lo=1, hi=N // 2, n_pilots=0, packet_len=1, known_sequence=known_sequence)
