@@ -451,6 +451,45 @@ class transmitter(CamG):
         pos = (len(bits) + np.arange(padding_length)) % dbs
         return np.hstack([bits, np.bitwise_xor(padding, self.known_sequence[:dbs][pos])])
 
+    def _modulate_packed(self, rows, filler, device_xor):
+        """rows uint8 [n_packets, bits_per_packet / 8] (MSB-first bytes, np.packbits order) -> framed waveform."""
+        import torch
+        phy = self.phy
+        n_packets = rows.shape[0]
+        self.no_packets = n_packets
+        d_bits = torch.zeros((1, n_packets, phy.bits_stride), dtype=torch.uint8, device=phy.device)
+        d_bits[0, :, : rows.shape[1]].copy_(torch.from_numpy(rows))
+        d_fill = torch.from_numpy(np.asarray(filler).astype(np.complex64)).to(phy.device).reshape(1, -1) if phy.K > phy.Nd else None
+        out = phy.tx_modulate(d_bits, d_fill, 1, n_packets, xor=device_xor)
+        return out[0].cpu().numpy().astype(np.float64)
+
+    def transmit_bytes(self, payload, graph_output=False):
+        """transmit(np.unpackbits(payload)) without the host bit array (file framing + XOR coding on the
+        device): the file's bytes ARE the packed bit stream (np.packbits order, OFDM.py:761), the XOR encode runs in the
+        transmit kernel, only the padding (< one packet, drawn with the reference's np.random.binomial call so seeded runs
+        agree with transmit()) is built from bits on the host.  Same waveform as transmit() (tested)."""
+        payload = np.ascontiguousarray(np.asarray(payload, dtype=np.uint8).reshape(-1))
+        bpp = self.data_bits_per_symbol * self.packet_length
+        if bpp % 8 or self.encoding not in ("XOR", "None"):          # packets not byte aligned: the bit path handles it
+            return self.transmit(np.unpackbits(payload), graph_output)
+        print("-" * 42 + "\nTRANSMIT\n" + "-" * 42)
+        print("OFDM Paramters:")
+        print(self)
+        nbits = 8 * len(payload)
+        padding_length = (bpp - nbits % bpp) % bpp
+        padding = np.random.binomial(n=1, p=0.5, size=(padding_length,))          # OFDM.py:172 / :183, same draw
+        device_xor = self.encoding == "XOR"
+        if device_xor:                                                             # see _pad_for_device_encode
+            dbs = self.data_bits_per_symbol
+            padding = np.bitwise_xor(padding, self.known_sequence[:dbs][(nbits + np.arange(padding_length)) % dbs])
+        filler = self.random_qpsk()
+        rows = np.concatenate([payload, np.packbits(padding.astype(np.uint8))]).reshape(-1, bpp // 8)
+        print("Number of bits to transmit:         " + str(nbits))
+        print("Number of OFDM symbols to transmit: " + str(rows.shape[0] * self.packet_length))
+        signal = self._modulate_packed(rows, filler, device_xor)
+        print("Number of packets to transmit:      " + str(self.no_packets))
+        return signal
+
     def transmit(self, bits, graph_output=False):
         """OFDM.py:296-343."""
         print("-" * 42 + "\nTRANSMIT\n" + "-" * 42)
@@ -607,19 +646,46 @@ class receiver(transmitter):
         d = torch.from_numpy(rx_cp.reshape(-1)).to(phy.device)
         return self._demod_device(d, n_packets, None, want_eq)
 
-    def _demod_device(self, d_samples, n_packets, d_off, want_eq):
+    def _demod_device(self, d_samples, n_packets, d_off, want_eq, packed=False):
         import torch
         phy = self.phy
         rx = phy.rx_receive if d_samples.dtype == torch.float32 else phy.rx_receive_pcm
         res, Hs, He, slope = rx(d_samples, n_packets, d_off, xor=(self.encoding == "XOR"), want_eq=want_eq)
         bits_packed, eq = res if want_eq else (res, None)
+        if packed:                                                 # receive_bytes: the rows' bytes, no host bit array
+            return dict(bits=bits_packed[:, : phy.bits_per_packet // 8].cpu().numpy().reshape(-1), bits_packed=bits_packed,
+                        Hs=Hs.cpu().numpy().astype(np.complex128), He=He.cpu().numpy().astype(np.complex128), slope=slope.cpu().numpy())
         out = dict(bits=phy.unpack_bits(bits_packed), Hs=Hs.cpu().numpy().astype(np.complex128),
                    He=He.cpu().numpy().astype(np.complex128), slope=slope.cpu().numpy())
         if want_eq:
             out["eq"] = eq.cpu().numpy().reshape(-1, phy.K)
         return out
 
-    def receive(self, signal, graph_output=False, _details=None):
+    def receive_bytes(self, signal):
+        """np.packbits(receive(signal)[0]) without the host bit array: the packed rows the kernel wrote are
+        the file's bytes.  Returns (bytes uint8, Hest_start[0], Hest_end[0]); save_file_bytes() writes them out and
+        bit_errors() counts differences against a file on the device."""
+        if (self.data_bits_per_symbol * self.packet_length) % 8:
+            bits, hs, he = self.receive(signal)[:3] if not self.old_api else (self.receive(signal), None, None)
+            return np.packbits(bits), hs, he
+        return self.receive(signal, _packed=True)
+
+    def bit_errors(self, a, b):
+        """(bit errors, bits compared) between two packed byte strings over their common length, counted on the
+        device (gf3_ber_count): the notebook's `np.sum(rx_bits[:n] != tx_bits) / n` (Final System Test.ipynb:150-160)."""
+        import torch
+        phy = self.phy
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.uint8).reshape(-1)); b = np.ascontiguousarray(np.asarray(b, dtype=np.uint8).reshape(-1))
+        n = min(len(a), len(b))
+        if n == 0:
+            return 0, 0
+        da = torch.from_numpy(a[:n]).to(phy.device); db = torch.from_numpy(b[:n]).to(phy.device)
+        counter = torch.zeros(2, dtype=torch.int64, device=phy.device)
+        phy.ber_count(da, db, 8 * n, counter)
+        c = counter.cpu().numpy()
+        return int(c[0]), int(c[1])
+
+    def receive(self, signal, graph_output=False, _details=None, _packed=False):
         """OFDM.py:581-657: sync -> slice -> FFT -> equalise -> demap -> decode, on the device."""
         import torch
         print("-" * 42 + "\nReceive \n" + "-" * 42)
@@ -642,9 +708,9 @@ class receiver(transmitter):
                              "(signal ends inside the last packet)")
         d_off = torch.from_numpy(starts.astype(np.int64)).to(phy.device)
         print("Number of received OFDM symbols:    " + str(self.no_packets * self.packet_length))
-        out = self._demod_device(d_r.reshape(-1), self.no_packets, d_off, want_eq=_details is not None)
+        out = self._demod_device(d_r.reshape(-1), self.no_packets, d_off, want_eq=_details is not None, packed=_packed)
         bits = out["bits"]
-        print("Number of received bits:            " + str(len(bits)))
+        print("Number of received bits:            " + str(len(bits) * (8 if _packed else 1)))
         if _details is not None:
             _details.update(out, peaks=peaks, starts=starts)
         self.Hest = out["Hs"][0]                                   # old API attribute (Week 2 Challenge.ipynb:305)
@@ -679,9 +745,21 @@ def load_file(file_name):
     return np.unpackbits(np.hstack([b, data_bytes]))
 
 
-def save_file(rx_bits):
+def load_file_bytes(file_name):
+    """np.packbits(load_file(file_name)): header + data as bytes, for transmitter.transmit_bytes."""
+    data_bytes = np.fromfile(_find_ci(os.path.join("input_files", file_name)), dtype=np.uint8)
+    file_info = file_name + "\x00" + str(len(data_bytes)) + "\x00"
+    return np.hstack([np.frombuffer(file_info.encode("latin-1"), dtype=np.uint8), data_bytes])
+
+
+def save_file_bytes(rx_bytes):
+    """save_file(np.unpackbits(rx_bytes)): for receiver.receive_bytes."""
+    return save_file(rx_bytes, _packed=True)
+
+
+def save_file(rx_bits, _packed=False):
     """OFDM.py:766-794."""
-    data = np.packbits(rx_bits)
+    data = np.asarray(rx_bits, dtype=np.uint8) if _packed else np.packbits(rx_bits)
     z1 = int(np.flatnonzero(data == 0)[0])
     file_name = "".join(chr(c) for c in data[:z1])
     data = data[z1 + 1:]

@@ -479,6 +479,42 @@ def test_dropin_transmit_receive_file_roundtrip(known_sequence, tmp_path, monkey
         rx.receive(np.concatenate([np.zeros(1000), sig[:600000]]))
 
 
+def test_dropin_packed_file_path(known_sequence, tmp_path, monkeypatch):
+    """file bytes -> transmit_bytes -> receive_bytes -> save_file_bytes with no bit array on the host gives
+    the same waveform and the same bytes as the bit-array calls, and bit_errors() (device popcount) reproduces the
+    notebook's BER of the real recording (Final System Test.ipynb:150-160: 24 525 errors, BER 0.0233756...)."""
+    _torch()
+    import OFDM
+    g = load_golden("kat1_gr5ch1.npz")
+    (tmp_path / "input_Files").mkdir()
+    (tmp_path / "output_files").mkdir()
+    g["bmp"].tofile(tmp_path / "input_Files" / "gr5ch1.bmp")
+    monkeypatch.chdir(tmp_path)
+    bits = OFDM.load_file("gr5ch1.bmp")
+    fb = OFDM.load_file_bytes("gr5ch1.bmp")
+    for mode, enc in (("A2", "XOR"), ("C2", "None")):
+        tx = OFDM.transmitter(mode=mode, encoding=enc)
+        np.random.seed(3)
+        sig = tx.transmit(bits)
+        np.random.seed(3)
+        sig_b = tx.transmit_bytes(fb)
+        assert np.array_equal(sig, sig_b)
+        rx = OFDM.receiver(mode=mode, encoding=enc)
+        r = np.concatenate([np.zeros(1000), sig, np.zeros(500)])
+        out, Hs, He = rx.receive(r)
+        out_b, Hs_b, He_b = rx.receive_bytes(r)
+        assert out_b.dtype == np.uint8 and np.array_equal(out_b, np.packbits(out)) and np.array_equal(Hs, Hs_b)
+        name, data = OFDM.save_file_bytes(out_b)
+        assert name == "gr5ch1.bmp" and np.array_equal(data, g["bmp"])
+        assert rx.bit_errors(out_b, fb) == (0, len(bits))
+    # KAT-1: the real recording against the transmitted file, counted on the device
+    rx = OFDM.receiver(mode="A2", encoding="XOR")
+    got, _, _ = rx.receive_bytes(g["wav_u8"])
+    assert np.array_equal(got, g["bits_packed"][: len(got)])
+    errors, n = rx.bit_errors(got, fb)
+    assert (errors, n) == (24525, 1049168) and errors / n == 0.023375665289067146
+
+
 def test_ber_sweep_sharding_invariance(known_sequence):
     """configs[4] / SURVEY 8e: the stream-sharded tx -> channel -> sync -> rx sweep gives identical
     counters however the streams are split across ranks (here: 3 emulated ranks on one GPU)."""

@@ -154,6 +154,11 @@ def test_dropin_file_framing(tmp_path, monkeypatch):
     ref_bits = np.unpackbits(g["bits_packed"])[:1512000]
     name2, data2 = OFDM.save_file(ref_bits)                  # the reference's own decoded bits (2.3 % BER)
     assert name2 == str(g["file_name"]) and np.array_equal(data2, g["file_payload"])
+    # the packed-byte forms carry the same stream as bytes
+    fb = OFDM.load_file_bytes("gr5ch1.bmp")
+    assert fb.dtype == np.uint8 and np.array_equal(np.unpackbits(fb), bits)
+    name3, data3 = OFDM.save_file_bytes(np.concatenate([fb, np.full(9, 255, dtype=np.uint8)]))
+    assert name3 == "gr5ch1.bmp" and np.array_equal(data3, g["bmp"])
 
 
 def test_get_symbols_slicing_matches_oracle(known_sequence):
