@@ -367,8 +367,9 @@ __host__ __device__ constexpr int zstride() {
 // layout, and the bin-pair walk of the data-symbol kernel (ascending k, descending M-k) then reads
 // conflict-free too (with padding, 16 descending bins straddle a pad slot and collide 2-way).
 // STORE = false (last pass only): the pass ends with its results in registers -- x[q*RAD + i] is bin
-// base(q) + i*NS, base(q) = (j / NS) * (NS * RAD) + j % NS, j = t + q*T -- for callers that consume the
-// transform straight from registers (the matched filter writes its output samples to global memory).
+// base(q) + i*NS, base(q) = (j / NS) * (NS * RAD) + j % NS, j = t + q*T (paired plans: j = 2t + q, i.e. x[i] and
+// x[RAD + i] are the neighbouring bins 2t + i*NS and 2t + 1 + i*NS) -- for callers that consume the transform
+// straight from registers (the matched filter and the transmitter write their output samples to global memory).
 template <class P, int NTHREADS, int PASS, bool NATURAL = false, bool STORE = true>
 __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__ zs,
                                          const float2* __restrict__ tw, int t, int grp) {
@@ -447,7 +448,7 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[P::R], float2* __restrict__
         Dft<RAD>::run(&x[q * RAD]);
     });
     if constexpr (!STORE) {
-        static_assert(PASS == P::NPASS - 1 && !P::PAIRED && !P::PAIRLAST, "register output is for the last pass of the unpaired plans");
+        static_assert(PASS == P::NPASS - 1, "register output is for the last pass");
         return;
     } else
     if constexpr (P::PAIRED && PASS == 0) {

@@ -168,51 +168,77 @@ __global__ void __launch_bounds__(kTxThreads, kTxMinBlocks) tx_symbols_kernel(co
         }
         __syncthreads();
 
-        // ---- phase A': forward FFT of conj(Z)
+        // ---- phase A': forward FFT of conj(Z), last pass left in registers
+        float2 x[R];
         {
-            float2 x[R];
             float2* zs = zbuf + g * MP;
 #pragma unroll
             for (int i = 0; i < R; ++i) x[i] = zs[t + i * T];
             group_sync<P, NT>(g);
-            fft_forward<P, NT, true>(x, zs, tw, t, g);
+            fft_forward_to_regs<P, NT>(x, zs, tw, t, g);
         }
-        __syncthreads();
 
-        // ---- epilogue: time samples with cyclic prefix (OFDM.py:221-226), gain (OFDM.py:256)
+        // ---- epilogue: time samples with cyclic prefix (OFDM.py:221-226), gain (OFDM.py:256), straight from the
+        // registers of the last pass: every symbol group writes its own symbol
         float* o0;
         if constexpr (KNOWN_SYMBOL) o0 = a.out + work * symlen;
         else o0 = a.out + stream * a.out_stride + pk * ((int64_t)a.chirp_len + (int64_t)(2 * a.P + a.L) * symlen)
                   + a.chirp_len + (int64_t)(a.P + l_first) * symlen;
-        const bool al8 = ((reinterpret_cast<uintptr_t>(o0) | (uintptr_t)(a.cp * 4) | (uintptr_t)(symlen * 4)) & 7) == 0;
+        constexpr int LR = P::rad(P::NPASS - 1), LNS = P::ns(P::NPASS - 1), LQ = R / LR;       // last pass: radix, stride, sub-transforms
+        constexpr bool PAIR = P::PAIRED || P::PAIRLAST;
         const int cp_first = (N - a.cp + 1) / 2;           // pairs m >= cp_first lie entirely inside the cyclic prefix's source
-        for (int s = g; s < nsym; s += SF) {               // every symbol group writes its own symbol
-            float* o = o0 + (int64_t)s * symlen;
-            const float2* zs = zbuf + s * MP;
-            if (al8) {                                     // 8-byte aligned symbol, even CP: two coalesced float2 streams
-                float2* body = reinterpret_cast<float2*>(o + a.cp);
-                float2* pre = reinterpret_cast<float2*>(o) - cp_first;      // pre[m] = o[2m - (N - cp)]
-#pragma unroll 8
-                for (int i = 0; i < R; ++i) {
-                    const int m = t + i * T;
-                    const float2 y = zs[m];
-                    const float2 v = make_float2(y.x * a.gain, -y.y * a.gain);
-                    body[m] = v;
-                    if (m >= cp_first) pre[m] = v;
+        if (g < nsym) {
+            float* o = o0 + (int64_t)g * symlen;
+            const uintptr_t amask = PAIR ? 15 : 7;
+            const bool al = ((reinterpret_cast<uintptr_t>(o) | (uintptr_t)(a.cp * 4) | (uintptr_t)(symlen * 4)) & amask) == 0;
+            if (al) {                                      // aligned symbol, even CP: coalesced vector stores
+                if constexpr (PAIR) {
+                    static_assert(!PAIR || LQ == 2, "paired last pass: two sub-transforms");
+                    // x[i], x[LR + i] = points m = 2t + i*LNS and m + 1: four consecutive samples
+                    float4* body = reinterpret_cast<float4*>(o + a.cp);
+                    float4* pre = reinterpret_cast<float4*>(o - (N - a.cp));            // pre[m/2] = o[2m - (N - cp)]
+#pragma unroll
+                    for (int i = 0; i < LR; ++i) {
+                        const int m = 2 * t + i * LNS;
+                        const float4 v = make_float4(x[i].x * a.gain, -x[i].y * a.gain, x[LR + i].x * a.gain, -x[LR + i].y * a.gain);
+                        body[m >> 1] = v;
+                        if (m >= cp_first) pre[m >> 1] = v;          // (cp is a multiple of 4 here: m and m + 1 are on the same side)
+                    }
+                } else {
+                    float2* body = reinterpret_cast<float2*>(o + a.cp);
+                    float2* pre = reinterpret_cast<float2*>(o) - cp_first;      // pre[m] = o[2m - (N - cp)]
+#pragma unroll
+                    for (int q = 0; q < LQ; ++q) {
+                        const int j = t + q * T;
+                        const int base = (j / LNS) * (LNS * LR) + (j % LNS);
+#pragma unroll
+                        for (int i = 0; i < LR; ++i) {
+                            const int m = base + i * LNS;
+                            const float2 v = make_float2(x[q * LR + i].x * a.gain, -x[q * LR + i].y * a.gain);
+                            body[m] = v;
+                            if (m >= cp_first) pre[m] = v;
+                        }
+                    }
                 }
             } else {
-                for (int m = t; m < M; m += T) {
-                    const float2 y = zs[m];
-                    const float v0 = y.x * a.gain, v1 = -y.y * a.gain;
-                    const int n0 = 2 * m - (N - a.cp);                   // position of this pair inside the cyclic prefix
-                    o[a.cp + 2 * m] = v0;
-                    o[a.cp + 2 * m + 1] = v1;
-                    if (n0 >= 0) o[n0] = v0;
-                    if (n0 + 1 >= 0) o[n0 + 1] = v1;
+#pragma unroll
+                for (int q = 0; q < LQ; ++q) {
+                    const int j = PAIR ? 2 * t + q : t + q * T;
+                    const int base = (j / LNS) * (LNS * LR) + (j % LNS);
+#pragma unroll
+                    for (int i = 0; i < LR; ++i) {
+                        const int m = base + i * LNS;
+                        const float v0 = x[q * LR + i].x * a.gain, v1 = -x[q * LR + i].y * a.gain;
+                        const int n0 = 2 * m - (N - a.cp);                   // position of this pair inside the cyclic prefix
+                        o[a.cp + 2 * m] = v0;
+                        o[a.cp + 2 * m + 1] = v1;
+                        if (n0 >= 0) o[n0] = v0;
+                        if (n0 + 1 >= 0) o[n0 + 1] = v1;
+                    }
                 }
             }
         }
-        // (the next work item's first barrier orders these zbuf reads before its phase B' writes)
+        // (the next work item's first barrier orders this item's FFT exchanges before its phase B' writes)
     }
 }
 

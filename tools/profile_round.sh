@@ -22,3 +22,4 @@ ncu --set full --clock-control none --import-source on -k regex:"rx_demod" -s 3 
 ncu --set full --clock-control none --import-source on -k regex:"xcorr_fused" -s 2 -c 1 -o $O/${TAG}_prof_xcorr python bench.py --workload c3-raw --steps 2 --warmup 3 --no-cpu --no-e2e --no-parity > $O/${TAG}_ncu4.log 2>&1
 tail -2 $O/${TAG}_ncu4.log
 head -c 1500 $O/${TAG}_bench_c3.json
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
