@@ -2,7 +2,7 @@
 """bench.py -- headline benchmark of the GF3 B200 physical layer (BASELINE.json metric:
 demodulated Mbit/s and OFDM symbols/s, % of the HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c3-raw|c4|c4-long|a2|w2048] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c3-raw|c4|c4-long|a2|a2-raw|w2048] [--impl reference]
 
 A "step" is one pass of the hot path over one batch of synthetic input.
   * packet workloads (c3, c4, c4-long, a2, w2048): the receive chain (gf3_rx_receive: channel estimate +
@@ -52,6 +52,8 @@ WORKLOADS = {
               "W2048 (parity-test geometry): 2048 streams x 1 packet, N=2048, CP=64, Nd=1023, P=20, L=180, random 30-tap multipath + AWGN 20 dB"),
     "a2": (dict(N=4096, cp=224, lo=100, hi=1500, n_pilots=20, packet_len=180), 512, False,
            "A2 (mode of the real recording): 512 streams x 1 packet, N=4096, CP=224, Nd=1400, P=20, L=180, random 30-tap multipath + AWGN 20 dB"),
+    "a2-raw": (dict(N=4096, cp=224, lo=100, hi=1500, n_pilots=20, packet_len=180), 256, True,
+               "A2-raw (mode of the real recording, as raw audio): 256 streams of [lead-in | chirp | packet | chirp | tail], N=4096, CP=224, Nd=1400, P=20, L=180, chirp 21600 (11 partitions), random 30-tap multipath + AWGN 20 dB; step = matched filter + detection + receive chain"),
 }
 METRIC, UNIT = "demodulated_mbit_per_s", "Mbit/s"
 RAW_LEAD_MAX, RAW_TAIL = 2000, 8
@@ -586,9 +588,13 @@ def run_gpu_arm(args, cfg, streams, raw, desc):
             if not args.split_sync:      # one call: seg[0] is empty, seg[1] = matched filter + detection + offsets
                 xc_ms, pk_ms = seg[1], 0.0
             Tb = 4.0 * T * n_packets                                        # one pass over the streams
-            dense = args.split_sync or args.dense_sync
+            parts = -(-phy.chirp_len // 2048)
+            one_kernel = parts <= 4          # longer chirps (the N = 4096 modes) take the two-kernel matched filter, which computes all of P
+            dense = args.split_sync or args.dense_sync or not one_kernel
             kb = 2 * Tb if dense else Tb        # all of P written (4T + 4T), or detection only: every sample read once (SURVEY 8d "ideal")
-            roof = {"bound": "hbm", "kernel": "xcorr_fused_kernel (matched filter: 4T read + 4T written per stream when all of P is computed)" + ("" if args.split_sync else " + detection walk (%s)" % ("gf3_sync_streams" if args.dense_sync else "gf3_sync_detect: inverse transforms only where a candidate is possible")),
+            kname = "xcorr_fused_kernel (matched filter: 4T read + 4T written per stream when all of P is computed)" if one_kernel else \
+                    "xcorr_fwd_kernel + xcorr_acc_kernel (two-kernel matched filter for %d chirp partitions: block spectra through a scratch array, all of P written)" % parts
+            roof = {"bound": "hbm", "kernel": kname + ("" if args.split_sync else " + detection walk (%s)" % ("gf3_sync_streams" if (args.dense_sync or not one_kernel) else "gf3_sync_detect: inverse transforms only where a candidate is possible")),
                     "achieved": kb / (xc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "traffic": traffic if dense else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kb, "avg_launch_ms": xc_ms,
                     "note": "the matched filter is bound by FP32 issue (144 flop per sample), not by HBM; " + ("4T read + 4T of P written" if dense else "detection only: 4T read, P written only where a candidate is possible (the dense form moves 8T: frac %.3f at this duration)" % (2 * Tb / (xc_ms * 1e-3) / 1e9 / peak)),

@@ -154,6 +154,7 @@ struct AccArgs {
     const float2* tw;
     float* P;                // [n_streams, p_stride]
     float* pmax;             // [n_streams]
+    float* blockmax;         // [n_streams, nblk_out] or null: signed maximum of every output block (guides the detection walk)
     int64_t p_stride, out_len;   // out_len = T + Lc - 1
     int nblk_in, nblk_out, parts;
     int64_t n_work;          // n_streams * nblk_out
@@ -268,9 +269,136 @@ __global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
         if (tid == 0) {
             float m = wmax[0];
             for (int w = 1; w < NT / 32; ++w) m = fmaxf(m, wmax[w]);
+            if (a.blockmax) a.blockmax[stream * a.nblk_out + b] = m;
             if (m > __int_as_float(0xff800000)) atomic_max_float(a.pmax + stream, m);
         }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Long chirps (the N = 4096 modes: 21 600 - 26 400 taps = 11 - 13 partitions): the partition sum as its own kernel.
+// xcorr_acc_kernel above reads `parts` input spectra AND `parts` chirp partitions from L2 for every output block
+// (352 KB per block at 11 partitions: L2-bandwidth bound).  Here one 512-thread CTA per SM keeps ALL chirp
+// partitions in shared memory (parts x 16 KB <= 208 KB) and computes a run of J consecutive output blocks of one
+// stream at a time: every input spectrum of the run's window is read once and used for up to J outputs
+// ((J + parts - 1) / J = 2.25 reads per output at J = 8, parts = 11, instead of 11).  Y goes to a scratch array in
+// the spectrum layout; xcorr_acc_kernel with ONE all-ones partition then does the inverse transform.  The sum runs
+// over p ascending with the fmaf nesting of xcorr_acc_kernel, so P is bit-identical to the two-kernel form (tested).
+// ------------------------------------------------------------------------------------------
+constexpr int kMacThreads = 1024;        // 32 warps per SM, two bins per thread
+constexpr int kMacJ = 8;                  // output blocks per run
+constexpr int kMacMinParts = 5, kMacMaxParts = 13;          // up to 13 x 16 KB of shared memory
+struct MacArgs {
+    const float2* spec;      // [n_streams, nblk_in, M]
+    const float2* H;         // [parts, M]
+    float2* Y;               // [n_streams, nblk_out, M]
+    int nblk_in, nblk_out;
+    int runs_per_stream;     // ceil(nblk_out / J)
+    int64_t n_units;         // n_streams * runs_per_stream
+};
+
+// The (input block, output) pairs of a run form a fixed band (output j takes input b0 + j - p, p < PARTS): with PARTS a
+// template parameter the whole run is straight-line code -- no per-pair index arithmetic or predicates, partitions
+// at immediate shared-memory offsets.  Input blocks outside the stream read as zero (adding x * h = +0 leaves the sums
+// as they are), outputs past the last block are computed and dropped.
+template <int PARTS>
+__global__ void __launch_bounds__(kMacThreads, 1) xcorr_mac_kernel(const MacArgs a) {
+    constexpr int NT = kMacThreads, M = SP::M, J = kMacJ, NB = M / NT;       // NB = 2 bins per thread: k = tid + NT i
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* Hs = reinterpret_cast<float2*>(smem_raw);                       // [PARTS][M]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < PARTS * (M / 2); i += NT)
+        reinterpret_cast<float4*>(Hs)[i] = __ldg(reinterpret_cast<const float4*>(a.H) + i);
+    __syncthreads();
+    // Element 0 packs (DC, Nyquist), whose products are component-wise.  With the Nyquist term taken out of the copy
+    // in shared memory, the complex multiply-add of slot 0 gives the DC sum exactly (x.x h.x - x.y 0 + acc); warp 0
+    // carries the Nyquist sums beside it (lane 0's are the real ones).
+    __shared__ float hny[PARTS];
+    if (tid < PARTS) { hny[tid] = Hs[tid * M].y; Hs[tid * M].y = 0.f; }
+    __syncthreads();
+    // (the partitions are re-read from shared memory for every pair on purpose -- volatile, or the compiler keeps the
+    //  thread's 4 x PARTS values in registers across the whole kernel and spills the sums)
+    const unsigned ht = (unsigned)__cvta_generic_to_shared(Hs + tid);
+    auto lds_h = [&](auto offc) -> float2 {
+        float2 v;
+        asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(ht), "n"(decltype(offc)::value));
+        return v;
+    };
+    uint64_t keep;           // L2 policy of the spectra: every block is read by two or three runs
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+    auto run = [&](auto nyc) {
+        constexpr bool NY = decltype(nyc)::value;
+        for (int64_t unit = blockIdx.x; unit < a.n_units; unit += gridDim.x) {      // (contiguous ranges per CTA: no faster, 1.25 vs 1.21 ms)
+            const int64_t stream = unit / a.runs_per_stream;
+            const int b0 = (int)(unit - stream * a.runs_per_stream) * J;
+            float2 acc[J][NB];
+            [[maybe_unused]] float ny[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                if constexpr (NY) ny[j] = 0.f;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) acc[j][i] = make_float2(0.f, 0.f);
+            }
+            // running pointer / index of the block being requested (kept opaque: one register each, not a table of addresses)
+            int bq = b0 + J - 1;
+            const float2* xp = a.spec + (stream * (int64_t)a.nblk_in + bq) * M + tid;
+            auto load_x = [&](float2 (&dst)[NB]) {
+                if (bq >= 0 && bq < a.nblk_in) {
+#pragma unroll
+                    for (int i = 0; i < NB; ++i)
+                        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(dst[i].x), "=f"(dst[i].y) : "l"(xp + i * NT), "l"(keep));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) dst[i] = make_float2(0.f, 0.f);
+                }
+                --bq;
+                xp -= M;
+                asm volatile("" : "+r"(bq), "+l"(xp));
+            };
+            float2 xn[NB], xn2[NB];                                           // the next two input blocks are in flight
+            load_x(xn);
+            load_x(xn2);
+            // input blocks newest first: output j then sees p = j - d ascending, as xcorr_acc_kernel sums
+            static_for<J + PARTS - 1>([&](auto dc_) {
+                constexpr int d = J - 1 - decltype(dc_)::value;               // input block b0 + d, d = J-1 ... -(PARTS-1)
+                float2 x[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) { x[i] = xn[i]; xn[i] = xn2[i]; }
+                if constexpr (d > -(PARTS - 1) + 1) load_x(xn2);
+                static_for<J>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value, p = j - d;
+                    if constexpr (p >= 0 && p < PARTS) {
+                        static_for<NB>([&](auto ic) {
+                            constexpr int i = decltype(ic)::value;
+                            const float2 h = lds_h(std::integral_constant<int, (p * M + i * NT) * 8>{});
+                            acc[j][i].x = fmaf(x[i].x, h.x, fmaf(-x[i].y, h.y, acc[j][i].x));
+                            acc[j][i].y = fmaf(x[i].x, h.y, fmaf(x[i].y, h.x, acc[j][i].y));
+                        });
+                        if constexpr (NY) ny[j] = fmaf(x[0].y, hny[p], ny[j]);
+                    }
+                });
+            });
+            float2* Yo = a.Y + (stream * (int64_t)a.nblk_out + b0) * M + tid;
+            const int nj = a.nblk_out - b0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                if (j < nj) {
+                    if constexpr (NY) { if (tid == 0) acc[j][0].y = ny[j]; }
+#pragma unroll
+                    for (int i = 0; i < NB; ++i)          // streaming store: the sums must not push the spectra out of L2
+                        asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(Yo + (int64_t)j * M + i * NT), "f"(acc[j][i].x), "f"(acc[j][i].y) : "memory");
+                }
+            }
+        }
+    };
+    if (tid < 32) run(std::true_type{});
+    else run(std::false_type{});
+}
+
+__global__ void xcorr_ones_kernel(float2* H1) {       // the unit partition of the inverse stage: (1, 1) packs (DC, Nyquist)
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < SP::M) H1[k] = make_float2(1.f, k == 0 ? 1.f : 0.f);
 }
 
 
@@ -999,11 +1127,16 @@ int sync_plan_init(gf3_plan* plan) {
                                                       reinterpret_cast<float4*>(plan->d_chirp_pairs), plan->d_chirp_dc);
         GF3_LAUNCH_CHECK();
     }
+    GF3_CHECK_CUDA(cudaMalloc(&plan->d_chirp_one, (size_t)SP::M * sizeof(float2)));
+    xcorr_ones_kernel<<<(SP::M + 255) / 256, 256>>>(plan->d_chirp_one);
+    GF3_LAUNCH_CHECK();
     GF3_CHECK_CUDA(cudaDeviceSynchronize());
     return GF3_OK;
 }
 
 void sync_plan_free(gf3_plan* plan) {
+    if (plan->d_chirp_one) cudaFree(plan->d_chirp_one);
+    plan->d_chirp_one = nullptr;
     if (plan->d_chirp_pairs) cudaFree(plan->d_chirp_pairs);
     if (plan->d_chirp_dc) cudaFree(plan->d_chirp_dc);
     plan->d_chirp_pairs = nullptr; plan->d_chirp_dc = nullptr;
@@ -1021,7 +1154,8 @@ static XcorrGeom xcorr_geom(const gf3_plan* plan, int64_t n_streams, int64_t T) 
     int64_t nin = (T - 1) / kB + 2;                      // blocks that see at least one real sample
     g.nblk_in = (int)(nin < g.nblk_out ? nin : g.nblk_out);
     g.per_stream = (size_t)g.nblk_in * SP::M * sizeof(float2);
-    const size_t cap = (size_t)2 << 30;                   // bound the scratch to 2 GiB: streams are tiled
+    size_t cap = (size_t)2 << 30;                         // bound the scratch to 2 GiB: streams are tiled
+    if (const char* e = getenv("GF3_XC_TILE_MB")) { const long mb = atol(e); if (mb > 0) cap = (size_t)mb << 20; }
     int64_t tile = (int64_t)(cap / g.per_stream);
     if (tile < 1) tile = 1;
     if (tile > n_streams) tile = n_streams;
@@ -1048,6 +1182,15 @@ static int fused_minb() {
 // The fused kernel pays (parts - 1) extra forward FFTs per CTA (the spectra before its first block), so it needs
 // runs of blocks that are long against the partition count; otherwise (one long recording with a 21 600-tap
 // chirp: 11 partitions) the two-kernel form stays.  GF3_XCORR_PATH=fused|split overrides (experiments).
+// Long chirps: partition sum in its own kernel (xcorr_mac_kernel), inverse transform by xcorr_acc_kernel with the unit
+// partition.  GF3_XCORR_MAC=0 keeps the two-kernel form (experiments / the bit-identity test).
+static bool mac_applies(const gf3_plan* plan) {
+    const bool can = plan->sync_parts >= kMacMinParts && plan->sync_parts <= kMacMaxParts;
+    if (const char* e = getenv("GF3_XCORR_MAC")) return atoi(e) != 0 && can;
+    return can;
+}
+static size_t mac_y_bytes(const XcorrGeom& g) { return (size_t)g.tile * (size_t)g.nblk_out * SP::M * sizeof(float2); }
+
 static bool fused_applies(const gf3_plan* plan, int64_t n_streams, const XcorrGeom& g) {
     if (plan->sync_parts > GF3_XC_FUSED_MAX_PARTS) return false;
     if (const char* e = getenv("GF3_XCORR_PATH")) {
@@ -1120,11 +1263,29 @@ static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_
         return launch_fused<uint8_t>(plan, a, st);
     }
     GF3_REQUIRE(work != nullptr, "xcorr: null work buffer");
-    GF3_REQUIRE(blockmax == nullptr, "xcorr: internal: block maxima come from the fused kernel only");
     float2* spec = reinterpret_cast<float2*>(work);
     const size_t smem = (size_t)(SP::MP + SP::TW_TOTAL) * sizeof(float2);
     GF3_CHECK_CUDA(cudaFuncSetAttribute(xcorr_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t esz = fmt == GF3_SAMPLE_F32 ? 4 : fmt == GF3_SAMPLE_I16 ? 2 : 1;
+    const bool mac = mac_applies(plan);
+    float2* Ysum = reinterpret_cast<float2*>(reinterpret_cast<char*>(work) + ((g.per_stream * (size_t)g.tile + 255) & ~(size_t)255));
+    const size_t mac_smem = (size_t)plan->sync_parts * SP::M * sizeof(float2);
+    void (*mac_kern)(const MacArgs) = nullptr;
+    if (mac) {
+        switch (plan->sync_parts) {
+            case 5: mac_kern = xcorr_mac_kernel<5>; break;
+            case 6: mac_kern = xcorr_mac_kernel<6>; break;
+            case 7: mac_kern = xcorr_mac_kernel<7>; break;
+            case 8: mac_kern = xcorr_mac_kernel<8>; break;
+            case 9: mac_kern = xcorr_mac_kernel<9>; break;
+            case 10: mac_kern = xcorr_mac_kernel<10>; break;
+            case 11: mac_kern = xcorr_mac_kernel<11>; break;
+            case 12: mac_kern = xcorr_mac_kernel<12>; break;
+            case 13: mac_kern = xcorr_mac_kernel<13>; break;
+            default: gf3::set_error("xcorr: internal: no partition-sum kernel for %d partitions", plan->sync_parts); return GF3_ERR_INVALID;
+        }
+        GF3_CHECK_CUDA(cudaFuncSetAttribute(mac_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mac_smem));
+    }
     for (int64_t s0 = 0; s0 < n_streams; s0 += g.tile) {
         const int64_t ns = (n_streams - s0 < g.tile) ? n_streams - s0 : g.tile;
         int rc = run_fwd(plan, reinterpret_cast<const char*>(r) + (size_t)(s0 * r_stride) * esz, fmt, r_stride, ns, T, g.nblk_in, 0, 0, 2 * kB,
@@ -1132,8 +1293,19 @@ static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_
         if (rc) return rc;
         AccArgs a;
         a.spec = spec; a.H = plan->d_chirp_spec; a.tw = plan->d_sync_tw; a.P = P + s0 * p_stride; a.pmax = pmax + s0;
+        a.blockmax = blockmax ? blockmax + s0 * g.nblk_out : nullptr;
         a.p_stride = p_stride; a.out_len = g.out_len; a.nblk_in = g.nblk_in; a.nblk_out = g.nblk_out; a.parts = plan->sync_parts;
         a.n_work = ns * g.nblk_out;
+        if (mac) {
+            MacArgs m;
+            m.spec = spec; m.H = plan->d_chirp_spec; m.Y = Ysum; m.nblk_in = g.nblk_in; m.nblk_out = g.nblk_out;
+            m.runs_per_stream = (g.nblk_out + kMacJ - 1) / kMacJ;
+            m.n_units = ns * m.runs_per_stream;
+            int64_t mg = m.n_units < plan->sm_count ? m.n_units : plan->sm_count;          // one CTA per SM: the partitions fill its shared memory
+            mac_kern<<<(unsigned)mg, kMacThreads, mac_smem, st>>>(m);
+            GF3_LAUNCH_CHECK();
+            a.spec = Ysum; a.H = plan->d_chirp_one; a.nblk_in = g.nblk_out; a.parts = 1;    // inverse stage: Y_b times the unit partition
+        }
         int64_t grid = a.n_work;
         if (grid > (int64_t)plan->sm_count * GF3_XC_ACC_CTAS) grid = (int64_t)plan->sm_count * GF3_XC_ACC_CTAS;   // 4 CTAs / SM resident
         xcorr_acc_kernel<<<(unsigned)grid, 128, smem, st>>>(a);
@@ -1187,7 +1359,8 @@ extern "C" size_t gf3_xcorr_work_bytes(const gf3_plan* plan, int64_t n_streams, 
     if (!plan || n_streams <= 0 || T <= 0) return 0;
     const XcorrGeom g = xcorr_geom(plan, n_streams, T);
     if (fused_applies(plan, n_streams, g)) return 16;                 // the fused kernel keeps its spectra on chip
-    return g.per_stream * (size_t)g.tile;
+    const size_t xs = (g.per_stream * (size_t)g.tile + 255) & ~(size_t)255;
+    return xs + (mac_applies(plan) ? mac_y_bytes(g) : 0);              // + the partition sums of the three-kernel form
 }
 
 extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride, int64_t n_streams,
@@ -1219,7 +1392,7 @@ static int sync_common(const gf3_plan* plan, const void* r, int32_t sample_forma
     const XcorrGeom g = xcorr_geom(plan, n_streams, T);
     char* w = reinterpret_cast<char*>(work);
     const bool fused = fused_applies(plan, n_streams, g);
-    float* blockmax = fused ? reinterpret_cast<float*>(w) : nullptr;
+    float* blockmax = reinterpret_cast<float*>(w);                     // both forms of the matched filter record the block maxima
     void* xwork = w + sync_off_blockmax(g, n_streams);
     void* pwork = reinterpret_cast<char*>(xwork) + ((gf3_xcorr_work_bytes(plan, n_streams, T) + 255) & ~(size_t)255);
     // detection only: blocks of P that provably hold no candidate are not computed (the detections are the same)

@@ -183,6 +183,31 @@ def test_a2_multistream_sync_vs_oracle(known_sequence):
     assert not bad and hist == {2: 8}
 
 
+@pytest.mark.parametrize("cp,parts", [(224, 11), (704, 12), (1184, 13)])
+def test_long_chirp_partition_sum_kernel_is_bit_identical(cp, parts, known_sequence, monkeypatch):
+    """The N = 4096 modes (21 600 / 24 000 / 26 400-tap chirps = 11 / 12 / 13 filter partitions): the three-kernel matched
+    filter (forward transforms, partition sums with every partition in shared memory and each input spectrum reused for a
+    run of 8 outputs, inverse transforms) gives P and its maxima bit for bit as the two-kernel form does -- which the
+    tests above and KAT-1 / KAT-4 pin to the reference's detections."""
+    torch = _torch()
+    phy, p = _pair(known_sequence, N=4096, cp=cp, lo=100, hi=1500, n_pilots=20, packet_len=180)
+    assert -(-phy.chirp_len // 2048) == parts
+    g = torch.Generator(device="cuda").manual_seed(cp)
+    for B, T in ((5, 123457), (1, 2048 * 9), (3, 30011)):          # ragged lengths, a run that ends inside the window, short streams
+        r = torch.randn((B, T), generator=g, device="cuda", dtype=torch.float32)
+        if T > 1000 + phy.chirp_len:
+            r[:, 1000:1000 + phy.chirp_len] += 3.0 * phy.sync_chirp()
+        monkeypatch.delenv("GF3_XCORR_MAC", raising=False)
+        P1, m1 = phy.xcorr(r)
+        monkeypatch.setenv("GF3_XCORR_MAC", "0")
+        P0, m0 = phy.xcorr(r)
+        monkeypatch.delenv("GF3_XCORR_MAC", raising=False)
+        assert torch.equal(P0, P1) and torch.equal(m0, m1), (B, T)
+        from scipy.signal import fftconvolve
+        ref = fftconvolve(r[0].double().cpu().numpy(), orc.sync_chirp(p)[::-1])
+        assert np.max(np.abs(P1[0].double().cpu().numpy() - ref)) / np.max(np.abs(ref)) < 5e-6
+
+
 # ----------------------------------------------------------------------------- KAT-4 (BASELINE.json configs[1])
 def test_kat4_gr5ch2_dropin_receive(known_sequence, capsys):
     """configs[1]: chirp-synchronised decode of a long recording (29 packets, 28.2 M samples, int16) with
