@@ -77,4 +77,5 @@ struct gf3_plan {
     float* d_chirp_pairs;  // [sync_parts][8][128] float4: the partitions in the fused matched filter's bin-pair layout, pre-scaled
     float2* d_chirp_dc;    // [sync_parts] (H[0], H[M]) pre-scaled
     float2* d_chirp_one;   // [NB/2] the unit partition (inverse stage of the three-kernel matched filter for long chirps)
+    float* d_chirp_energy; // [sync_parts][32] weighted energy of every partition's spectrum per bin group (detection-only bound)
 };

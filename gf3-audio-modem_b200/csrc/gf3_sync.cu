@@ -47,7 +47,14 @@ struct FwdArgs {
     int reverse;             // 1: input is read time-reversed (building the filter spectrum)
     int in_off;              // block b covers input samples [b*B - B + in_off, +2B)
     int valid_len;           // only the first valid_len samples of a block are taken (rest zero)
+    float* energy;           // optional [n_streams * nblk, kGroups] (zeroed by the caller): weighted energy of the block's spectrum per bin group
 };
+// Bin groups of the energy output: the 64 bins k = t + 128 q that one half of the thread group owns in slot q (groups
+// 2q, 2q + 1), and their mirror images M - k (groups 16 + 2q, 16 + 2q + 1) -- contiguous runs of the spectrum.  DC and
+// k = M/2 go with group 0, the Nyquist bin with group 16.  Weights as in the inverse real transform: 1 for DC and
+// Nyquist, 2 for the others.  Input spectra and chirp partitions come from the same kernel, hence the same grouping,
+// which is all the Cauchy-Schwarz bound of the detection-only matched filter needs (see xcorr_bound_kernel).
+constexpr int kGroups = 32;
 
 // block b of a stream = samples [b*B - B, b*B + B), zero outside [0, T)
 // Each 128-thread group transforms one block and untangles it itself: thread t owns the bin pairs
@@ -128,6 +135,7 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
             x1 = make_float2(0.5f * (s.x + tt.x), 0.5f * (s.y + tt.y));
             x2 = make_float2(0.5f * (s.x - tt.x), 0.5f * (tt.y - s.y));
         };
+        float e1[Q], e2[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const int k = t + q * T;
@@ -135,15 +143,45 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
             pair(k, uw[q], x1, x2);
             if (q == 0 && t == 0) {
                 out[0] = make_float2(x1.x, x2.x);      // (X[0], X[M]), both real
+                e1[q] = x1.x * x1.x;
+                e2[q] = x2.x * x2.x;
             } else {
                 out[k] = x1;
                 out[M - k] = x2;
+                e1[q] = 2.f * fmaf(x1.x, x1.x, x1.y * x1.y);
+                e2[q] = 2.f * fmaf(x2.x, x2.x, x2.y * x2.y);
             }
         }
         if (t == 0) {                                   // k = M/2 pairs with itself; w2 = -j e^{-j pi/2} = -1
             float2 x1, x2;
             pair(M / 2, make_float2(-1.f, 0.f), x1, x2);
             out[M / 2] = x1;
+            e1[0] += 2.f * fmaf(x1.x, x1.x, x1.y * x1.y);
+        }
+        if (a.energy) {                                 // (uniform)
+            // 16 sums over the warp's 32 lanes by a halving exchange (16 shuffles instead of 80): after the steps with
+            // lane distances 16, 8, 4, 2 a lane holds ONE slot -- bits 4..1 of its index say which -- summed over 16
+            // lanes, the last step adds the other 16.  Two warps share a group: one atomic each.
+            static_assert(Q == 8, "energy slots: 8 pairs per thread");
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) { v[q] = e1[q]; v[8 + q] = e2[q]; }
+            const int lane = t & 31;
+#pragma unroll
+            for (int h = 8; h >= 1; h >>= 1) {           // h = number of slots kept; partner distance 2h
+                const bool up = (lane & (2 * h)) != 0;
+#pragma unroll
+                for (int i = 0; i < h; ++i) {
+                    const float give = up ? v[i] : v[i + h];
+                    const float got = __shfl_xor_sync(0xffffffffu, give, 2 * h);
+                    v[i] = (up ? v[i + h] : v[i]) + got;
+                }
+            }
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+            if ((lane & 1) == 0) {
+                const int slot = lane >> 1;               // bits 4..1: 0..7 = e1[q], 8..15 = e2[q - 8]
+                atomicAdd(a.energy + bg * kGroups + (slot < 8 ? 2 * slot : 16 + 2 * (slot - 8)) + (t >= T / 2 ? 1 : 0), v[0]);
+            }
         }
     }
 }
@@ -155,6 +193,10 @@ struct AccArgs {
     float* P;                // [n_streams, p_stride]
     float* pmax;             // [n_streams]
     float* blockmax;         // [n_streams, nblk_out] or null: signed maximum of every output block (guides the detection walk)
+    const float* bound;      // detection only: [n_streams, nblk_out] upper bound of |P| in every block (xcorr_mac_kernel<.., true>), else null
+    float thresh;            // detection threshold (OFDM.py:361)
+    int select;              // 0: every block; 1: per stream, the block with the largest bound (n_work = n_streams);
+                             // 2: the blocks that can hold a candidate, and their neighbours (see the kernel)
     int64_t p_stride, out_len;   // out_len = T + Lc - 1
     int nblk_in, nblk_out, parts;
     int64_t n_work;          // n_streams * nblk_out
@@ -189,9 +231,58 @@ __global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
     }
     // persistent: the twiddle table is staged once per CTA; co-resident CTAs work on neighbouring
     // blocks, so the chirp-partition spectra and the shared input spectra stay hot in L2
+    __shared__ int s_sel;
     for (int64_t work = blockIdx.x; work < a.n_work; work += gridDim.x) {
-        const int64_t stream = work / a.nblk_out;
-        const int b = (int)(work - stream * a.nblk_out);
+        int64_t stream = work / a.nblk_out;
+        int b = (int)(work - stream * a.nblk_out);
+        if (a.select == 1) {
+            // the block with the largest bound very likely holds the chirp peak: its maximum seeds pmax[stream], the
+            // lower bound of max(P) that the selection of pass 2 needs
+            stream = work;
+            const float* bd = a.bound + stream * a.nblk_out;
+            float best = -1.f;
+            int bi = 0;
+            for (int i = tid; i < a.nblk_out; i += NT) {
+                const float v = bd[i];
+                if (v > best) { best = v; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            __shared__ float wbest[NT / 32];
+            __shared__ int wsel[NT / 32];
+            if ((tid & 31) == 0) { wbest[tid >> 5] = best; wsel[tid >> 5] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < NT / 32; ++w)
+                    if (wbest[w] > best) { best = wbest[w]; bi = wsel[w]; }
+                s_sel = bi;
+            }
+            __syncthreads();
+            b = s_sel;
+        } else if (a.select == 2) {
+            // |P| <= bound inside a block, and a candidate needs P > thresh * max(P) >= thresh * pmax[stream] (any lower
+            // bound of the maximum will do: pass 1 seeded it, the atomics of this pass only raise it).  A block whose
+            // bound passes that test -- every block that really holds a candidate or the maximum does, whoever
+            // evaluates it and whenever -- is transformed back together with both its neighbours (the detection rule
+            // reads one sample either side of a candidate); so are the first and the last block.  One thread decides:
+            // pmax moves while the others would read it.
+            if (tid == 0) {
+                const float* bd = a.bound + stream * a.nblk_out;
+                const float lim = a.thresh * a.pmax[stream];
+                bool go = b == 0 || b == a.nblk_out - 1 || !(lim > 0.f);
+                for (int i = (b > 0 ? b - 1 : 0); i <= b + 1 && i < a.nblk_out; ++i) go = go || bd[i] * 1.001f >= lim;
+                s_sel = go ? 1 : 0;
+                if (!go && a.blockmax) a.blockmax[stream * a.nblk_out + b] = __int_as_float(0xff800000);
+            }
+            __syncthreads();
+            const int go = s_sel;
+            __syncthreads();
+            if (!go) continue;
+        }
         __syncthreads();
 
         float2 acc1[Q], acc2[Q];
@@ -379,8 +470,8 @@ __global__ void __launch_bounds__(kMacThreads, 1) xcorr_mac_kernel(const MacArgs
                     }
                 });
             });
-            float2* Yo = a.Y + (stream * (int64_t)a.nblk_out + b0) * M + tid;
             const int nj = a.nblk_out - b0;
+            float2* Yo = a.Y + (stream * (int64_t)a.nblk_out + b0) * M + tid;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 if (j < nj) {
@@ -394,6 +485,30 @@ __global__ void __launch_bounds__(kMacThreads, 1) xcorr_mac_kernel(const MacArgs
     };
     if (tid < 32) run(std::true_type{});
     else run(std::false_type{});
+}
+
+// Detection only: an upper bound of |P| inside every output block from the group energies of the input spectra and
+// of the chirp partitions, without forming the partition sums:
+//   |y[n]| <= (1/N) sum_k w_k |Y_b[k]| <= (1/N) sum_p sum_k w_k |X_{b-p}[k]| |H_p[k]|
+//          <= (1/N) sum_p sum_groups sqrt(E_{b-p}[g]) sqrt(E_{H_p}[g])            (Cauchy-Schwarz inside every group).
+// With 32 groups of 64 neighbouring bins the last step costs a few per cent against the l1 norm itself (a partition of
+// a linear chirp is narrow-band and smooth in magnitude); the blocks it rules out are the same.  One warp per block.
+__global__ void __launch_bounds__(256) xcorr_bound_kernel(const float* __restrict__ E, const float* __restrict__ HE, float* __restrict__ bound,
+                                                          int nblk_in, int nblk_out, int parts, int64_t n_blocks) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t blk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < n_blocks; blk += nwarps) {
+        const int64_t stream = blk / nblk_out;
+        const int b = (int)(blk - stream * nblk_out);
+        float sum = 0.f;
+        for (int p = 0; p < parts; ++p) {
+            const int bp = b - p;
+            if (bp >= 0 && bp < nblk_in) sum = fmaf(sqrtf(E[(stream * nblk_in + bp) * kGroups + lane]), sqrtf(__ldg(HE + p * kGroups + lane)), sum);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) bound[blk] = sum * (1.0f / (float)SP::N);
+    }
 }
 
 __global__ void xcorr_ones_kernel(float2* H1) {       // the unit partition of the inverse stage: (1, 1) packs (DC, Nyquist)
@@ -1082,11 +1197,12 @@ __global__ void __launch_bounds__(256) schmidlcox_kernel(const ScArgs a) {
 
 // ------------------------------------------------------------------------------------------ host side
 static int run_fwd(const gf3_plan* plan, const void* r, int fmt, int64_t r_stride, int64_t n_streams, int64_t T, int nblk, int reverse,
-                   int in_off, int valid_len, float2* spec, const float2* tw, float* pmax, cudaStream_t st) {
+                   int in_off, int valid_len, float2* spec, const float2* tw, float* pmax, cudaStream_t st, float* energy = nullptr) {
     constexpr int SF = kSyncThreads / SP::T;
     FwdArgs f;
     f.r = r; f.spec = spec; f.tw = tw; f.pmax = pmax; f.r_stride = r_stride; f.T = T; f.n_streams = n_streams;
-    f.nblk = nblk; f.reverse = reverse; f.in_off = in_off; f.valid_len = valid_len;
+    f.nblk = nblk; f.reverse = reverse; f.in_off = in_off; f.valid_len = valid_len; f.energy = energy;
+    if (energy) GF3_CHECK_CUDA(cudaMemsetAsync(energy, 0, (size_t)n_streams * nblk * kGroups * sizeof(float), st));
     const size_t smem = (size_t)(SF * SP::MP + SP::TW_TOTAL) * sizeof(float2);
     int64_t gx = (n_streams * nblk + SF - 1) / SF;
     const int sms = plan->sm_count;
@@ -1115,8 +1231,9 @@ int sync_plan_init(gf3_plan* plan) {
     else { rc = upload_twiddles(SP::LOGN, &plan->d_sync_tw); if (rc) return rc; }
     GF3_CHECK_CUDA(cudaMalloc(&plan->d_chirp_spec, (size_t)plan->sync_parts * SP::M * sizeof(float2)));
     // H_p = rfft_{2B}([h[pB .. pB+B), 0 ... 0]),  h[m] = chirp[Lc-1-m]  (fsweep of OFDM.py:357)
+    GF3_CHECK_CUDA(cudaMalloc(&plan->d_chirp_energy, (size_t)plan->sync_parts * kGroups * sizeof(float)));
     rc = run_fwd(plan, plan->d_chirp, GF3_SAMPLE_F32, 0, 1, p.chirp_len, plan->sync_parts, 1, kB, kB, plan->d_chirp_spec,
-                 plan->d_sync_tw, nullptr, 0);
+                 plan->d_sync_tw, nullptr, 0, plan->d_chirp_energy);
     if (rc) return rc;
     {
         constexpr int QN = (SP::M / 2);
@@ -1136,7 +1253,8 @@ int sync_plan_init(gf3_plan* plan) {
 
 void sync_plan_free(gf3_plan* plan) {
     if (plan->d_chirp_one) cudaFree(plan->d_chirp_one);
-    plan->d_chirp_one = nullptr;
+    if (plan->d_chirp_energy) cudaFree(plan->d_chirp_energy);
+    plan->d_chirp_one = nullptr; plan->d_chirp_energy = nullptr;
     if (plan->d_chirp_pairs) cudaFree(plan->d_chirp_pairs);
     if (plan->d_chirp_dc) cudaFree(plan->d_chirp_dc);
     plan->d_chirp_pairs = nullptr; plan->d_chirp_dc = nullptr;
@@ -1271,32 +1389,46 @@ static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_
     float2* Ysum = reinterpret_cast<float2*>(reinterpret_cast<char*>(work) + ((g.per_stream * (size_t)g.tile + 255) & ~(size_t)255));
     const size_t mac_smem = (size_t)plan->sync_parts * SP::M * sizeof(float2);
     void (*mac_kern)(const MacArgs) = nullptr;
+    const bool bound_only = sparse && blockmax;             // detection only: bounds of |P| per block, two selective inverse passes
     if (mac) {
         switch (plan->sync_parts) {
-            case 5: mac_kern = xcorr_mac_kernel<5>; break;
-            case 6: mac_kern = xcorr_mac_kernel<6>; break;
-            case 7: mac_kern = xcorr_mac_kernel<7>; break;
-            case 8: mac_kern = xcorr_mac_kernel<8>; break;
-            case 9: mac_kern = xcorr_mac_kernel<9>; break;
-            case 10: mac_kern = xcorr_mac_kernel<10>; break;
-            case 11: mac_kern = xcorr_mac_kernel<11>; break;
-            case 12: mac_kern = xcorr_mac_kernel<12>; break;
-            case 13: mac_kern = xcorr_mac_kernel<13>; break;
+#define GF3_MAC_CASE(N_) case N_: mac_kern = xcorr_mac_kernel<N_>; break;
+            GF3_MAC_CASE(5) GF3_MAC_CASE(6) GF3_MAC_CASE(7) GF3_MAC_CASE(8) GF3_MAC_CASE(9) GF3_MAC_CASE(10) GF3_MAC_CASE(11)
+            GF3_MAC_CASE(12) GF3_MAC_CASE(13)
+#undef GF3_MAC_CASE
             default: gf3::set_error("xcorr: internal: no partition-sum kernel for %d partitions", plan->sync_parts); return GF3_ERR_INVALID;
         }
         GF3_CHECK_CUDA(cudaFuncSetAttribute(mac_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mac_smem));
     }
     for (int64_t s0 = 0; s0 < n_streams; s0 += g.tile) {
         const int64_t ns = (n_streams - s0 < g.tile) ? n_streams - s0 : g.tile;
+        float* energy = reinterpret_cast<float*>(Ysum);                               // detection only: [ns * nblk_in, kGroups], then the bounds
+        float* bound = energy + (size_t)ns * g.nblk_in * kGroups;
         int rc = run_fwd(plan, reinterpret_cast<const char*>(r) + (size_t)(s0 * r_stride) * esz, fmt, r_stride, ns, T, g.nblk_in, 0, 0, 2 * kB,
-                         spec, plan->d_sync_tw, pmax + s0, st);
+                         spec, plan->d_sync_tw, pmax + s0, st, bound_only ? energy : nullptr);
         if (rc) return rc;
         AccArgs a;
         a.spec = spec; a.H = plan->d_chirp_spec; a.tw = plan->d_sync_tw; a.P = P + s0 * p_stride; a.pmax = pmax + s0;
         a.blockmax = blockmax ? blockmax + s0 * g.nblk_out : nullptr;
         a.p_stride = p_stride; a.out_len = g.out_len; a.nblk_in = g.nblk_in; a.nblk_out = g.nblk_out; a.parts = plan->sync_parts;
         a.n_work = ns * g.nblk_out;
-        if (mac) {
+        a.bound = nullptr; a.thresh = plan->p.thresh; a.select = 0;
+        if (bound_only) {
+            // detection only (gf3_sync_detect): 1. bounds of |P| per block from the group energies the forward kernel
+            // recorded; 2. per stream, the block with the largest bound is transformed back (partition sum + inverse in
+            // xcorr_acc_kernel) and seeds pmax; 3. the same for every block that can hold a candidate, and its
+            // neighbours.  The detections are those of the full computation (tested).
+            const int64_t nb = ns * g.nblk_out;
+            int64_t bgrid = (nb + 7) / 8;
+            if (bgrid > (int64_t)plan->sm_count * 8) bgrid = (int64_t)plan->sm_count * 8;
+            xcorr_bound_kernel<<<(unsigned)bgrid, 256, 0, st>>>(energy, plan->d_chirp_energy, bound, g.nblk_in, g.nblk_out, plan->sync_parts, nb);
+            GF3_LAUNCH_CHECK();
+            a.bound = bound;
+            a.select = 1; a.n_work = ns;
+            xcorr_acc_kernel<<<(unsigned)(ns < (int64_t)plan->sm_count * GF3_XC_ACC_CTAS ? ns : (int64_t)plan->sm_count * GF3_XC_ACC_CTAS), 128, smem, st>>>(a);
+            GF3_LAUNCH_CHECK();
+            a.select = 2; a.n_work = ns * g.nblk_out;
+        } else if (mac) {
             MacArgs m;
             m.spec = spec; m.H = plan->d_chirp_spec; m.Y = Ysum; m.nblk_in = g.nblk_in; m.nblk_out = g.nblk_out;
             m.runs_per_stream = (g.nblk_out + kMacJ - 1) / kMacJ;
@@ -1360,7 +1492,9 @@ extern "C" size_t gf3_xcorr_work_bytes(const gf3_plan* plan, int64_t n_streams, 
     const XcorrGeom g = xcorr_geom(plan, n_streams, T);
     if (fused_applies(plan, n_streams, g)) return 16;                 // the fused kernel keeps its spectra on chip
     const size_t xs = (g.per_stream * (size_t)g.tile + 255) & ~(size_t)255;
-    return xs + (mac_applies(plan) ? mac_y_bytes(g) : 0);              // + the partition sums of the three-kernel form
+    const size_t ys = mac_applies(plan) ? mac_y_bytes(g) : 0;          // the partition sums of the three-kernel form, or
+    const size_t es = (size_t)g.tile * ((size_t)g.nblk_in * kGroups + (size_t)g.nblk_out) * sizeof(float);   // group energies + bounds (detection only)
+    return xs + (ys > es ? ys : es);
 }
 
 extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride, int64_t n_streams,
@@ -1396,7 +1530,7 @@ static int sync_common(const gf3_plan* plan, const void* r, int32_t sample_forma
     void* xwork = w + sync_off_blockmax(g, n_streams);
     void* pwork = reinterpret_cast<char*>(xwork) + ((gf3_xcorr_work_bytes(plan, n_streams, T) + 255) & ~(size_t)255);
     // detection only: blocks of P that provably hold no candidate are not computed (the detections are the same)
-    const bool sparse = detect_only && fused && single_pass_picker(plan, n_streams, true) && !getenv("GF3_SYNC_DENSE");
+    const bool sparse = detect_only && single_pass_picker(plan, n_streams, true) && !getenv("GF3_SYNC_DENSE");
     int* counter = reinterpret_cast<int*>(w + sync_off_blockmax(g, n_streams) - 256);
     int rc = xcorr_common(plan, r, sample_format, r_stride, n_streams, T, P, p_stride, pmax, blockmax, xwork, st, sparse, counter);
     if (rc) return rc;

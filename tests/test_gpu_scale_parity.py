@@ -183,6 +183,36 @@ def test_a2_multistream_sync_vs_oracle(known_sequence):
     assert not bad and hist == {2: 8}
 
 
+@pytest.mark.parametrize("snr_db", [0.0, 6.0, 15.0])
+def test_long_chirp_sync_detect_equals_dense(snr_db, known_sequence, monkeypatch):
+    """The N = 4096 modes' detection-only matched filter (bounds of |P| per block from the partition sums, inverse
+    transforms only where a candidate is possible) against the full computation, and that against the two-kernel form:
+    identical detections and maxima on 80 A2 streams (one noise-only, one that loses its last chirp), float32 and int16."""
+    torch = _torch()
+    from gf3b200 import synth
+    phy, p = _pair(known_sequence, N=4096, cp=224, lo=100, hi=1500, n_pilots=20, packet_len=180)
+    b = synth.make_batch(phy, 80, 1, snr_db=snr_db, seed=int(300 + snr_db), lead=777, trail=5)
+    r = b["r"]
+    r[5, -12000:] = 0.0
+    r[7] = 0.05 * torch.randn(r.shape[1], device="cuda")
+    P, pmax, peaks, count = phy.sync_streams(r, 16)
+    _, pmax2, peaks2, count2 = phy.sync_streams(r, 16, detect_only=True)
+    bad = torch.nonzero((count != count2) | (peaks != peaks2).any(dim=1) | (pmax != pmax2)).reshape(-1).tolist()
+    assert not bad, [(s_, int(count[s_]), int(count2[s_]), peaks[s_, :4].tolist(), peaks2[s_, :4].tolist(), float(pmax[s_]), float(pmax2[s_])) for s_ in bad[:6]]
+    monkeypatch.setenv("GF3_XCORR_MAC", "0")
+    _, pmax0, peaks0, count0 = phy.sync_streams(r, 16)
+    monkeypatch.delenv("GF3_XCORR_MAC", raising=False)
+    assert torch.equal(pmax0, pmax) and torch.equal(peaks0, peaks) and torch.equal(count0, count)
+    for s_ in (0, 5, 7):
+        ref = np.flatnonzero(orc.chirp_method(p, r[s_].cpu().numpy().astype(np.float64)))
+        assert np.array_equal(peaks2[s_, : int(count2[s_])].cpu().numpy(), ref[:16]), s_
+    q = torch.round(r * (20000.0 / float(r.abs().max()))).to(torch.int16)
+    _, pq, kq, cq = phy.sync_streams(q, 16)
+    _, pq2, kq2, cq2 = phy.sync_streams(q, 16, detect_only=True)
+    assert torch.equal(pq, pq2) and torch.equal(kq, kq2) and torch.equal(cq, cq2)
+    print("long-chirp sync detect %g dB: detections per stream %s" % (snr_db, sorted({int(c): int((count == c).sum()) for c in count.unique()}.items())))
+
+
 @pytest.mark.parametrize("cp,parts", [(224, 11), (704, 12), (1184, 13)])
 def test_long_chirp_partition_sum_kernel_is_bit_identical(cp, parts, known_sequence, monkeypatch):
     """The N = 4096 modes (21 600 / 24 000 / 26 400-tap chirps = 11 / 12 / 13 filter partitions): the three-kernel matched
