@@ -498,7 +498,10 @@ def run_gpu_arm(args, cfg, streams, raw, desc):
                 h_q = torch.empty(tuple(q.shape), dtype=dt).pin_memory()
                 h_q.copy_(q)
                 qf = q.to(torch.float32).contiguous() if dt != torch.float32 else None
-                hr = HostReceiver(phy, n_packets, chunk=256, sample_dtype=dt, raw_T=T if raw else None)
+                # chunks of 256 packets / streams; few long streams (a2-raw): halves, so that copies and kernels still overlap
+                # while a chunk keeps enough streams for the detection-only matched filter (>= half the SM count)
+                e_chunk = 256 if n_packets >= 1024 else max(96, (n_packets + 1) // 2)
+                hr = HostReceiver(phy, n_packets, chunk=e_chunk, sample_dtype=dt, raw_T=T if raw else None)
                 hr.run(h_q, xor=True)
                 barrier()
                 q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -589,12 +592,16 @@ def run_gpu_arm(args, cfg, streams, raw, desc):
                 xc_ms, pk_ms = seg[1], 0.0
             Tb = 4.0 * T * n_packets                                        # one pass over the streams
             parts = -(-phy.chirp_len // 2048)
-            one_kernel = parts <= 4          # longer chirps (the N = 4096 modes) take the two-kernel matched filter, which computes all of P
-            dense = args.split_sync or args.dense_sync or not one_kernel
+            one_kernel = parts <= 4          # longer chirps (the N = 4096 modes) take the multi-kernel matched filter (block spectra through a scratch array)
+            dense = args.split_sync or args.dense_sync
             kb = 2 * Tb if dense else Tb        # all of P written (4T + 4T), or detection only: every sample read once (SURVEY 8d "ideal")
-            kname = "xcorr_fused_kernel (matched filter: 4T read + 4T written per stream when all of P is computed)" if one_kernel else \
-                    "xcorr_fwd_kernel + xcorr_acc_kernel (two-kernel matched filter for %d chirp partitions: block spectra through a scratch array, all of P written)" % parts
-            roof = {"bound": "hbm", "kernel": kname + ("" if args.split_sync else " + detection walk (%s)" % ("gf3_sync_streams" if (args.dense_sync or not one_kernel) else "gf3_sync_detect: inverse transforms only where a candidate is possible")),
+            if one_kernel:
+                kname = "xcorr_fused_kernel (matched filter: 4T read + 4T written per stream when all of P is computed)"
+            elif dense:
+                kname = "xcorr_fwd_kernel + xcorr_mac_kernel + xcorr_acc_kernel (%d chirp partitions: block spectra and partition sums through scratch arrays, all of P written)" % parts
+            else:
+                kname = "xcorr_fwd_kernel (block spectra + group energies) + xcorr_bound_kernel + xcorr_acc_kernel on the blocks that can hold a candidate (%d chirp partitions)" % parts
+            roof = {"bound": "hbm", "kernel": kname + ("" if args.split_sync else " + detection walk (%s)" % ("gf3_sync_streams" if args.dense_sync else "gf3_sync_detect: inverse transforms only where a candidate is possible")),
                     "achieved": kb / (xc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "traffic": traffic if dense else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kb, "avg_launch_ms": xc_ms,
                     "note": "the matched filter is bound by FP32 issue (144 flop per sample), not by HBM; " + ("4T read + 4T of P written" if dense else "detection only: 4T read, P written only where a candidate is possible (the dense form moves 8T: frac %.3f at this duration)" % (2 * Tb / (xc_ms * 1e-3) / 1e9 / peak)),

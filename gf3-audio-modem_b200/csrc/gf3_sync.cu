@@ -91,9 +91,25 @@ __global__ void __launch_bounds__(kSyncThreads, 2) xcorr_fwd_kernel(const FwdArg
         const int64_t s0 = (int64_t)b * kB - kB + a.in_off;
         const bool fast = sizeof(S) == 4 && live && !a.reverse && s0 >= 0 && s0 + 2 * kB <= a.T && a.valid_len >= 2 * kB &&
                           ((reinterpret_cast<uintptr_t>(row + s0) & 7) == 0);
+        const bool fast_pcm = sizeof(S) < 4 && live && !a.reverse && s0 >= 0 && s0 + 2 * kB <= a.T && a.valid_len >= 2 * kB &&
+                              ((reinterpret_cast<uintptr_t>(row + s0) & (2 * sizeof(S) - 1)) == 0);
         if (fast) {      // interior block, 8-byte aligned: vector loads without bounds checks
 #pragma unroll
             for (int i = 0; i < R; ++i) x[i] = __ldg(reinterpret_cast<const float2*>(row + s0) + (t + i * T));
+        } else if (fast_pcm) {      // PCM as recorded: one 32- / 16-bit load per sample pair
+            if constexpr (sizeof(S) == 2) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const short2 v = __ldg(reinterpret_cast<const short2*>(row + s0) + (t + i * T));
+                    x[i] = make_float2((float)v.x, (float)v.y);
+                }
+            } else if constexpr (sizeof(S) == 1) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(row + s0) + (t + i * T));
+                    x[i] = make_float2((float)v.x, (float)v.y);
+                }
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < R; ++i) {
