@@ -211,6 +211,15 @@ def test_long_chirp_sync_detect_equals_dense(snr_db, known_sequence, monkeypatch
     _, pq2, kq2, cq2 = phy.sync_streams(q, 16, detect_only=True)
     assert torch.equal(pq, pq2) and torch.equal(kq, kq2) and torch.equal(cq, cq2)
     print("long-chirp sync detect %g dB: detections per stream %s" % (snr_db, sorted({int(c): int((count == c).sum()) for c in count.unique()}.items())))
+    # short and ragged streams (fewer blocks than partitions, streams shorter than the chirp), many candidates
+    g = torch.Generator(device="cuda").manual_seed(int(snr_db) + 1)
+    for B, T in ((100, 5003), (90, 30011), (75, 2048 * 14)):
+        rs = torch.randn((B, T), generator=g, device="cuda", dtype=torch.float32)
+        if T > 25000:
+            rs[::2, 1500:1500 + phy.chirp_len] += 2.0 * phy.sync_chirp()
+        _, m1, k1, c1 = phy.sync_streams(rs, 16)
+        _, m2, k2, c2 = phy.sync_streams(rs, 16, detect_only=True)
+        assert torch.equal(m1, m2) and torch.equal(k1, k2) and torch.equal(c1, c2), (B, T)
 
 
 @pytest.mark.parametrize("cp,parts", [(224, 11), (704, 12), (1184, 13)])
