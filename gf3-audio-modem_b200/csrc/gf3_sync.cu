@@ -685,6 +685,46 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
         }
     };
 
+    // ---- detection only: group energies.  The 32 bins k = t + 128 q a warp owns in slot q form a group, their mirror
+    // images M - k another (two contiguous runs of the spectrum; mixing them would pair the chirp band with bins the
+    // chirp does not reach and cost the bound a factor sqrt 2).  With the weights of the inverse real transform (2 per
+    // bin; DC and Nyquist are carried separately)
+    //   sum_{k in group} 2 |X[k]| |H[k]| <= sqrt(sum 2 |X[k]|^2) sqrt(sum 2 |H[k]|^2)          (Cauchy-Schwarz),
+    // so a few square roots per block bound |y[n]| <= sum_k w_k |Y[k]|, Y = sum_p X_{b-p} H_p, BEFORE any partition
+    // product is formed.  warp_slots16: 16 per-thread values summed over the warp by a halving exchange (16 shuffles);
+    // every lane returns the total of slot lane >> 1 (0..7: bins k of slot q, 8..15: bins M - k).
+    auto warp_slots16 = [&](float (&v)[2 * Q]) -> float {
+        const int lane = tid & 31;
+#pragma unroll
+        for (int h = 8; h >= 1; h >>= 1) {
+            const bool up = (lane & (2 * h)) != 0;
+#pragma unroll
+            for (int i = 0; i < h; ++i) {
+                const float give = up ? v[i] : v[i + h];
+                const float got = __shfl_xor_sync(0xffffffffu, give, 2 * h);
+                v[i] = (up ? v[i + h] : v[i]) + got;
+            }
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        return v[0];
+    };
+    float hs[PARTS];                                       // sqrt of the group energy of partition p, this lane's slot
+    float hist[PARTS];                                     // the same of the input blocks b-1, b-2, ... ([0] unused)
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) hs[p] = hist[p] = 0.f;
+    if (a.sparse) {
+#pragma unroll
+        for (int p = 0; p < PARTS; ++p) {
+            float e[2 * Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float4 h = __ldg(a.Hs + ((size_t)p * Q + q) * NT + tid);
+                e[q] = 2.f * fmaf(h.x, h.x, h.z * h.z);
+                e[Q + q] = (q == 0 && tid == 0) ? 0.f : 2.f * fmaf(h.y, h.y, h.w * h.w);     // k = M/2 sits in both lanes of its slot: once
+            }
+            hs[p] = sqrtf(warp_slots16(e));
+        }
+    }
     __syncthreads();                                       // twiddles staged
     int64_t cur_stream = -1;
     float2 x[R];
@@ -700,7 +740,7 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
     // 88 % at 20 dB and 83 % at 8 dB on the C3 framing, none below ~5 dB).
     float runmax = __int_as_float(0xff800000);
     bool prev_hotish = true, prev_skipped = false;
-    __shared__ float wl1[NT / 32];
+    __shared__ float wl1[NT / 32], wl2[NT / 32];       // partial bounds of the two tests (separate: no barrier between them)
     // Work distribution.  Dense: one contiguous, equally sized range of blocks per CTA (uniform cost).  Sparse: the
     // cost of a block depends on the data, and the skip rule needs the stream's chirp peak, which lies at the stream's
     // beginning -- so CTAs take WHOLE streams from a global counter (dynamic: a CTA whose streams cannot skip much
@@ -733,6 +773,8 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
             runmax = __int_as_float(0xff800000);
             prev_hotish = true;
             prev_skipped = false;
+#pragma unroll
+            for (int p = 0; p < PARTS; ++p) hist[p] = 0.f;
             ring_zero();
             if constexpr (R1 > 0) {
 #pragma unroll 1
@@ -764,6 +806,51 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
             load_block(x, stream, b + 1, std::true_type{});
         }
 
+        float* Prow = a.P + stream * a.p_stride;
+        const int64_t n0 = (int64_t)b * kB - kB;
+        if (a.sparse) {
+            // bound of |y[n]| over the block from the group energies (see above); the partition sums, the inverse FFT
+            // and the stores are skipped when it stays below thresh * (largest sample of the stream so far)
+            float e[2 * Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float2 m2 = pk_unpack(p_fma(xre[q], xre[q], p_mul(xim[q], xim[q])));
+                e[q] = 2.f * m2.x;
+                e[Q + q] = (q == 0 && tid == 0) ? 0.f : 2.f * m2.y;
+            }
+            const float eb = sqrtf(warp_slots16(e));
+            float part = eb * hs[0];
+#pragma unroll
+            for (int p = 1; p < PARTS; ++p) part = fmaf(hist[p], hs[p], part);
+            if ((tid & 1) != 0) part = 0.f;                                  // two lanes hold every slot
+            if (tid == 0) {
+                const float2 h0 = __ldg(a.Hdc);
+                part += fabsf(dcny.x * h0.x) + fabsf(dcny.y * h0.y);
+#pragma unroll
+                for (int p = 1; p <= R1; ++p) {
+                    const float2 xv = ring_dc[((b - p) % R1 + R1) % R1], hp = __ldg(a.Hdc + p);
+                    part += fabsf(xv.x * hp.x) + fabsf(xv.y * hp.y);
+                }
+            }
+#pragma unroll
+            for (int p = PARTS - 1; p >= 2; --p) hist[p] = hist[p - 1];
+            if constexpr (PARTS > 1) hist[1] = eb;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if ((tid & 31) == 0) wl1[tid >> 5] = part;
+            __syncthreads();
+            float bound = wl1[0];
+#pragma unroll
+            for (int w = 1; w < NT / 32; ++w) bound += wl1[w];
+            const bool forced = c == c_lo || c + 1 == c_hi || prev_hotish;
+            if (!forced && bound * 1.001f < a.thresh * runmax) {             // (runmax = -inf or <= 0: never true)
+                if constexpr (R1 > 0) ring_store(b % R1, xre, xim, dcny);
+                if (tid == 0 && a.blockmax) a.blockmax[stream * a.nblk_out + b] = __int_as_float(0xff800000);
+                prev_hotish = false;
+                prev_skipped = true;
+                continue;
+            }
+        }
         // ---- Y_b = sum_p X_{b-p} H_p   (re = pos - neg; all four products are plain FFMA2)
         pk64 arp[Q], arn[Q], ai[Q];
         float dc, ny;
@@ -808,10 +895,9 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
         // Y of the thread's pairs
 #pragma unroll
         for (int q = 0; q < Q; ++q) arp[q] = p_sub(arp[q], arn[q]);
-        float* Prow = a.P + stream * a.p_stride;
-        const int64_t n0 = (int64_t)b * kB - kB;
         if (a.sparse) {
-            // l1 norm of the block's spectrum, sum_k |Y[k]| (bins 1..N/2-1 count twice: Hermitian halves).  |Y| by
+            // second level, for the blocks the energy bound let through: the l1 norm of the block's spectrum itself,
+            // sum_k |Y[k]| (bins 1..N/2-1 count twice: Hermitian halves).  |Y| by
             // rsqrt (relative error 2^-22, covered by the 1.001 slack of the comparison below)
             float l1 = 0.f;
 #pragma unroll
@@ -825,12 +911,12 @@ __global__ void __launch_bounds__(128, MINB) xcorr_fused_kernel(const FusedArgs 
             if (tid == 0) l1 += fabsf(dc) + fabsf(ny);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, o);
-            if ((tid & 31) == 0) wl1[tid >> 5] = l1;
+            if ((tid & 31) == 0) wl2[tid >> 5] = l1;
             __syncthreads();
-            float bound = wl1[0];
+            float bound = wl2[0];
 #pragma unroll
-            for (int w = 1; w < NT / 32; ++w) bound += wl1[w];
-            const bool forced = c == c_lo || c + 1 == c_hi || prev_hotish;
+            for (int w = 1; w < NT / 32; ++w) bound += wl2[w];
+            const bool forced = c == c_lo || c + 1 == c_hi || prev_hotish;      // (as above)
             if (!forced && bound * 1.001f < a.thresh * runmax) {             // (runmax = -inf or <= 0: never true)
                 if (tid == 0 && a.blockmax) a.blockmax[stream * a.nblk_out + b] = __int_as_float(0xff800000);
                 prev_hotish = false;
