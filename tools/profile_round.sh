@@ -4,8 +4,10 @@
 TAG=${1:-rXX}
 O=gpurun_out
 set -x
+timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider 2>&1 | tail -3
 python bench.py > $O/${TAG}_bench_c3.json 2> $O/${TAG}_bench.err
 python bench.py --workload c3-raw --steps 20 > $O/${TAG}_bench_c3raw.json 2>> $O/${TAG}_bench.err
+python bench.py --workload a2-raw --steps 20 > $O/${TAG}_bench_a2raw.json 2>> $O/${TAG}_bench.err
 python bench.py --workload c4 --no-cpu > $O/${TAG}_bench_c4.json 2>> $O/${TAG}_bench.err
 python bench.py --workload c4-long --no-cpu > $O/${TAG}_bench_c4long.json 2>> $O/${TAG}_bench.err
 python bench.py --workload a2 --no-cpu > $O/${TAG}_bench_a2.json 2>> $O/${TAG}_bench.err
