@@ -44,6 +44,10 @@ constexpr int kThreads = 256;
 #ifndef GF3_PREFETCH_PART
 #define GF3_PREFETCH_PART 16   // GF3_PREFETCH == 3: registers (complex points) of the next batch requested ahead
 #endif
+#ifndef GF3_WHOLE_PACKETS
+#define GF3_WHOLE_PACKETS 0    // 1: CTA ranges on packet boundaries in the fused kernel (no packet estimated twice): C3 0.976 vs 0.981 ms in
+#endif                         // one run, 1.035 in the next -- every CTA then sits in the same phase of its packet at the same time
+
 #ifndef GF3_EST_U
 #define GF3_EST_U 20
 #endif
@@ -511,8 +515,17 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
     // on how the chunks are spread over CTAs.
     const int cpp = a.chunks_per_packet;
     const int64_t total_chunks = a.n_packets * cpp;
-    const int64_t c_begin = total_chunks * blockIdx.x / gridDim.x;
-    const int64_t c_end = total_chunks * (blockIdx.x + 1) / gridDim.x;
+    int64_t c_begin = total_chunks * blockIdx.x / gridDim.x;
+    int64_t c_end = total_chunks * (blockIdx.x + 1) / gridDim.x;
+#if GF3_WHOLE_PACKETS
+    // experiment (off): ranges on packet boundaries, so that no packet's estimate is computed by two CTAs.  The chunk
+    // ranges above stagger the CTAs' positions inside their packets, which decorrelates the load / FFT / estimate phases
+    // of the CTAs sharing an SM; that is worth more than the 592 estimates saved
+    if (FUSE_EST && a.n_packets >= 4 * (int64_t)gridDim.x) {
+        c_begin = (a.n_packets * blockIdx.x / gridDim.x) * cpp;
+        c_end = (a.n_packets * (blockIdx.x + 1) / gridDim.x) * cpp;
+    }
+#endif
     int64_t cur_pkt = -1;
     const S* const samples = reinterpret_cast<const S*>(a.samples);
     const S* pkt_base = nullptr;

@@ -203,6 +203,13 @@ def test_long_chirp_sync_detect_equals_dense(snr_db, known_sequence, monkeypatch
     _, pmax0, peaks0, count0 = phy.sync_streams(r, 16)
     monkeypatch.delenv("GF3_XCORR_MAC", raising=False)
     assert torch.equal(pmax0, pmax) and torch.equal(peaks0, peaks) and torch.equal(count0, count)
+    # streams processed in tiles of five (scratch capped at 40 MB): the same, dense and detection only
+    monkeypatch.setenv("GF3_XC_TILE_MB", "40")
+    _, pmax3, peaks3, count3 = phy.sync_streams(r, 16)
+    _, pmax4, peaks4, count4 = phy.sync_streams(r, 16, detect_only=True)
+    monkeypatch.delenv("GF3_XC_TILE_MB", raising=False)
+    assert torch.equal(pmax3, pmax) and torch.equal(peaks3, peaks) and torch.equal(count3, count)
+    assert torch.equal(pmax4, pmax) and torch.equal(peaks4, peaks) and torch.equal(count4, count)
     for s_ in (0, 5, 7):
         ref = np.flatnonzero(orc.chirp_method(p, r[s_].cpu().numpy().astype(np.float64)))
         assert np.array_equal(peaks2[s_, : int(count2[s_])].cpu().numpy(), ref[:16]), s_
