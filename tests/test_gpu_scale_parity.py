@@ -170,6 +170,13 @@ def test_sync_detect_equals_dense_across_snr(snr_db, known_sequence):
     _, pq2, kq2, cq2 = phy.sync_streams(q, 16, detect_only=True)
     assert torch.equal(pq, pq2) and torch.equal(kq, kq2) and torch.equal(cq, cq2)
     print("sync detect %g dB: detections per stream %s" % (snr_db, sorted({int(c): int((count == c).sum()) for c in count.unique()}.items())))
+    # short streams: too few blocks per CTA for the fused kernel, so the multi-kernel form (group energies from the forward
+    # kernel, selective inverse passes) serves three partitions too
+    for B2, T2 in ((100, 20011), (80, 6000)):
+        rs = r[:B2, :T2].contiguous()
+        _, m1, k1, c1 = phy.sync_streams(rs, 16)
+        _, m2, k2, c2 = phy.sync_streams(rs, 16, detect_only=True)
+        assert torch.equal(m1, m2) and torch.equal(k1, k2) and torch.equal(c1, c2), (B2, T2)
 
 
 def test_a2_multistream_sync_vs_oracle(known_sequence):
