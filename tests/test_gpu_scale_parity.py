@@ -261,6 +261,36 @@ def test_long_chirp_partition_sum_kernel_is_bit_identical(cp, parts, known_seque
         assert np.max(np.abs(P1[0].double().cpu().numpy() - ref)) / np.max(np.abs(ref)) < 5e-6
 
 
+@pytest.mark.parametrize("chirp_len,parts", [(8200, 5), (12000, 6), (20000, 10)])
+def test_mid_length_chirps_through_the_partition_sum_kernel(chirp_len, parts, known_sequence, monkeypatch):
+    """Chirp lengths between the fused kernel's four partitions and the N = 4096 modes' eleven (gf3_params.chirp_len is
+    a free parameter): the partition-sum kernel's other instantiations against the two-kernel form (bit-identical P),
+    against a float64 convolution, and detection only against the full computation."""
+    torch = _torch()
+    import gf3b200
+    from scipy.signal import fftconvolve
+    phy = gf3b200.Phy(N=1024, cp=32, lo=1, hi=512, n_pilots=2, packet_len=4, known_sequence=known_sequence, chirp_len=chirp_len)
+    assert -(-phy.chirp_len // 2048) == parts
+    c = phy.sync_chirp()
+    g = torch.Generator(device="cuda").manual_seed(chirp_len)
+    r = torch.randn((3, 50021), generator=g, device="cuda", dtype=torch.float32)
+    r[:, 700:700 + chirp_len] += 2.0 * c
+    P1, m1 = phy.xcorr(r)
+    monkeypatch.setenv("GF3_XCORR_MAC", "0")
+    P0, m0 = phy.xcorr(r)
+    monkeypatch.delenv("GF3_XCORR_MAC", raising=False)
+    assert torch.equal(P0, P1) and torch.equal(m0, m1)
+    ref = fftconvolve(r[1].double().cpu().numpy(), c.double().cpu().numpy()[::-1])
+    assert np.max(np.abs(P1[1].double().cpu().numpy() - ref)) / np.max(np.abs(ref)) < 5e-6
+    rs = torch.randn((80, 30011), generator=g, device="cuda", dtype=torch.float32)
+    rs[::3, 1500:1500 + chirp_len] += 1.5 * c
+    rs[1::3, 5000:5000 + chirp_len] += 0.8 * c
+    _, ma, ka, ca = phy.sync_streams(rs, 16)
+    _, mb, kb, cb = phy.sync_streams(rs, 16, detect_only=True)
+    assert torch.equal(ma, mb) and torch.equal(ka, kb) and torch.equal(ca, cb)
+    assert int(ca.max()) >= 1
+
+
 # ----------------------------------------------------------------------------- KAT-4 (BASELINE.json configs[1])
 def test_kat4_gr5ch2_dropin_receive(known_sequence, capsys):
     """configs[1]: chirp-synchronised decode of a long recording (29 packets, 28.2 M samples, int16) with
