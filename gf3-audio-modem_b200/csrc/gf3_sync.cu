@@ -212,7 +212,10 @@ struct AccArgs {
     const float* bound;      // detection only: [n_streams, nblk_out] upper bound of |P| in every block (xcorr_mac_kernel<.., true>), else null
     float thresh;            // detection threshold (OFDM.py:361)
     int select;              // 0: every block; 1: per stream, the block with the largest bound (n_work = n_streams);
-                             // 2: the blocks that can hold a candidate, and their neighbours (see the kernel)
+                             // 2: the blocks that can hold a candidate, and their neighbours (see the kernel);
+                             // 3: the blocks listed in sel_idx[0 .. *sel_count) (xcorr_select_kernel)
+    const int* sel_idx;
+    const int* sel_count;
     int64_t p_stride, out_len;   // out_len = T + Lc - 1
     int nblk_in, nblk_out, parts;
     int64_t n_work;          // n_streams * nblk_out
@@ -248,9 +251,11 @@ __global__ void __launch_bounds__(128, 4) xcorr_acc_kernel(const AccArgs a) {
     // persistent: the twiddle table is staged once per CTA; co-resident CTAs work on neighbouring
     // blocks, so the chirp-partition spectra and the shared input spectra stay hot in L2
     __shared__ int s_sel;
-    for (int64_t work = blockIdx.x; work < a.n_work; work += gridDim.x) {
-        int64_t stream = work / a.nblk_out;
-        int b = (int)(work - stream * a.nblk_out);
+    const int64_t n_work = a.select == 3 ? (int64_t)__ldg(a.sel_count) : a.n_work;
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
+        const int64_t item = a.select == 3 ? (int64_t)__ldg(a.sel_idx + work) : work;
+        int64_t stream = item / a.nblk_out;
+        int b = (int)(item - stream * a.nblk_out);
         if (a.select == 1) {
             // the block with the largest bound very likely holds the chirp peak: its maximum seeds pmax[stream], the
             // lower bound of max(P) that the selection of pass 2 needs
@@ -403,6 +408,7 @@ struct MacArgs {
     int nblk_in, nblk_out;
     int runs_per_stream;     // ceil(nblk_out / J)
     int64_t n_units;         // n_streams * runs_per_stream
+    const uint8_t* run_sel;  // optional [n_units]: only the runs flagged here are computed (detection only)
 };
 
 // The (input block, output) pairs of a run form a fixed band (output j takes input b0 + j - p, p < PARTS): with PARTS a
@@ -437,6 +443,7 @@ __global__ void __launch_bounds__(kMacThreads, 1) xcorr_mac_kernel(const MacArgs
     auto run = [&](auto nyc) {
         constexpr bool NY = decltype(nyc)::value;
         for (int64_t unit = blockIdx.x; unit < a.n_units; unit += gridDim.x) {      // (contiguous ranges per CTA: no faster, 1.25 vs 1.21 ms)
+            if (a.run_sel && !a.run_sel[unit]) continue;                              // (uniform over the CTA)
             const int64_t stream = unit / a.runs_per_stream;
             const int b0 = (int)(unit - stream * a.runs_per_stream) * J;
             float2 acc[J][NB];
@@ -524,6 +531,31 @@ __global__ void __launch_bounds__(256) xcorr_bound_kernel(const float* __restric
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if (lane == 0) bound[blk] = sum * (1.0f / (float)SP::N);
+    }
+}
+
+// Detection only, after pmax[stream] has been seeded with the maximum of the stream's most promising block: the list of
+// blocks that are transformed back.  |P| <= bound inside a block and a candidate needs P > thresh * max(P) >= thresh *
+// pmax, so a block whose bound passes that test -- every block that really holds a candidate or the maximum does -- is
+// listed together with both its neighbours (the detection rule reads one sample either side of a candidate); so are
+// the first and the last block of a stream.  All other blocks get block maximum -inf.  run_sel flags the runs of
+// kMacJ blocks that hold a listed block (for the partition-sum kernel).
+__global__ void __launch_bounds__(256) xcorr_select_kernel(const float* __restrict__ bound, const float* __restrict__ pmax, float thresh,
+                                                           int nblk_out, int runs_per_stream, int64_t n_blocks, float* __restrict__ blockmax,
+                                                           int* __restrict__ sel_idx, int* __restrict__ sel_count, uint8_t* __restrict__ run_sel) {
+    const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= n_blocks) return;
+    const int64_t stream = blk / nblk_out;
+    const int b = (int)(blk - stream * nblk_out);
+    const float* bd = bound + stream * nblk_out;
+    const float lim = thresh * pmax[stream];
+    bool go = b == 0 || b == nblk_out - 1 || !(lim > 0.f);
+    for (int i = (b > 0 ? b - 1 : 0); i <= b + 1 && i < nblk_out; ++i) go = go || bd[i] * 1.001f >= lim;
+    if (go) {
+        sel_idx[atomicAdd(sel_count, 1)] = (int)blk;
+        run_sel[stream * runs_per_stream + b / kMacJ] = 1;
+    } else {
+        blockmax[blk] = __int_as_float(0xff800000);
     }
 }
 
@@ -1409,7 +1441,13 @@ static bool mac_applies(const gf3_plan* plan) {
     if (const char* e = getenv("GF3_XCORR_MAC")) return atoi(e) != 0 && can;
     return can;
 }
-static size_t mac_y_bytes(const XcorrGeom& g) { return (size_t)g.tile * (size_t)g.nblk_out * SP::M * sizeof(float2); }
+static size_t mac_y_bytes(const XcorrGeom& g) { return (((size_t)g.tile * (size_t)g.nblk_out * SP::M * sizeof(float2)) + 255) & ~(size_t)255; }
+// detection only: group energies [tile * nblk_in, kGroups] | bounds [tile * nblk_out] | listed blocks [tile * nblk_out] |
+// their count (256 B) | run flags [tile * ceil(nblk_out / kMacJ)]
+static size_t detect_scratch_bytes(const XcorrGeom& g) {
+    const size_t nb = (size_t)g.tile * g.nblk_out, runs = (size_t)g.tile * ((g.nblk_out + kMacJ - 1) / kMacJ);
+    return (size_t)g.tile * g.nblk_in * kGroups * sizeof(float) + nb * sizeof(float) + nb * sizeof(int) + 256 + ((runs + 255) & ~(size_t)255);
+}
 
 static bool fused_applies(const gf3_plan* plan, int64_t n_streams, const XcorrGeom& g) {
     if (plan->sync_parts > GF3_XC_FUSED_MAX_PARTS) return false;
@@ -1504,8 +1542,12 @@ static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_
     }
     for (int64_t s0 = 0; s0 < n_streams; s0 += g.tile) {
         const int64_t ns = (n_streams - s0 < g.tile) ? n_streams - s0 : g.tile;
-        float* energy = reinterpret_cast<float*>(Ysum);                               // detection only: [ns * nblk_in, kGroups], then the bounds
+        // detection only: group energies, bounds, listed blocks, their count, run flags (detect_scratch_bytes)
+        float* energy = reinterpret_cast<float*>(reinterpret_cast<char*>(Ysum) + (mac ? mac_y_bytes(g) : 0));
         float* bound = energy + (size_t)ns * g.nblk_in * kGroups;
+        int* sel_idx = reinterpret_cast<int*>(bound + (size_t)ns * g.nblk_out);
+        int* sel_count = sel_idx + (size_t)ns * g.nblk_out;
+        uint8_t* run_sel = reinterpret_cast<uint8_t*>(sel_count) + 256;
         int rc = run_fwd(plan, reinterpret_cast<const char*>(r) + (size_t)(s0 * r_stride) * esz, fmt, r_stride, ns, T, g.nblk_in, 0, 0, 2 * kB,
                          spec, plan->d_sync_tw, pmax + s0, st, bound_only ? energy : nullptr);
         if (rc) return rc;
@@ -1514,7 +1556,7 @@ static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_
         a.blockmax = blockmax ? blockmax + s0 * g.nblk_out : nullptr;
         a.p_stride = p_stride; a.out_len = g.out_len; a.nblk_in = g.nblk_in; a.nblk_out = g.nblk_out; a.parts = plan->sync_parts;
         a.n_work = ns * g.nblk_out;
-        a.bound = nullptr; a.thresh = plan->p.thresh; a.select = 0;
+        a.bound = nullptr; a.thresh = plan->p.thresh; a.select = 0; a.sel_idx = nullptr; a.sel_count = nullptr;
         if (bound_only) {
             // detection only (gf3_sync_detect): 1. bounds of |P| per block from the group energies the forward kernel
             // recorded; 2. per stream, the block with the largest bound is transformed back (partition sum + inverse in
@@ -1530,11 +1572,28 @@ static int xcorr_common(const gf3_plan* plan, const void* r, int fmt, int64_t r_
             xcorr_acc_kernel<<<(unsigned)(ns < (int64_t)plan->sm_count * GF3_XC_ACC_CTAS ? ns : (int64_t)plan->sm_count * GF3_XC_ACC_CTAS), 128, smem, st>>>(a);
             GF3_LAUNCH_CHECK();
             a.select = 2; a.n_work = ns * g.nblk_out;
+            if (mac) {
+                // long chirps: the listed blocks go through the partition-sum kernel (runs that hold one) and the inverse
+                // stage with the unit partition, as in the full computation -- the same P, a third of the time per block
+                const int runs = (g.nblk_out + kMacJ - 1) / kMacJ;
+                GF3_CHECK_CUDA(cudaMemsetAsync(sel_count, 0, 256 + (size_t)ns * runs, st));
+                xcorr_select_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(bound, a.pmax, a.thresh, g.nblk_out, runs, nb, a.blockmax,
+                                                                                 sel_idx, sel_count, run_sel);
+                GF3_LAUNCH_CHECK();
+                MacArgs m;
+                m.spec = spec; m.H = plan->d_chirp_spec; m.Y = Ysum; m.nblk_in = g.nblk_in; m.nblk_out = g.nblk_out;
+                m.runs_per_stream = runs; m.n_units = ns * runs; m.run_sel = run_sel;
+                const int64_t mg = m.n_units < plan->sm_count ? m.n_units : plan->sm_count;
+                mac_kern<<<(unsigned)mg, kMacThreads, mac_smem, st>>>(m);
+                GF3_LAUNCH_CHECK();
+                a.spec = Ysum; a.H = plan->d_chirp_one; a.nblk_in = g.nblk_out; a.parts = 1;
+                a.select = 3; a.sel_idx = sel_idx; a.sel_count = sel_count;
+            }
         } else if (mac) {
             MacArgs m;
             m.spec = spec; m.H = plan->d_chirp_spec; m.Y = Ysum; m.nblk_in = g.nblk_in; m.nblk_out = g.nblk_out;
             m.runs_per_stream = (g.nblk_out + kMacJ - 1) / kMacJ;
-            m.n_units = ns * m.runs_per_stream;
+            m.n_units = ns * m.runs_per_stream; m.run_sel = nullptr;
             int64_t mg = m.n_units < plan->sm_count ? m.n_units : plan->sm_count;          // one CTA per SM: the partitions fill its shared memory
             mac_kern<<<(unsigned)mg, kMacThreads, mac_smem, st>>>(m);
             GF3_LAUNCH_CHECK();
@@ -1594,9 +1653,7 @@ extern "C" size_t gf3_xcorr_work_bytes(const gf3_plan* plan, int64_t n_streams, 
     const XcorrGeom g = xcorr_geom(plan, n_streams, T);
     if (fused_applies(plan, n_streams, g)) return 16;                 // the fused kernel keeps its spectra on chip
     const size_t xs = (g.per_stream * (size_t)g.tile + 255) & ~(size_t)255;
-    const size_t ys = mac_applies(plan) ? mac_y_bytes(g) : 0;          // the partition sums of the three-kernel form, or
-    const size_t es = (size_t)g.tile * ((size_t)g.nblk_in * kGroups + (size_t)g.nblk_out) * sizeof(float);   // group energies + bounds (detection only)
-    return xs + (ys > es ? ys : es);
+    return xs + (mac_applies(plan) ? mac_y_bytes(g) : 0) + detect_scratch_bytes(g);
 }
 
 extern "C" int gf3_xcorr(const gf3_plan* plan, const float* r, int64_t r_stride, int64_t n_streams,
