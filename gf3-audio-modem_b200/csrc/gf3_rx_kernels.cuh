@@ -55,7 +55,7 @@ constexpr int kThreads = 256;
 #define GF3_FUSE_SEQUENTIAL 0      // 1: fuse the estimate at N = 4096 too (pilot blocks one after the other)
 #endif
 #ifndef GF3_FLUSH_UNROLL
-#define GF3_FLUSH_UNROLL 2
+#define GF3_FLUSH_UNROLL 0     // 0: per plan (4 words per step at N <= 1024: C3 0.978 vs 0.981 ms; 2 above: A2 0.684 vs 0.687)
 #endif
 #ifndef GF3_DMASK_ONCE
 #define GF3_DMASK_ONCE (-1)    // data-carrier mask of a thread's bins: 1 once per CTA, 0 per batch, -1 per-plan default
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(NT, MINB) rx_demod_kernel(const RxArgs a) {
                     const uint32_t t0 = v.x * 0x40100401u, t1 = v.y * 0x40100401u, t2 = v.z * 0x40100401u, t3 = v.w * 0x40100401u;
                     return __byte_perm(__byte_perm(t0, t1, 0x0073), __byte_perm(t2, t3, 0x0073), 0x5410);
                 };
-                constexpr int FU = GF3_FLUSH_UNROLL;
+                constexpr int FU = GF3_FLUSH_UNROLL > 0 ? GF3_FLUSH_UNROLL : (P::LOGN <= 10 ? 4 : 2);   // re-swept on the final kernel (r02ay / r02az)
                 if (use_xor) {
 #pragma unroll FU
                     for (int w = tid; w < nfull; w += NT) out[w] = pack16(w) ^ xorw[w];
